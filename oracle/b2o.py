@@ -1,0 +1,168 @@
+"""ctypes wrapper of the CPU oracle (oracle/libb2o.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never by robovat_b200.  Mirrors the b2s_* C-ABI
+with host pointers; arrays come back as numpy views of the oracle's own storage.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from robovat_b200 import _capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libb2o.so')
+
+BUF_IDS = {'body_state': 100, 'joint_state': 101, 'action': 102, 'obs_position': 103,
+           'num_movables': 104, 'body_mask': 105, 'depth': 106, 'segmask': 107, 'point_cloud': 108,
+           'reward': 109, 'termination': 110, 'is_safe': 111, 'is_effective': 112, 'episode_return': 113}
+DTYPES = {
+    _capi.ARR_MANIFOLD_KEYS: np.int32, _capi.ARR_MANIFOLD_NPTS: np.int32, _capi.ARR_MANIFOLD_PTS: np.float32,
+    _capi.ARR_NUM_MANIFOLDS: np.int32, _capi.ARR_PAIR_KEYS: np.int32, _capi.ARR_NUM_PAIRS: np.int32,
+    _capi.ARR_PHASE: np.int32, _capi.ARR_NUM_STEPS: np.int32, _capi.ARR_CTRL: np.float32,
+    _capi.ARR_CTRL_FLAGS: np.int32, _capi.ARR_LINK_POSES: np.float32, _capi.ARR_MOV_PARAMS: np.float32,
+    _capi.ARR_TABLE_DZ: np.float32, _capi.ARR_ERROR_FLAGS: np.int32, _capi.ARR_WAYPOINTS: np.float32,
+    _capi.ARR_STATUS: np.float32, _capi.ARR_CONTACT_FLAGS: np.int32, _capi.ARR_PHASE_STATE: np.int32,
+    _capi.ARR_SOLVER_STATS: np.int32, _capi.ARR_CTRL_TIME: np.float64, _capi.ARR_LINK_VEL: np.float32,
+    _capi.ARR_NUM_COLLIDERS: np.int32, _capi.ARR_COL_SLOT: np.int32, _capi.ARR_COL_HULL: np.int32,
+    100: np.float32, 101: np.float32, 102: np.float32, 103: np.float32, 104: np.int32, 105: np.uint8,
+    106: np.float32, 107: np.uint8, 108: np.float32, 109: np.float32, 110: np.uint8, 111: np.uint8,
+    112: np.uint8, 113: np.float32,
+}
+_lib = None
+
+
+def build():
+    subprocess.check_call(['make', '-s', '-C', HERE])
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.b2o_last_error.restype = C.c_char_p
+        _lib.b2o_substeps_executed.restype = C.c_int64
+    return _lib
+
+
+class OracleWorld(object):
+    def __init__(self, params, scene, threads=1):
+        self.lib = load()
+        self.params = params
+        self.scene = scene
+        self.h = C.c_void_p()
+        self._chk(self.lib.b2o_create(C.byref(params), C.byref(self.h)))
+        self._chk(self.lib.b2o_load_scene(self.h, C.byref(scene.desc)))
+        self.lib.b2o_set_threads(int(threads))
+        self.B, self.N = params.num_envs, params.max_movables
+
+    def _chk(self, code):
+        if code != 0:
+            raise RuntimeError('oracle error %d: %s' % (code, self.lib.b2o_last_error()))
+
+    def close(self):
+        if self.h:
+            self.lib.b2o_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def array(self, which):
+        if isinstance(which, str):
+            which = BUF_IDS[which]
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._chk(self.lib.b2o_array(self.h, which, C.byref(ptr), C.byref(nbytes)))
+        dt = np.dtype(DTYPES[which])
+        n = nbytes.value // dt.itemsize
+        if n == 0:
+            return np.zeros(0, dtype=dt)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,))
+
+    # views with the documented shapes
+    @property
+    def body_state(self):
+        return self.array('body_state').reshape(13, self.B, self.N)
+
+    @property
+    def joint_state(self):
+        return self.array('joint_state').reshape(2, 7, self.B)
+
+    def set_threads(self, n):
+        self.lib.b2o_set_threads(int(n))
+
+    def reset(self, seed=0, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
+        self._chk(self.lib.b2o_reset(self.h, m, C.c_uint64(seed)))
+
+    def settle(self, lin=0.005, ang=0.005, max_steps=2000):
+        self._chk(self.lib.b2o_settle(self.h, C.c_float(lin), C.c_float(ang), int(max_steps)))
+
+    def step(self, n=1):
+        self._chk(self.lib.b2o_step(self.h, int(n)))
+
+    def set_action(self, action):
+        self.array('action')[:] = np.asarray(action, np.float32).ravel()
+        self._chk(self.lib.b2o_set_action(self.h))
+
+    def env_substeps(self, n):
+        u = C.c_int()
+        self._chk(self.lib.b2o_env_substeps(self.h, int(n), C.byref(u)))
+        return u.value
+
+    def move_to_gripper_pose(self, pose, mask=None):
+        p = np.ascontiguousarray(pose, np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
+        self._chk(self.lib.b2o_arm_move_to_gripper_pose(self.h, p.ctypes.data_as(C.c_void_p), m))
+
+    def move_to_joint_positions(self, q, mask=None):
+        p = np.ascontiguousarray(q, np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
+        self._chk(self.lib.b2o_arm_move_to_joint_positions(self.h, p.ctypes.data_as(C.c_void_p), m))
+
+    def arm_is_ready(self):
+        out = np.zeros(self.B, np.uint8)
+        self._chk(self.lib.b2o_arm_is_ready(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def inverse_kinematics(self, pose, q_start):
+        p = np.ascontiguousarray(pose, np.float32)
+        qs = np.ascontiguousarray(q_start, np.float32)
+        out = np.zeros((7, self.B), np.float32)
+        self._chk(self.lib.b2o_inverse_kinematics(self.h, p.ctypes.data_as(C.c_void_p), qs.ctypes.data_as(C.c_void_p),
+                                                  out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def forward_kinematics(self):
+        self._chk(self.lib.b2o_forward_kinematics(self.h))
+        return self.array(_capi.ARR_LINK_POSES).reshape(self.B, -1, 7)
+
+    def observe(self):
+        self._chk(self.lib.b2o_observe(self.h))
+        return self.array('obs_position').reshape(self.B, self.N, 3)
+
+    def reward(self, prev_xy=None, next_xy=None):
+        a = None if prev_xy is None else np.ascontiguousarray(prev_xy, np.float32)
+        b = None if next_xy is None else np.ascontiguousarray(next_xy, np.float32)
+        self._chk(self.lib.b2o_reward(self.h, None if a is None else a.ctypes.data_as(C.c_void_p),
+                                      None if b is None else b.ctypes.data_as(C.c_void_p)))
+        return self.array('reward').copy(), self.array('termination').copy()
+
+    def set_camera(self, K, R, t, per_env=False):
+        K, R, t = (np.ascontiguousarray(x, np.float32) for x in (K, R, t))
+        fp = C.POINTER(C.c_float)
+        self._chk(self.lib.b2o_set_camera(self.h, K.ctypes.data_as(fp), R.ctypes.data_as(fp), t.ctypes.data_as(fp),
+                                          int(bool(per_env))))
+
+    def render(self):
+        self._chk(self.lib.b2o_render(self.h))
+        H, W = self.params.cam_height, self.params.cam_width
+        return self.array('depth').reshape(self.B, H, W), self.array('segmask').reshape(self.B, H, W)
+
+    def point_cloud(self, seed=0):
+        self._chk(self.lib.b2o_point_cloud(self.h, C.c_uint64(seed)))
+        return self.array('point_cloud').reshape(self.B, self.N, self.params.num_points, 3)
+
+    def substeps_executed(self):
+        return self.lib.b2o_substeps_executed(self.h)

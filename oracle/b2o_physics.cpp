@@ -1,0 +1,678 @@
+/* b2o_physics.cpp -- CPU oracle: one rigid-body substep of one environment.
+ *
+ * TEST INFRASTRUCTURE ONLY (see b2o_world.h).  PARITY UNPINNED vs pybullet.
+ *
+ * Restates what `BulletPhysics.step` -> `pybullet.stepSimulation`
+ * (robovat/simulation/physics/bullet_physics.py:106-109) does for the PushEnv
+ * scene, per SURVEY.md 3.4: gravity + damping, AABB broad phase, GJK/EPA narrow
+ * phase over convex hulls with margins, persistent <=4-point manifolds,
+ * sequential-impulse PGS contact/friction solve (50 iterations, warm start,
+ * ERP on penetration, speculative margin on separation), semi-implicit Euler.
+ * Scalar and sequential; the CUDA kernels in robovat_b200/csrc do the same work
+ * one environment per warp.
+ */
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "b2o_world.h"
+
+namespace b2o {
+
+void derive_scene(Scene& S) {
+  for (size_t h = 0; h < S.hulls.size(); ++h) {
+    Hull& H = S.hulls[h];
+    V3 mn = S.verts[H.voff], mx = S.verts[H.voff];
+    float r2 = 0.0f;
+    for (int i = 0; i < H.vcnt; ++i) {
+      V3 v = S.verts[H.voff + i];
+      mn = v3(fminf(mn.x, v.x), fminf(mn.y, v.y), fminf(mn.z, v.z));
+      mx = v3(fmaxf(mx.x, v.x), fmaxf(mx.y, v.y), fmaxf(mx.z, v.z));
+      r2 = fmaxf(r2, len2(v));
+    }
+    H.lc = (mn + mx) * 0.5f;
+    H.lh = (mx - mn) * 0.5f;
+    H.rad = sqrtf(r2);
+  }
+  for (size_t a = 0; a < S.assets.size(); ++a) {
+    Asset& A = S.assets[a];
+    V3 mn = v3(3e38f, 3e38f, 3e38f), mx = v3(-3e38f, -3e38f, -3e38f);
+    for (int h = A.hoff; h < A.hoff + A.hcnt; ++h) {
+      const Hull& H = S.hulls[h];
+      V3 lo = (H.lc - H.lh) - v3(H.margin, H.margin, H.margin);
+      V3 hi = (H.lc + H.lh) + v3(H.margin, H.margin, H.margin);
+      mn = v3(fminf(mn.x, lo.x), fminf(mn.y, lo.y), fminf(mn.z, lo.z));
+      mx = v3(fmaxf(mx.x, hi.x), fmaxf(mx.y, hi.y), fmaxf(mx.z, hi.z));
+    }
+    A.half = (mx - mn) * 0.5f;
+  }
+}
+
+void build_colliders(World& w, int e) {
+  const Scene& S = w.S;
+  int n = 0;
+  int32_t* cs = &w.col_slot[(size_t)e * w.Hmax];
+  int32_t* ch = &w.col_hull[(size_t)e * w.Hmax];
+  bool overflow = false;
+  auto push = [&](int slot, int asset) {
+    const Asset& A = S.assets[asset];
+    for (int h = A.hoff; h < A.hoff + A.hcnt; ++h) {
+      if (n >= w.Hmax) { overflow = true; return; }
+      cs[n] = slot; ch[n] = h; ++n;
+    }
+  };
+  for (int s = 0; s < w.Ns; ++s)
+    if (!(S.static_flags[s] & B2S_STATIC_NO_COLLIDE)) push(s, S.static_asset[s]);
+  for (int k = 0; k < w.L; ++k) push(w.Ns + k, S.d.link_asset[k]);
+  int nm = w.num_movables[e];
+  for (int i = 0; i < nm; ++i) {
+    float af = w.mov_params[((size_t)0 * w.B + e) * w.Nmax + i];
+    int32_t asset; memcpy(&asset, &af, 4);
+    push(w.Ns + w.L + i, asset);
+  }
+  w.ncol[e] = n;
+  if (overflow) w.error_flags[e] |= 32;
+}
+
+int support(const World& w, const ColX& c, V3 d, V3* p) {
+  const Hull& H = w.S.hulls[c.hull];
+  V3 dl = mtmul(c.R, d);
+  int bi = 0;
+  float best = dot(w.S.verts[H.voff], dl);
+  for (int i = 1; i < H.vcnt; ++i) {
+    float t = dot(w.S.verts[H.voff + i], dl);
+    if (t > best) { best = t; bi = i; }
+  }
+  *p = c.pos + mmul(c.R, w.S.verts[H.voff + bi] * c.scale);
+  return bi;
+}
+
+/* ---------------------------------------------------------------- GJK ---- */
+struct Simplex {
+  V3 w[4], a[4], b[4];
+  int ia[4], ib[4];
+  int n;
+};
+
+/* status: 0 no contact (cores further apart than limit), 1 separated cores
+ * (v = closest vector, pa/pb witness points), 2 cores overlap or touch. */
+static int gjk(const World& w, const ColX& A, const ColX& B, float limit, Simplex* sx,
+               V3* v_out, V3* pa, V3* pb) {
+  V3 v = (A.amin + A.amax) * 0.5f - (B.amin + B.amax) * 0.5f;
+  if (len2(v) < 1e-12f) v = v3(1.0f, 0.0f, 0.0f);
+  sx->n = 0;
+  bool have = false;       /* v is a true closest point of the current simplex */
+  float bary[4] = {0, 0, 0, 0};
+  int status = 1;
+  for (int it = 0; it < w.P.gjk_max_iters; ++it) {
+    V3 a, b;
+    int ia = support(w, A, -v, &a);
+    int ib = support(w, B, v, &b);
+    V3 ww = a - b;
+    float vv = dot(v, v), vw = dot(v, ww);
+    if (vw > 0.0f && vw * vw > (limit * limit) * vv) return 0;
+    bool dup = false;
+    for (int k = 0; k < sx->n; ++k) if (sx->ia[k] == ia && sx->ib[k] == ib) dup = true;
+    if (dup) break;
+    if (have && (vv - vw) <= vv * 1e-6f) break;
+    int n = sx->n;
+    sx->w[n] = ww; sx->a[n] = a; sx->b[n] = b; sx->ia[n] = ia; sx->ib[n] = ib;
+    sx->n = n + 1;
+    b2s_simplex_result r;
+    b2s_closest_simplex(sx->w, sx->n, &r);
+    if (r.inside) { status = 2; break; }
+    /* compact to the vertices that support the closest point */
+    int m = 0;
+    for (int k = 0; k < sx->n; ++k) {
+      if (r.used & (1 << k)) {
+        sx->w[m] = sx->w[k]; sx->a[m] = sx->a[k]; sx->b[m] = sx->b[k];
+        sx->ia[m] = sx->ia[k]; sx->ib[m] = sx->ib[k];
+        bary[m] = r.bary[k];
+        ++m;
+      }
+    }
+    sx->n = m;
+    float nv = len2(r.v);
+    if (nv < 1e-14f) { status = 2; break; }
+    if (have && nv >= vv) { v = r.v; break; }   /* no progress: keep the newest consistent state */
+    v = r.v;
+    have = true;
+  }
+  if (status == 2) return 2;
+  if (!have) return 0;
+  V3 xa = v3(0, 0, 0), xb = v3(0, 0, 0);
+  for (int k = 0; k < sx->n; ++k) { xa = xa + sx->a[k] * bary[k]; xb = xb + sx->b[k] * bary[k]; }
+  *pa = xa; *pb = xb; *v_out = v;
+  return 1;
+}
+
+/* ---------------------------------------------------------------- EPA ---- */
+struct EpaFace { int i0, i1, i2; V3 n; float d; int alive; };
+
+static bool epa_make_face(const V3* W, int i0, int i1, int i2, EpaFace* f) {
+  V3 n = cross(W[i1] - W[i0], W[i2] - W[i0]);
+  float l2 = len2(n);
+  if (l2 < 1e-20f) return false;
+  n = n * (1.0f / sqrtf(l2));
+  f->i0 = i0; f->i1 = i1; f->i2 = i2; f->n = n; f->d = dot(n, W[i0]); f->alive = 1;
+  return true;
+}
+
+/* grow a GJK simplex that touches the origin into a tetrahedron */
+static bool epa_complete(const World& w, const ColX& A, const ColX& B, Simplex* sx) {
+  const V3 axes[6] = {v3(1, 0, 0), v3(-1, 0, 0), v3(0, 1, 0), v3(0, -1, 0), v3(0, 0, 1), v3(0, 0, -1)};
+  auto add = [&](V3 d) -> bool {
+    V3 a, b;
+    int ia = support(w, A, d, &a);
+    int ib = support(w, B, -d, &b);
+    for (int k = 0; k < sx->n; ++k) if (sx->ia[k] == ia && sx->ib[k] == ib) return false;
+    int n = sx->n;
+    sx->w[n] = a - b; sx->a[n] = a; sx->b[n] = b; sx->ia[n] = ia; sx->ib[n] = ib;
+    sx->n = n + 1;
+    return true;
+  };
+  if (sx->n == 1) {
+    for (int k = 0; k < 6 && sx->n == 1; ++k) add(axes[k]);
+    if (sx->n == 1) return false;
+  }
+  if (sx->n == 2) {
+    V3 d = sx->w[1] - sx->w[0];
+    for (int k = 0; k < 6 && sx->n == 2; k += 2) {
+      V3 dir = cross(d, axes[k]);
+      if (len2(dir) < 1e-12f * len2(d)) continue;
+      if (!add(dir)) add(-dir);
+      if (sx->n == 3) {
+        V3 n = cross(sx->w[1] - sx->w[0], sx->w[2] - sx->w[0]);
+        if (len2(n) < 1e-20f) sx->n = 2;   /* collinear: try the next axis */
+      }
+    }
+    if (sx->n == 2) return false;
+  }
+  if (sx->n == 3) {
+    V3 n = cross(sx->w[1] - sx->w[0], sx->w[2] - sx->w[0]);
+    if (len2(n) < 1e-20f) return false;
+    if (!add(n)) { if (!add(-n)) return false; }
+    float vol = dot(sx->w[3] - sx->w[0], n);
+    if (vol * vol < 1e-12f * len2(n) * len2(sx->w[3] - sx->w[0])) {
+      sx->n = 3;
+      if (!add(-n)) return false;
+      vol = dot(sx->w[3] - sx->w[0], n);
+      if (vol * vol < 1e-12f * len2(n) * len2(sx->w[3] - sx->w[0])) return false;
+    }
+  }
+  return sx->n == 4;
+}
+
+/* returns 1 on success: n_out = outward normal of the closest face of A-B,
+ * depth = its distance from the origin, pa/pb = witness points on the cores */
+static int epa(const World& w, const ColX& A, const ColX& B, Simplex* sx, V3* n_out, float* depth,
+               V3* pa, V3* pb) {
+  if (sx->n < 4 && !epa_complete(w, A, B, sx)) return 0;
+  V3 W[EPA_MAXV], PA[EPA_MAXV], PB[EPA_MAXV];
+  int IA[EPA_MAXV], IB[EPA_MAXV];
+  int nv = 4;
+  for (int k = 0; k < 4; ++k) { W[k] = sx->w[k]; PA[k] = sx->a[k]; PB[k] = sx->b[k]; IA[k] = sx->ia[k]; IB[k] = sx->ib[k]; }
+  EpaFace F[EPA_MAXF];
+  int nf = 0;
+  const int tet[4][4] = {{0, 1, 2, 3}, {0, 3, 1, 2}, {0, 2, 3, 1}, {1, 3, 2, 0}};
+  for (int k = 0; k < 4; ++k) {
+    EpaFace f;
+    if (!epa_make_face(W, tet[k][0], tet[k][1], tet[k][2], &f)) return 0;
+    /* orient away from the opposite vertex */
+    if (dot(f.n, W[tet[k][3]]) - f.d > 0.0f) {
+      int t = f.i1; f.i1 = f.i2; f.i2 = t;
+      f.n = -f.n; f.d = -f.d;
+    }
+    F[nf++] = f;
+  }
+  int best = 0;
+  for (int it = 0; it < w.P.epa_max_iters; ++it) {
+    best = -1;
+    float bd = 3e38f;
+    for (int f = 0; f < nf; ++f) if (F[f].alive && F[f].d < bd) { bd = F[f].d; best = f; }
+    if (best < 0) return 0;
+    V3 n = F[best].n;
+    V3 a, b;
+    int ia = support(w, A, n, &a);
+    int ib = support(w, B, -n, &b);
+    V3 ww = a - b;
+    float s = dot(ww, n);
+    if (s - bd < 1e-6f) break;
+    bool dup = false;
+    for (int k = 0; k < nv; ++k) if (IA[k] == ia && IB[k] == ib) dup = true;
+    if (dup || nv >= EPA_MAXV) break;
+    /* horizon of the faces visible from the new vertex */
+    int eu[EPA_MAXF], ev[EPA_MAXF], ne = 0;
+    int vis[EPA_MAXF];
+    for (int f = 0; f < nf; ++f) vis[f] = F[f].alive && (dot(F[f].n, ww) - F[f].d > 0.0f);
+    for (int f = 0; f < nf; ++f) {
+      if (!vis[f]) continue;
+      int e0[3] = {F[f].i0, F[f].i1, F[f].i2}, e1[3] = {F[f].i1, F[f].i2, F[f].i0};
+      for (int k = 0; k < 3; ++k) {
+        int found = -1;
+        for (int j = 0; j < ne; ++j) if (eu[j] == e1[k] && ev[j] == e0[k]) { found = j; break; }
+        if (found >= 0) { for (int j = found; j + 1 < ne; ++j) { eu[j] = eu[j + 1]; ev[j] = ev[j + 1]; } --ne; }
+        else if (ne < EPA_MAXF) { eu[ne] = e0[k]; ev[ne] = e1[k]; ++ne; }
+      }
+    }
+    if (ne < 3 || nf + ne > EPA_MAXF) break;
+    W[nv] = ww; PA[nv] = a; PB[nv] = b; IA[nv] = ia; IB[nv] = ib;
+    EpaFace NF[EPA_MAXF];
+    bool ok = true;
+    for (int j = 0; j < ne; ++j) if (!epa_make_face(W, eu[j], ev[j], nv, &NF[j])) { ok = false; break; }
+    if (!ok) break;
+    for (int f = 0; f < nf; ++f) if (vis[f]) F[f].alive = 0;
+    for (int j = 0; j < ne; ++j) F[nf++] = NF[j];
+    ++nv;
+  }
+  if (best < 0) return 0;
+  /* the loop can leave `best` pointing at a face that was just replaced only via break-before-modify, so it is alive */
+  const EpaFace& f = F[best];
+  V3 p = f.n * f.d;
+  b2s_simplex_result r;
+  b2s_closest_triangle(W[f.i0] - p, W[f.i1] - p, W[f.i2] - p, 0, 1, 2, &r);
+  *pa = (PA[f.i0] * r.bary[0] + PA[f.i1] * r.bary[1]) + PA[f.i2] * r.bary[2];
+  *pb = (PB[f.i0] * r.bary[0] + PB[f.i1] * r.bary[1]) + PB[f.i2] * r.bary[2];
+  *n_out = f.n;
+  *depth = f.d;
+  return 1;
+}
+
+int collide_pair(const World& w, const ColX& A, const ColX& B, float threshold, V3* pA, V3* pB,
+                 V3* normal, float* distance) {
+  float msum = A.margin + B.margin;
+  Simplex sx;
+  V3 v, pa, pb;
+  int st = gjk(w, A, B, msum + threshold, &sx, &v, &pa, &pb);
+  if (st == 0) return 0;
+  V3 n;
+  float dist;
+  if (st == 1) {
+    float l = len(v);
+    n = v * (1.0f / l);
+    dist = l - msum;
+  } else {
+    V3 no;
+    float depth;
+    if (!epa(w, A, B, &sx, &no, &depth, &pa, &pb)) {
+      /* degenerate overlap: push apart along the centre line */
+      V3 c = (A.amin + A.amax) * 0.5f - (B.amin + B.amax) * 0.5f;
+      float l2 = len2(c);
+      n = (l2 < 1e-12f) ? v3(0.0f, 0.0f, 1.0f) : c * (1.0f / sqrtf(l2));
+      pa = (A.amin + A.amax) * 0.5f; pb = pa;
+      dist = -msum;
+    } else {
+      n = -no;
+      dist = -depth - msum;
+    }
+  }
+  if (!(dist < threshold)) return 0;
+  *pA = pa - n * A.margin;
+  *pB = pb + n * B.margin;
+  *normal = n;
+  *distance = dist;
+  return 1;
+}
+
+/* ------------------------------------------------------- manifold cache ---- */
+static void manifold_refresh(float* pts, int* npts, const BodyX& bA, const M3& RA, const BodyX& bB,
+                             const M3& RB, float threshold) {
+  int m = 0;
+  for (int k = 0; k < *npts; ++k) {
+    float* p = pts + k * B2S_CP_FLOATS;
+    V3 wA = bA.pos + mmul(RA, v3(p[0], p[1], p[2]));
+    V3 wB = bB.pos + mmul(RB, v3(p[3], p[4], p[5]));
+    V3 n = v3(p[6], p[7], p[8]);
+    float dist = dot(wA - wB, n);
+    if (dist > threshold) continue;
+    V3 proj = wA - n * dist;
+    V3 dd = wB - proj;
+    if (len2(dd) > threshold * threshold) continue;
+    p[9] = dist;
+    if (m != k) memcpy(pts + m * B2S_CP_FLOATS, p, sizeof(float) * B2S_CP_FLOATS);
+    ++m;
+  }
+  *npts = m;
+}
+
+static void manifold_add(float* pts, int* npts, V3 lA, V3 lB, V3 n, float dist, float threshold) {
+  int nearest = -1;
+  float shortest = threshold * threshold;
+  for (int k = 0; k < *npts; ++k) {
+    const float* p = pts + k * B2S_CP_FLOATS;
+    V3 d = v3(p[0], p[1], p[2]) - lA;
+    float dd = len2(d);
+    if (dd < shortest) { shortest = dd; nearest = k; }
+  }
+  int idx;
+  bool keep = false;
+  if (nearest >= 0) { idx = nearest; keep = true; }
+  else if (*npts < 4) { idx = (*npts)++; }
+  else {
+    V3 P[4]; float D[4];
+    for (int k = 0; k < 4; ++k) {
+      const float* p = pts + k * B2S_CP_FLOATS;
+      P[k] = v3(p[0], p[1], p[2]); D[k] = p[9];
+    }
+    idx = b2s_manifold_replace_index(P, D, lA, dist);
+  }
+  float* p = pts + idx * B2S_CP_FLOATS;
+  p[0] = lA.x; p[1] = lA.y; p[2] = lA.z;
+  p[3] = lB.x; p[4] = lB.y; p[5] = lB.z;
+  p[6] = n.x; p[7] = n.y; p[8] = n.z;
+  p[9] = dist;
+  if (!keep) { p[10] = 0.0f; p[11] = 0.0f; p[12] = 0.0f; }
+  p[13] = 0.0f; p[14] = 0.0f; p[15] = 0.0f;
+}
+
+/* ------------------------------------------------------------ substep ---- */
+static M3 inv_inertia_world(M3 R, V3 d) {
+  /* R diag(d) R^T */
+  V3 a0 = vmul(R.r0, d), a1 = vmul(R.r1, d), a2 = vmul(R.r2, d);
+  M3 m;
+  m.r0 = v3(dot(a0, R.r0), dot(a0, R.r1), dot(a0, R.r2));
+  m.r1 = v3(dot(a1, R.r0), dot(a1, R.r1), dot(a1, R.r2));
+  m.r2 = v3(dot(a2, R.r0), dot(a2, R.r1), dot(a2, R.r2));
+  return m;
+}
+
+static inline float& bs(World& w, int c, int e, int i) { return w.body_state[((size_t)c * w.B + e) * w.Nmax + i]; }
+
+void substep(World& w, int e) {
+  const Scene& S = w.S;
+  const B2SParams& P = w.P;
+  const float dt = (float)P.time_step;
+  const int B = w.B, Nmax = w.Nmax, Ns = w.Ns, L = w.L, NB = w.NB;
+  const int nm = w.num_movables[e];
+
+  /* 1. arm controller + motor (ControllableBody.update, controllable_body.py:387-413) */
+  arm_update(w, e);
+  float q[7], qd[7];
+  for (int j = 0; j < 7; ++j) { q[j] = w.joint_state[(0 * 7 + j) * B + e]; qd[j] = w.joint_state[(1 * 7 + j) * B + e]; }
+  float* lp = &w.link_poses[(size_t)e * (L + 1) * 7];
+  float* lv = &w.link_vel[(size_t)e * L * 6];
+  arm_fk(w, q, qd, lp, lv);
+
+  /* 2. body table */
+  std::vector<BodyX> body(NB);
+  std::vector<M3> Rb(NB);
+  const M3 zero3 = {v3(0, 0, 0), v3(0, 0, 0), v3(0, 0, 0)};
+  for (int s = 0; s < Ns; ++s) {
+    BodyX& b = body[s];
+    const float* sp = &S.static_pose[s * 7];
+    float dz = (S.static_flags[s] & B2S_STATIC_ON_TABLE) ? w.table_dz[e] : 0.0f;
+    b.pos = v3(sp[0], sp[1], sp[2] + dz); b.quat = q4(sp[3], sp[4], sp[5], sp[6]);
+    b.vel = v3(0, 0, 0); b.ang = v3(0, 0, 0); b.inv_mass = 0.0f; b.inv_inertia = zero3;
+    b.friction = S.static_friction[s]; b.type = TYPE_STATIC;
+  }
+  for (int k = 0; k < L; ++k) {
+    BodyX& b = body[Ns + k];
+    b.pos = v3(lp[k * 7 + 0], lp[k * 7 + 1], lp[k * 7 + 2]);
+    b.quat = q4(lp[k * 7 + 3], lp[k * 7 + 4], lp[k * 7 + 5], lp[k * 7 + 6]);
+    b.vel = v3(lv[k * 6 + 0], lv[k * 6 + 1], lv[k * 6 + 2]);
+    b.ang = v3(lv[k * 6 + 3], lv[k * 6 + 4], lv[k * 6 + 5]);
+    b.inv_mass = 0.0f; b.inv_inertia = zero3; b.friction = S.d.arm_friction; b.type = TYPE_KINEMATIC;
+  }
+  const V3 g = v3(P.gravity[0], P.gravity[1], P.gravity[2]);
+  const float ld = fmaxf(0.0f, 1.0f - P.linear_damping * dt), ad = fmaxf(0.0f, 1.0f - P.angular_damping * dt);
+  for (int i = 0; i < Nmax; ++i) {
+    BodyX& b = body[Ns + L + i];
+    if (i >= nm) { b.pos = v3(0, 0, 0); b.quat = q4(0, 0, 0, 1); b.vel = b.ang = v3(0, 0, 0); b.inv_mass = 0; b.inv_inertia = zero3; b.friction = 0; b.type = TYPE_STATIC; continue; }
+    b.pos = v3(bs(w, 0, e, i), bs(w, 1, e, i), bs(w, 2, e, i));
+    b.quat = q4(bs(w, 3, e, i), bs(w, 4, e, i), bs(w, 5, e, i), bs(w, 6, e, i));
+    V3 v = v3(bs(w, 7, e, i), bs(w, 8, e, i), bs(w, 9, e, i));
+    V3 om = v3(bs(w, 10, e, i), bs(w, 11, e, i), bs(w, 12, e, i));
+    b.vel = (v + g * dt) * ld;
+    b.ang = om * ad;
+    float af = w.mov_params[((size_t)0 * B + e) * Nmax + i];
+    int32_t asset; memcpy(&asset, &af, 4);
+    float sc = w.mov_params[((size_t)1 * B + e) * Nmax + i];
+    float mass = w.mov_params[((size_t)2 * B + e) * Nmax + i];
+    b.friction = w.mov_params[((size_t)3 * B + e) * Nmax + i];
+    b.type = TYPE_DYNAMIC;
+    b.inv_mass = 1.0f / mass;
+    V3 h = S.assets[asset].half * sc;
+    float k3 = mass * (1.0f / 3.0f);
+    V3 I = v3(k3 * (h.y * h.y + h.z * h.z), k3 * (h.x * h.x + h.z * h.z), k3 * (h.x * h.x + h.y * h.y));
+    M3 R = q_to_m3(b.quat);
+    b.inv_inertia = inv_inertia_world(R, v3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
+  }
+  for (int s = 0; s < NB; ++s) Rb[s] = q_to_m3(body[s].quat);
+
+  /* 3. collider transforms + AABBs */
+  const int nc = w.ncol[e];
+  std::vector<ColX> col(nc);
+  int first_dyn = nc, arm0 = nc, arm1 = 0;
+  for (int c = 0; c < nc; ++c) {
+    ColX& C = col[c];
+    C.slot = w.col_slot[(size_t)e * w.Hmax + c];
+    C.hull = w.col_hull[(size_t)e * w.Hmax + c];
+    const Hull& H = S.hulls[C.hull];
+    const BodyX& b = body[C.slot];
+    C.type = b.type;
+    C.flags = (C.slot < Ns) ? S.static_flags[C.slot] : 0u;
+    C.pos = b.pos; C.R = Rb[C.slot];
+    C.scale = (C.slot >= Ns + L) ? w.mov_params[((size_t)1 * B + e) * Nmax + (C.slot - Ns - L)] : 1.0f;
+    C.margin = H.margin;
+    C.rad = H.rad * C.scale + H.margin;
+    V3 cen = C.pos + mmul(C.R, H.lc * C.scale);
+    V3 hs = H.lh * C.scale;
+    float pad = H.margin + P.breaking_factor * C.rad;
+    V3 ext = v3((fabsf(C.R.r0.x) * hs.x + fabsf(C.R.r0.y) * hs.y) + fabsf(C.R.r0.z) * hs.z + pad,
+                (fabsf(C.R.r1.x) * hs.x + fabsf(C.R.r1.y) * hs.y) + fabsf(C.R.r1.z) * hs.z + pad,
+                (fabsf(C.R.r2.x) * hs.x + fabsf(C.R.r2.y) * hs.y) + fabsf(C.R.r2.z) * hs.z + pad);
+    C.amin = cen - ext; C.amax = cen + ext;
+    if (C.type == TYPE_DYNAMIC && c < first_dyn) first_dyn = c;
+    if (C.type == TYPE_KINEMATIC) { if (c < arm0) arm0 = c; arm1 = c + 1; }
+  }
+  auto overlap = [&](const ColX& a, const ColX& b) {
+    return a.amin.x <= b.amax.x && b.amin.x <= a.amax.x && a.amin.y <= b.amax.y && b.amin.y <= a.amax.y &&
+           a.amin.z <= b.amax.z && b.amin.z <= a.amax.z;
+  };
+
+  /* 4. broad phase: sorted pair keys (a << 16) | b, a > b */
+  int32_t* pk = &w.pair_keys[(size_t)e * P.max_pairs];
+  int np = 0;
+  bool pair_over = false;
+  for (int a = arm0; a < arm1; ++a)
+    for (int b = 0; b < a; ++b) {
+      if (col[b].type != TYPE_STATIC || !(col[b].flags & B2S_STATIC_IS_TABLE)) continue;
+      if (!overlap(col[a], col[b])) continue;
+      if (np < P.max_pairs) pk[np++] = (a << 16) | b; else pair_over = true;
+    }
+  for (int a = first_dyn; a < nc; ++a)
+    for (int b = 0; b < a; ++b) {
+      if (col[b].slot == col[a].slot) continue;
+      if (!overlap(col[a], col[b])) continue;
+      if (np < P.max_pairs) pk[np++] = (a << 16) | b; else pair_over = true;
+    }
+  w.num_pairs[e] = np;
+  if (pair_over) w.error_flags[e] |= 1;
+
+  /* 5. narrow phase + persistent manifolds */
+  const int M = P.max_manifolds;
+  int32_t* mk = &w.man_keys[(size_t)e * M];
+  int32_t* mn = &w.man_npts[(size_t)e * M];
+  float* mp = &w.man_pts[(size_t)e * M * 4 * B2S_CP_FLOATS];
+  const int old_n = w.num_manifolds[e];
+  std::vector<int32_t> nk(M), nn(M);
+  std::vector<float> npnts((size_t)M * 4 * B2S_CP_FLOATS, 0.0f);
+  int newn = 0;
+  bool man_over = false;
+  int cflags = 0;
+  for (int p = 0; p < np; ++p) {
+    int key = pk[p];
+    int a = key >> 16, b = key & 0xffff;
+    const ColX& A = col[a];
+    const ColX& Bc = col[b];
+    float threshold = P.breaking_factor * fminf(A.rad, Bc.rad);
+    float pts[4 * B2S_CP_FLOATS];
+    int n = 0;
+    for (int k = 0; k < old_n; ++k)
+      if (mk[k] == key) { n = mn[k]; memcpy(pts, mp + (size_t)k * 4 * B2S_CP_FLOATS, sizeof(float) * n * B2S_CP_FLOATS); break; }
+    manifold_refresh(pts, &n, body[A.slot], Rb[A.slot], body[Bc.slot], Rb[Bc.slot], threshold);
+    V3 pA, pB, nrm;
+    float dist;
+    if (collide_pair(w, A, Bc, threshold, &pA, &pB, &nrm, &dist)) {
+      V3 lA = mtmul(Rb[A.slot], pA - body[A.slot].pos);
+      V3 lB = mtmul(Rb[Bc.slot], pB - body[Bc.slot].pos);
+      manifold_add(pts, &n, lA, lB, nrm, dist, threshold);
+    }
+    if (n > 0) {
+      if (newn < M) {
+        nk[newn] = key; nn[newn] = n;
+        memcpy(&npnts[(size_t)newn * 4 * B2S_CP_FLOATS], pts, sizeof(float) * n * B2S_CP_FLOATS);
+        ++newn;
+        if (A.type == TYPE_KINEMATIC && (Bc.flags & B2S_STATIC_IS_TABLE)) cflags |= 1;
+        if ((A.type == TYPE_DYNAMIC && Bc.type == TYPE_KINEMATIC)) cflags |= 2;
+      } else man_over = true;
+    }
+  }
+  if (man_over) w.error_flags[e] |= 2;
+  for (int k = 0; k < M; ++k) { mk[k] = (k < newn) ? nk[k] : -1; mn[k] = (k < newn) ? nn[k] : 0; }
+  memcpy(mp, npnts.data(), sizeof(float) * (size_t)M * 4 * B2S_CP_FLOATS);
+  w.num_manifolds[e] = newn;
+  w.contact_flags[e] = cflags;
+
+  /* 6. contact rows */
+  std::vector<Contact> con;
+  const int nrows = 1 + P.friction_dirs;
+  bool con_over = false;
+  for (int m = 0; m < newn; ++m) {
+    int a = mk[m] >> 16, b = mk[m] & 0xffff;
+    int sA = col[a].slot, sB = col[b].slot;
+    const BodyX& bA = body[sA];
+    const BodyX& bB = body[sB];
+    if (bA.type != TYPE_DYNAMIC && bB.type != TYPE_DYNAMIC) continue;  /* arm-table: detection only */
+    for (int k = 0; k < mn[m]; ++k) {
+      if ((int)con.size() >= P.max_contacts) { con_over = true; break; }
+      float* p = mp + ((size_t)m * 4 + k) * B2S_CP_FLOATS;
+      Contact c;
+      c.slotA = sA; c.slotB = sB; c.manifold = m; c.point = k; c.colour = -1;
+      c.mu = bA.friction * bB.friction;
+      V3 wA = bA.pos + mmul(Rb[sA], v3(p[0], p[1], p[2]));
+      V3 wB = bB.pos + mmul(Rb[sB], v3(p[3], p[4], p[5]));
+      V3 n = v3(p[6], p[7], p[8]);
+      V3 rA = wA - bA.pos, rB = wB - bB.pos;
+      V3 t1, t2;
+      plane_space(n, &t1, &t2);
+      if (P.friction_dirs == 1) {
+        V3 rel = (bA.vel + cross(bA.ang, rA)) - (bB.vel + cross(bB.ang, rB));
+        V3 lat = rel - n * dot(rel, n);
+        float l2 = len2(lat);
+        if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
+      }
+      for (int r = 0; r < 3; ++r) {
+        ContactRow& row = c.row[r];
+        V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
+        row.dir = dir;
+        row.angA = cross(rA, dir); row.angB = cross(rB, dir);
+        row.iangA = mmul(bA.inv_inertia, row.angA); row.iangB = mmul(bB.inv_inertia, row.angB);
+        float d = ((bA.inv_mass + bB.inv_mass) + dot(row.iangA, row.angA)) + dot(row.iangB, row.angB);
+        row.inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
+        row.d = d;
+        row.bias = 0.0f;
+        row.lambda = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
+        if (r >= nrows) row.lambda = 0.0f;
+      }
+      float pen = p[9] + P.linear_slop;
+      c.row[0].bias = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
+      con.push_back(c);
+    }
+  }
+  if (con_over) w.error_flags[e] |= 8;
+
+  /* 7. greedy colouring in contact order: same-colour contacts share no dynamic body */
+  const int C = (int)con.size();
+  std::vector<uint64_t> used(NB, 0);
+  int ncolours = 0;
+  for (int i = 0; i < C; ++i) {
+    uint64_t mask = 0;
+    if (body[con[i].slotA].type == TYPE_DYNAMIC) mask |= used[con[i].slotA];
+    if (body[con[i].slotB].type == TYPE_DYNAMIC) mask |= used[con[i].slotB];
+    if (mask == ~(uint64_t)0) { w.error_flags[e] |= 16; con[i].colour = -1; continue; }
+    int k = 0;
+    while (mask & ((uint64_t)1 << k)) ++k;
+    con[i].colour = k;
+    if (k + 1 > ncolours) ncolours = k + 1;
+    if (body[con[i].slotA].type == TYPE_DYNAMIC) used[con[i].slotA] |= (uint64_t)1 << k;
+    if (body[con[i].slotB].type == TYPE_DYNAMIC) used[con[i].slotB] |= (uint64_t)1 << k;
+  }
+  std::vector<int> order;
+  for (int k = 0; k < ncolours; ++k) for (int i = 0; i < C; ++i) if (con[i].colour == k) order.push_back(i);
+
+  auto apply = [&](Contact& c, const ContactRow& row, float dl) {
+    BodyX& bA = body[c.slotA];
+    BodyX& bB = body[c.slotB];
+    if (bA.type == TYPE_DYNAMIC) { bA.vel = bA.vel + row.dir * (bA.inv_mass * dl); bA.ang = bA.ang + row.iangA * dl; }
+    if (bB.type == TYPE_DYNAMIC) { bB.vel = bB.vel - row.dir * (bB.inv_mass * dl); bB.ang = bB.ang - row.iangB * dl; }
+  };
+  auto jv = [&](const Contact& c, const ContactRow& row) {
+    const BodyX& bA = body[c.slotA];
+    const BodyX& bB = body[c.slotB];
+    return ((dot(row.dir, bA.vel) + dot(row.angA, bA.ang)) - dot(row.dir, bB.vel)) - dot(row.angB, bB.ang);
+  };
+  /* warm start */
+  for (int oi = 0; oi < (int)order.size(); ++oi) {
+    Contact& c = con[order[oi]];
+    for (int r = 0; r < nrows; ++r) apply(c, c.row[r], c.row[r].lambda);
+  }
+  /* 8. projected Gauss-Seidel: all normal rows, then all friction rows, per iteration */
+  int iters_used = 0;
+  for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
+    float maxres = 0.0f;
+    for (int oi = 0; oi < (int)order.size(); ++oi) {
+      Contact& c = con[order[oi]];
+      ContactRow& row = c.row[0];
+      float dl = (row.bias - jv(c, row)) * row.inv_d;
+      float nl = fmaxf(0.0f, row.lambda + dl);
+      dl = nl - row.lambda;
+      row.lambda = nl;
+      apply(c, row, dl);
+      float res = dl * row.d;
+      maxres = fmaxf(maxres, res * res);
+    }
+    for (int oi = 0; oi < (int)order.size(); ++oi) {
+      Contact& c = con[order[oi]];
+      float lim = c.mu * c.row[0].lambda;
+      for (int r = 1; r < nrows; ++r) {
+        ContactRow& row = c.row[r];
+        float dl = (0.0f - jv(c, row)) * row.inv_d;
+        float nl = fminf(lim, fmaxf(-lim, row.lambda + dl));
+        dl = nl - row.lambda;
+        row.lambda = nl;
+        apply(c, row, dl);
+        float res = dl * row.d;
+        maxres = fmaxf(maxres, res * res);
+      }
+    }
+    iters_used = it + 1;
+    if (maxres <= P.residual_threshold) break;
+  }
+  for (int i = 0; i < C; ++i) {
+    float* p = mp + ((size_t)con[i].manifold * 4 + con[i].point) * B2S_CP_FLOATS;
+    p[10] = con[i].row[0].lambda; p[11] = con[i].row[1].lambda; p[12] = con[i].row[2].lambda;
+  }
+  int32_t* st = &w.solver_stats[(size_t)e * 4];
+  st[0] = C * nrows; st[1] = ncolours; st[2] = iters_used; st[3] = C;
+
+  /* 9. integrate */
+  for (int i = 0; i < nm; ++i) {
+    BodyX& b = body[Ns + L + i];
+    float wl = len(b.ang);
+    if (wl * dt > B2S_HALF_PI) b.ang = b.ang * (B2S_HALF_PI / (wl * dt));
+    V3 pos = b.pos + b.vel * dt;
+    Q4 qq = q_integrate(b.quat, b.ang, dt);
+    bs(w, 0, e, i) = pos.x; bs(w, 1, e, i) = pos.y; bs(w, 2, e, i) = pos.z;
+    bs(w, 3, e, i) = qq.x; bs(w, 4, e, i) = qq.y; bs(w, 5, e, i) = qq.z; bs(w, 6, e, i) = qq.w;
+    bs(w, 7, e, i) = b.vel.x; bs(w, 8, e, i) = b.vel.y; bs(w, 9, e, i) = b.vel.z;
+    bs(w, 10, e, i) = b.ang.x; bs(w, 11, e, i) = b.ang.y; bs(w, 12, e, i) = b.ang.z;
+    float chk = (pos.x + pos.y) + pos.z;
+    if (!(fabsf(chk) < 1e6f)) w.error_flags[e] |= 4;
+  }
+  for (int j = 0; j < 7; ++j) w.joint_state[(0 * 7 + j) * B + e] = q[j] + qd[j] * dt;
+  w.num_steps[e] += 1;
+}
+
+}  // namespace b2o
