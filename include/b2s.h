@@ -306,6 +306,8 @@ int b2s_allgather_returns(B2SWorld* world, void* nccl_comm, float* out_dev, void
 
 /* inspection: device pointer + byte size of a world-owned array */
 int b2s_array(B2SWorld* world, int which, void** dev_ptr, int64_t* bytes);
+/* sizeof(B2SParams / B2SSceneDesc / B2SBuffers) for which = 0 / 1 / 2: lets a binding check its layout */
+int b2s_sizeof(int which);
 /* number of kernels this library has launched on this world since creation */
 int64_t b2s_launch_count(const B2SWorld* world);
 /* sum over envs of substeps executed since creation (device counter, synchronises) */

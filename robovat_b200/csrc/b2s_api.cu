@@ -1,0 +1,519 @@
+// b2s_api.cu -- host side of the C-ABI declared in include/b2s.h.
+//
+// Error convention: 0 / negative code + thread-local message; nothing throws
+// across the boundary; CUDA errors are mapped to B2S_E_CUDA.  There is no CPU
+// path behind these entry points: without a CUDA device b2s_create fails.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "b2s_dev.cuh"
+
+struct B2SWorld {
+  DWorld d;
+  int device;
+  bool scene_loaded, buffers_bound;
+  std::vector<void*> allocs;
+  int64_t launches;
+  // export staging for b2s_array(MANIFOLD_*)
+  int32_t* exp_keys; int32_t* exp_npts; float* exp_pts;
+  size_t arr_bytes[B2S_ARR_COUNT];
+  void* arr_ptr[B2S_ARR_COUNT];
+  int* unfinished_pinned;
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(expr)                                                                                 \
+  do {                                                                                           \
+    cudaError_t err_ = (expr);                                                                   \
+    if (err_ != cudaSuccess) return fail(B2S_E_CUDA, "%s: %s", #expr, cudaGetErrorString(err_)); \
+  } while (0)
+#define NEED(w) \
+  if (!(w)) return fail(B2S_E_INVALID, "%s: world is NULL", __func__)
+#define NEED_READY(w)                                                                            \
+  NEED(w);                                                                                       \
+  if (!(w)->scene_loaded) return fail(B2S_E_STATE, "%s: call b2s_load_scene first", __func__);   \
+  if (!(w)->buffers_bound) return fail(B2S_E_STATE, "%s: call b2s_bind_buffers first", __func__)
+
+template <class T>
+static int dalloc(B2SWorld* w, T** p, size_t n, int fill = 0) {
+  void* q = nullptr;
+  size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  CU(cudaMalloc(&q, bytes));
+  CU(cudaMemset(q, fill, bytes));
+  w->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+template <class T>
+static int upload(B2SWorld* w, const T** p, const T* host, size_t n) {
+  T* q = nullptr;
+  int rc = dalloc(w, &q, n);
+  if (rc) return rc;
+  if (n) CU(cudaMemcpy(q, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  *p = q;
+  return 0;
+}
+
+static int check_launch(B2SWorld* w, const char* what, int n = 1) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(B2S_E_CUDA, "%s launch: %s", what, cudaGetErrorString(err));
+  w->launches += n;
+  return 0;
+}
+
+extern "C" {
+
+int b2s_version(void) { return B2S_VERSION; }
+const char* b2s_last_error(void) { return g_err.c_str(); }
+int b2s_sizeof(int which) {
+  return which == 0 ? (int)sizeof(B2SParams) : which == 1 ? (int)sizeof(B2SSceneDesc) : which == 2 ? (int)sizeof(B2SBuffers) : -1;
+}
+
+int b2s_default_params(B2SParams* p) {
+  if (!p) return fail(B2S_E_INVALID, "b2s_default_params: NULL");
+  memset(p, 0, sizeof(*p));
+  p->solver_iterations = 50; p->friction_dirs = 2; p->gjk_max_iters = 32; p->epa_max_iters = 32;
+  p->ik_max_iters = 20; p->ik_interval = 10; p->check_done_interval = 100;
+  p->steps_check = 20; p->max_phase_steps = 3000; p->max_motion_steps = 4000; p->max_offstage_steps = 4000;
+  p->stable_check_after = 100; p->stable_min_steps = 100; p->stable_max_steps = 2000;
+  p->clamp_joint_velocity = 1; p->warps_per_block = 4;
+  p->time_step = 1e-3;
+  p->gravity[0] = 0; p->gravity[1] = 0; p->gravity[2] = -9.8f;
+  p->erp2 = 0.08f; p->linear_slop = 1e-5f; p->warmstart = 0.85f; p->residual_threshold = 1e-7f;
+  p->linear_damping = 0.04f; p->angular_damping = 0.04f; p->breaking_factor = 0.02f;
+  p->ik_damping = 0.1f; p->ik_residual = 1e-4f; p->ik_max_step = 0.78539816f;
+  p->position_gain = 0.05f; p->velocity_gain = 1.0f;
+  p->joint_pos_threshold = 0.008726640f; p->joint_vel_threshold = 0.05f; p->limb_timeout = 15.0f;
+  p->limb_velocity_ratio = 0.5f; p->stable_lin_threshold = 0.005f; p->stable_ang_threshold = 0.005f;
+  p->cam_near = 0.02f; p->cam_far = 100.0f;
+  return 0;
+}
+
+int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
+  if (!p || !out) return fail(B2S_E_INVALID, "b2s_create: NULL argument");
+  if (p->num_envs <= 0 || p->max_movables <= 0 || p->max_movables > 64) return fail(B2S_E_INVALID, "b2s_create: num_envs/max_movables out of range");
+  if (p->max_pairs <= 0 || p->max_manifolds <= 0 || p->max_contacts <= 0 || p->max_colliders <= 0)
+    return fail(B2S_E_INVALID, "b2s_create: capacities must be positive");
+  if (p->max_colliders > 65535) return fail(B2S_E_INVALID, "b2s_create: max_colliders > 65535");
+  if (p->warps_per_block < 1 || p->warps_per_block > 4) return fail(B2S_E_INVALID, "b2s_create: warps_per_block must be 1..4");
+  if (p->friction_dirs != 1 && p->friction_dirs != 2) return fail(B2S_E_INVALID, "b2s_create: friction_dirs must be 1 or 2");
+  if (!(p->time_step > 0)) return fail(B2S_E_INVALID, "b2s_create: time_step must be > 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(B2S_E_CUDA, "b2s_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(B2S_E_INVALID, "b2s_create: device %d of %d", device, ndev);
+  CU(cudaSetDevice(device));
+  B2SWorld* w = new B2SWorld();
+  memset(&w->d, 0, sizeof(w->d));
+  w->d.P = *p;
+  w->d.B = p->num_envs; w->d.Nmax = p->max_movables; w->d.Hmax = p->max_colliders;
+  w->device = device; w->scene_loaded = false; w->buffers_bound = false; w->launches = 0;
+  w->exp_keys = nullptr; w->exp_npts = nullptr; w->exp_pts = nullptr; w->unfinished_pinned = nullptr;
+  memset(w->arr_bytes, 0, sizeof(w->arr_bytes)); memset(w->arr_ptr, 0, sizeof(w->arr_ptr));
+  *out = w;
+  return 0;
+}
+
+int b2s_destroy(B2SWorld* w) {
+  if (!w) return 0;
+  cudaSetDevice(w->device);
+  for (void* p : w->allocs) cudaFree(p);
+  if (w->unfinished_pinned) cudaFreeHost(w->unfinished_pinned);
+  delete w;
+  return 0;
+}
+
+int b2s_get_params(const B2SWorld* w, B2SParams* out) {
+  if (!w || !out) return fail(B2S_E_INVALID, "b2s_get_params: NULL");
+  *out = w->d.P;
+  return 0;
+}
+
+int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
+  NEED(w);
+  if (!s) return fail(B2S_E_INVALID, "b2s_load_scene: scene is NULL");
+  if (w->scene_loaded) return fail(B2S_E_STATE, "b2s_load_scene: scene already loaded");
+  if (s->num_links < 1 || s->num_links > B2S_MAX_LINKS) return fail(B2S_E_INVALID, "b2s_load_scene: num_links out of range");
+  if (s->num_statics < 0 || s->num_hulls <= 0 || s->num_assets <= 0 || s->num_verts <= 0) return fail(B2S_E_INVALID, "b2s_load_scene: empty hull library");
+  if (s->num_movable_assets <= 0) return fail(B2S_E_INVALID, "b2s_load_scene: no movable assets (reference asserts len(movable_paths) > 0, push_env.py:107)");
+  CU(cudaSetDevice(w->device));
+  DWorld& d = w->d;
+  const B2SParams& P = d.P;
+  // hull library: derived quantities (local AABB, bounding radius, inertia box)
+  std::vector<float4> verts(s->num_verts);
+  for (int i = 0; i < s->num_verts; ++i) verts[i] = make_float4(s->verts[i * 3], s->verts[i * 3 + 1], s->verts[i * 3 + 2], 0.0f);
+  std::vector<DHull> hulls(s->num_hulls);
+  for (int h = 0; h < s->num_hulls; ++h) {
+    DHull& H = hulls[h];
+    H.voff = s->hull_vert_off[h]; H.vcnt = s->hull_vert_cnt[h]; H.margin = s->hull_margin[h];
+    H.poff = s->hull_plane_off ? s->hull_plane_off[h] : 0; H.pcnt = s->hull_plane_cnt ? s->hull_plane_cnt[h] : 0;
+    if (H.vcnt < 1 || H.vcnt > 64 || H.voff < 0 || H.voff + H.vcnt > s->num_verts) return fail(B2S_E_INVALID, "b2s_load_scene: hull %d has %d vertices (1..64 allowed)", h, H.vcnt);
+    V3 mn = v3(verts[H.voff].x, verts[H.voff].y, verts[H.voff].z), mx = mn;
+    float r2 = 0.0f;
+    for (int i = 0; i < H.vcnt; ++i) {
+      V3 v = v3(verts[H.voff + i].x, verts[H.voff + i].y, verts[H.voff + i].z);
+      mn = v3(fminf(mn.x, v.x), fminf(mn.y, v.y), fminf(mn.z, v.z));
+      mx = v3(fmaxf(mx.x, v.x), fmaxf(mx.y, v.y), fmaxf(mx.z, v.z));
+      r2 = fmaxf(r2, len2(v));
+    }
+    V3 lc = (mn + mx) * 0.5f, lh = (mx - mn) * 0.5f;
+    H.lc[0] = lc.x; H.lc[1] = lc.y; H.lc[2] = lc.z; H.lh[0] = lh.x; H.lh[1] = lh.y; H.lh[2] = lh.z;
+    H.rad = sqrtf(r2);
+  }
+  std::vector<DAsset> assets(s->num_assets);
+  for (int a = 0; a < s->num_assets; ++a) {
+    DAsset& A = assets[a];
+    A.hoff = s->asset_hull_off[a]; A.hcnt = s->asset_hull_cnt[a]; A.pad = 0;
+    if (A.hcnt < 1 || A.hoff < 0 || A.hoff + A.hcnt > s->num_hulls) return fail(B2S_E_INVALID, "b2s_load_scene: asset %d hull range", a);
+    V3 mn = v3(3e38f, 3e38f, 3e38f), mx = v3(-3e38f, -3e38f, -3e38f);
+    for (int h = A.hoff; h < A.hoff + A.hcnt; ++h) {
+      const DHull& H = hulls[h];
+      V3 lc = v3(H.lc[0], H.lc[1], H.lc[2]), lh = v3(H.lh[0], H.lh[1], H.lh[2]);
+      V3 lo = (lc - lh) - v3(H.margin, H.margin, H.margin), hi = (lc + lh) + v3(H.margin, H.margin, H.margin);
+      mn = v3(fminf(mn.x, lo.x), fminf(mn.y, lo.y), fminf(mn.z, lo.z));
+      mx = v3(fmaxf(mx.x, hi.x), fmaxf(mx.y, hi.y), fmaxf(mx.z, hi.z));
+    }
+    V3 half = (mx - mn) * 0.5f;
+    A.half[0] = half.x; A.half[1] = half.y; A.half[2] = half.z;
+  }
+  std::vector<float4> planes(std::max(s->num_planes, 1));
+  for (int i = 0; i < s->num_planes; ++i) planes[i] = make_float4(s->planes[i * 4], s->planes[i * 4 + 1], s->planes[i * 4 + 2], s->planes[i * 4 + 3]);
+  int rc;
+  if ((rc = upload(w, &d.verts, verts.data(), verts.size()))) return rc;
+  if ((rc = upload(w, &d.hulls, hulls.data(), hulls.size()))) return rc;
+  if ((rc = upload(w, &d.assets, assets.data(), assets.size()))) return rc;
+  if ((rc = upload(w, &d.planes, planes.data(), planes.size()))) return rc;
+  if ((rc = upload(w, &d.static_asset, s->static_asset, s->num_statics))) return rc;
+  if ((rc = upload(w, &d.static_pose, s->static_pose, (size_t)s->num_statics * 7))) return rc;
+  if ((rc = upload(w, &d.static_friction, s->static_friction, s->num_statics))) return rc;
+  if ((rc = upload(w, &d.static_flags, s->static_flags, s->num_statics))) return rc;
+  if ((rc = upload(w, &d.movable_assets, s->movable_assets, s->num_movable_assets))) return rc;
+  if ((rc = upload(w, &d.target_assets, s->target_assets, std::max(s->num_target_assets, 0)))) return rc;
+  DArm arm;
+  memset(&arm, 0, sizeof(arm));
+  memcpy(arm.base, s->arm_base_pose, sizeof(arm.base));
+  memcpy(arm.joint_origin, s->joint_origin, sizeof(arm.joint_origin));
+  memcpy(arm.joint_axis, s->joint_axis, sizeof(arm.joint_axis));
+  memcpy(arm.lower, s->joint_lower, sizeof(arm.lower)); memcpy(arm.upper, s->joint_upper, sizeof(arm.upper));
+  memcpy(arm.max_vel, s->joint_max_velocity, sizeof(arm.max_vel));
+  memcpy(arm.ee, s->ee_pose, sizeof(arm.ee));
+  arm.num_links = s->num_links;
+  memcpy(arm.link_joint, s->link_joint, sizeof(arm.link_joint)); memcpy(arm.link_asset, s->link_asset, sizeof(arm.link_asset));
+  memcpy(arm.link_pose, s->link_pose, sizeof(arm.link_pose));
+  arm.friction = s->arm_friction;
+  for (int k = 0; k < s->num_links; ++k)
+    if (s->link_joint[k] < -1 || s->link_joint[k] >= B2S_NUM_JOINTS || s->link_asset[k] < 0 || s->link_asset[k] >= s->num_assets)
+      return fail(B2S_E_INVALID, "b2s_load_scene: link %d joint/asset out of range", k);
+  if ((rc = upload(w, &d.arm, &arm, 1))) return rc;
+  DLayout lay;
+  memset(&lay, 0, sizeof(lay));
+  lay.tile_size = s->tile_size; memcpy(lay.tile_offset, s->tile_offset, 8);
+  lay.num_region = s->num_region; lay.num_goal = s->num_goal; lay.num_target = s->num_target; lay.num_obstacle = s->num_obstacle;
+  memcpy(lay.region, s->region, sizeof(lay.region)); memcpy(lay.goal, s->goal, sizeof(lay.goal));
+  memcpy(lay.target, s->target, sizeof(lay.target)); memcpy(lay.obstacle, s->obstacle, sizeof(lay.obstacle));
+  memcpy(lay.scale_range, s->scale_range, 8); memcpy(lay.mass_range, s->mass_range, 8); memcpy(lay.friction_range, s->friction_range, 8);
+  memcpy(lay.pose_x, s->pose_x, 8); memcpy(lay.pose_y, s->pose_y, 8); memcpy(lay.pose_z, s->pose_z, 8);
+  memcpy(lay.pose_roll, s->pose_roll, 8); memcpy(lay.pose_pitch, s->pose_pitch, 8); memcpy(lay.pose_yaw, s->pose_yaw, 8);
+  lay.placement_margin = s->placement_margin; lay.min_movables = s->min_movables;
+  memcpy(lay.table_height_range, s->table_height_range, 8); lay.safe_drop_height = s->safe_drop_height;
+  lay.num_movable_assets = s->num_movable_assets; lay.num_target_assets = s->num_target_assets;
+  if ((rc = upload(w, &d.layout, &lay, 1))) return rc;
+
+  d.Ns = s->num_statics; d.L = s->num_links; d.NB = d.Ns + d.L + d.Nmax;
+  const size_t B = d.B, N = d.Nmax, M = P.max_manifolds;
+#define ALLOC(field, count, fill) if ((rc = dalloc(w, &d.field, (count), (fill)))) return rc
+  ALLOC(man_keys, 2 * B * M, 0xff); ALLOC(man_npts, 2 * B * M, 0); ALLOC(man_pts, 2 * B * M * 4 * B2S_CP_FLOATS, 0);
+  ALLOC(man_parity, B, 0); ALLOC(num_manifolds, B, 0);
+  ALLOC(pair_keys, B * P.max_pairs, 0); ALLOC(num_pairs, B, 0);
+  ALLOC(phase, B, 0); ALLOC(num_steps, B, 0);
+  ALLOC(ctrl, B * B2S_CTRL_FLOATS, 0); ALLOC(ctrl_flags, B * 4, 0); ALLOC(ctrl_time, B * 5, 0);
+  ALLOC(link_poses, B * (d.L + 1) * 7, 0); ALLOC(link_vel, B * d.L * 6, 0);
+  ALLOC(mov_params, 4 * B * N, 0); ALLOC(table_dz, B, 0); ALLOC(error_flags, B, 0);
+  ALLOC(waypoints, B * 14, 0); ALLOC(status, B * 2 * N * 4, 0);
+  ALLOC(contact_flags, B, 0); ALLOC(phase_state, B * 8, 0); ALLOC(solver_stats, B * 4, 0);
+  ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
+  ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
+  ALLOC(substeps, 1, 0); ALLOC(unfinished, 1, 0);
+  if ((rc = dalloc(w, &w->exp_keys, B * M, 0))) return rc;
+  if ((rc = dalloc(w, &w->exp_npts, B * M, 0))) return rc;
+  if ((rc = dalloc(w, &w->exp_pts, B * M * 4 * B2S_CP_FLOATS, 0))) return rc;
+#undef ALLOC
+  {
+    std::vector<int32_t> ph(B, B2S_PHASE_IDLE), ps(B * 8, 0);
+    for (size_t e = 0; e < B; ++e) ps[e * 8] = -1;
+    CU(cudaMemcpy(d.phase, ph.data(), B * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.phase_state, ps.data(), B * 8 * 4, cudaMemcpyHostToDevice));
+  }
+  CU(cudaMallocHost((void**)&w->unfinished_pinned, sizeof(int)));
+  // shared-memory carve-up per warp
+  SmemLayout& sm = d.sm;
+  int o = 0;
+  auto take = [&](int words) { int at = o; o += (words + 1) & ~1; return at; };   // keep 8-byte alignment
+  sm.body = take(d.NB * BODY_STRIDE);
+  sm.col = take(d.Hmax * COL_STRIDE);
+  sm.pairs = take(P.max_pairs);
+  sm.oldkeys = take(P.max_manifolds);
+  sm.cmk = take(P.max_contacts);
+  sm.con = take(std::max(P.max_contacts * CON_STRIDE, (int)(EPA_MAXV * 11 + EPA_MAXF * 7)));
+  sm.order = take(P.max_contacts);
+  sm.colstart = take(66);
+  sm.used = take(d.NB * 2);
+  sm.stage = take(4 * B2S_CP_FLOATS);
+  sm.fk = take(FK_WORDS);
+  sm.simplex = take(48);
+  sm.words = o;
+  size_t smem = b2s_smem_bytes(d);
+  if (smem > 227 * 1024) return fail(B2S_E_CAPACITY, "b2s_load_scene: %zu bytes of shared memory per block exceed 227 KB; lower warps_per_block or the capacities", smem);
+  // arrays exposed through b2s_array
+  auto reg = [&](int id, void* p, size_t bytes) { w->arr_ptr[id] = p; w->arr_bytes[id] = bytes; };
+  reg(B2S_ARR_MANIFOLD_KEYS, w->exp_keys, B * M * 4); reg(B2S_ARR_MANIFOLD_NPTS, w->exp_npts, B * M * 4);
+  reg(B2S_ARR_MANIFOLD_PTS, w->exp_pts, B * M * 4 * B2S_CP_FLOATS * 4); reg(B2S_ARR_NUM_MANIFOLDS, d.num_manifolds, B * 4);
+  reg(B2S_ARR_PAIR_KEYS, d.pair_keys, B * P.max_pairs * 4); reg(B2S_ARR_NUM_PAIRS, d.num_pairs, B * 4);
+  reg(B2S_ARR_PHASE, d.phase, B * 4); reg(B2S_ARR_NUM_STEPS, d.num_steps, B * 4);
+  reg(B2S_ARR_CTRL, d.ctrl, B * B2S_CTRL_FLOATS * 4); reg(B2S_ARR_CTRL_FLAGS, d.ctrl_flags, B * 16);
+  reg(B2S_ARR_LINK_POSES, d.link_poses, B * (d.L + 1) * 28); reg(B2S_ARR_MOV_PARAMS, d.mov_params, 4 * B * N * 4);
+  reg(B2S_ARR_TABLE_DZ, d.table_dz, B * 4); reg(B2S_ARR_ERROR_FLAGS, d.error_flags, B * 4);
+  reg(B2S_ARR_WAYPOINTS, d.waypoints, B * 56); reg(B2S_ARR_STATUS, d.status, B * 2 * N * 16);
+  reg(B2S_ARR_CONTACT_FLAGS, d.contact_flags, B * 4); reg(B2S_ARR_PHASE_STATE, d.phase_state, B * 32);
+  reg(B2S_ARR_SOLVER_STATS, d.solver_stats, B * 16); reg(B2S_ARR_CTRL_TIME, d.ctrl_time, B * 40);
+  reg(B2S_ARR_LINK_VEL, d.link_vel, B * d.L * 24); reg(B2S_ARR_NUM_COLLIDERS, d.ncol, B * 4);
+  reg(B2S_ARR_COL_SLOT, d.col_slot, B * d.Hmax * 4); reg(B2S_ARR_COL_HULL, d.col_hull, B * d.Hmax * 4);
+  w->scene_loaded = true;
+  return 0;
+}
+
+int b2s_bind_buffers(B2SWorld* w, const B2SBuffers* b) {
+  NEED(w);
+  if (!b) return fail(B2S_E_INVALID, "b2s_bind_buffers: NULL");
+  if (!b->body_state || !b->joint_state || !b->action || !b->obs_position || !b->num_movables || !b->body_mask || !b->reward ||
+      !b->termination || !b->is_safe || !b->is_effective || !b->episode_return)
+    return fail(B2S_E_INVALID, "b2s_bind_buffers: body_state, joint_state, action, obs_position, num_movables, body_mask, reward, termination, is_safe, is_effective and episode_return are required");
+  w->d.buf = *b;
+  w->buffers_bound = true;
+  return 0;
+}
+
+int b2s_reset(B2SWorld* w, const uint8_t* mask, uint64_t seed, void* stream) {
+  NEED_READY(w);
+  b2s_launch_reset(w->d, mask, seed, (cudaStream_t)stream);
+  return check_launch(w, "reset");
+}
+
+int b2s_settle(B2SWorld* w, float lin, float ang, int max_steps, void* stream) {
+  NEED_READY(w);
+  if (max_steps < 1) return fail(B2S_E_INVALID, "b2s_settle: max_steps < 1");
+  b2s_launch_substeps(w->d, 0, MODE_SETTLE, lin, ang, max_steps, (cudaStream_t)stream);
+  return check_launch(w, "settle");
+}
+
+int b2s_step(B2SWorld* w, int n, void* stream) {
+  NEED_READY(w);
+  if (n < 0) return fail(B2S_E_INVALID, "b2s_step: n < 0");
+  if (n == 0) return 0;
+  b2s_launch_substeps(w->d, n, MODE_RAW, 0, 0, 0, (cudaStream_t)stream);
+  return check_launch(w, "step");
+}
+
+int b2s_step_staged(B2SWorld* w, int n, void* stream) {
+  NEED_READY(w);
+  if (n < 0) return fail(B2S_E_INVALID, "b2s_step_staged: n < 0");
+  int64_t launches = 0;
+  b2s_launch_staged(w->d, n, (cudaStream_t)stream, &launches);
+  return check_launch(w, "step_staged", (int)launches);
+}
+
+int b2s_set_action(B2SWorld* w, void* stream) {
+  NEED_READY(w);
+  b2s_launch_set_action(w->d, (cudaStream_t)stream);
+  return check_launch(w, "set_action");
+}
+
+int b2s_env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream) {
+  NEED_READY(w);
+  if (n < 0) return fail(B2S_E_INVALID, "b2s_env_substeps: n < 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(w->d.unfinished, 0, sizeof(int), s));
+  b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, s);
+  int rc = check_launch(w, "env_substeps");
+  if (rc) return rc;
+  if (unfinished_host) {
+    CU(cudaMemcpyAsync(w->unfinished_pinned, w->d.unfinished, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *unfinished_host = *w->unfinished_pinned;
+  }
+  return 0;
+}
+
+int b2s_env_step(B2SWorld* w, int chunk, int max_substeps, void* stream) {
+  NEED_READY(w);
+  if (chunk < 1) return fail(B2S_E_INVALID, "b2s_env_step: chunk < 1");
+  int rc = b2s_set_action(w, stream);
+  if (rc) return rc;
+  int done = 0, unfinished = 1;
+  while (unfinished > 0 && done < max_substeps) {
+    rc = b2s_env_substeps(w, chunk, &unfinished, stream);
+    if (rc) return rc;
+    done += chunk;
+  }
+  return 0;
+}
+
+int b2s_arm_move_to_gripper_pose(B2SWorld* w, const float* pose, const uint8_t* mask, void* stream) {
+  NEED_READY(w);
+  if (!pose) return fail(B2S_E_INVALID, "b2s_arm_move_to_gripper_pose: pose is NULL");
+  b2s_launch_arm_cmd(w->d, 0, pose, mask, nullptr, (cudaStream_t)stream);
+  return check_launch(w, "arm_cmd");
+}
+int b2s_arm_move_to_joint_positions(B2SWorld* w, const float* q, const uint8_t* mask, void* stream) {
+  NEED_READY(w);
+  if (!q) return fail(B2S_E_INVALID, "b2s_arm_move_to_joint_positions: q is NULL");
+  b2s_launch_arm_cmd(w->d, 1, q, mask, nullptr, (cudaStream_t)stream);
+  return check_launch(w, "arm_cmd");
+}
+int b2s_arm_reset_targets(B2SWorld* w, const uint8_t* mask, void* stream) {
+  NEED_READY(w);
+  b2s_launch_arm_cmd(w->d, 2, nullptr, mask, nullptr, (cudaStream_t)stream);
+  return check_launch(w, "arm_cmd");
+}
+int b2s_arm_is_ready(B2SWorld* w, uint8_t* out, void* stream) {
+  NEED_READY(w);
+  if (!out) return fail(B2S_E_INVALID, "b2s_arm_is_ready: out is NULL");
+  b2s_launch_arm_cmd(w->d, 3, nullptr, nullptr, out, (cudaStream_t)stream);
+  return check_launch(w, "arm_cmd");
+}
+int b2s_inverse_kinematics(B2SWorld* w, const float* pose, const float* q_start, float* q_out, void* stream) {
+  NEED_READY(w);
+  if (!pose || !q_start || !q_out) return fail(B2S_E_INVALID, "b2s_inverse_kinematics: NULL argument");
+  b2s_launch_ik(w->d, pose, q_start, q_out, (cudaStream_t)stream);
+  return check_launch(w, "ik");
+}
+int b2s_forward_kinematics(B2SWorld* w, void* stream) {
+  NEED_READY(w);
+  b2s_launch_fk(w->d, (cudaStream_t)stream);
+  return check_launch(w, "fk");
+}
+int b2s_query_contacts(B2SWorld* w, uint8_t* arm_table, uint8_t* arm_movable, void* stream) {
+  NEED_READY(w);
+  b2s_launch_query_contacts(w->d, arm_table, arm_movable, (cudaStream_t)stream);
+  return check_launch(w, "query_contacts");
+}
+int b2s_observe(B2SWorld* w, void* stream) {
+  NEED_READY(w);
+  b2s_launch_observe(w->d, (cudaStream_t)stream);
+  return check_launch(w, "observe");
+}
+
+int b2s_set_camera(B2SWorld* w, const float* K, const float* R, const float* t, int per_env) {
+  NEED(w);
+  if (!w->scene_loaded) return fail(B2S_E_STATE, "b2s_set_camera: call b2s_load_scene first");
+  if (!K || !R || !t) return fail(B2S_E_INVALID, "b2s_set_camera: NULL argument");
+  const int B = w->d.B;
+  std::vector<float> cam((size_t)B * 21);
+  for (int e = 0; e < B; ++e) {
+    size_t o = per_env ? (size_t)e : 0;
+    memcpy(&cam[(size_t)e * 21], K + o * 9, 36); memcpy(&cam[(size_t)e * 21 + 9], R + o * 9, 36); memcpy(&cam[(size_t)e * 21 + 18], t + o * 3, 12);
+  }
+  CU(cudaSetDevice(w->device));
+  CU(cudaMemcpy(w->d.cam, cam.data(), cam.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+int b2s_render(B2SWorld* w, void* stream) {
+  NEED_READY(w);
+  if (!w->d.buf.depth || !w->d.buf.segmask) return fail(B2S_E_STATE, "b2s_render: depth/segmask buffers are not bound");
+  b2s_launch_render(w->d, (cudaStream_t)stream);
+  return check_launch(w, "render");
+}
+int b2s_point_cloud(B2SWorld* w, uint64_t seed, void* stream) {
+  NEED_READY(w);
+  if (!w->d.buf.depth || !w->d.buf.segmask || !w->d.buf.point_cloud) return fail(B2S_E_STATE, "b2s_point_cloud: depth/segmask/point_cloud buffers are not bound");
+  b2s_launch_point_cloud(w->d, seed, (cudaStream_t)stream);
+  return check_launch(w, "point_cloud");
+}
+int b2s_reward(B2SWorld* w, const float* prev_xy, const float* next_xy, void* stream) {
+  NEED_READY(w);
+  if (w->d.Nmax > 64) return fail(B2S_E_CAPACITY, "b2s_reward: max_movables > 64");
+  b2s_launch_reward(w->d, prev_xy, next_xy, (cudaStream_t)stream);
+  return check_launch(w, "reward");
+}
+
+// one ncclAllGather of the episode returns (replaces tools/parallel_run.py).  NCCL is resolved at run
+// time from the process (torch loads libnccl.so.2), so the library itself does not link against it.
+int b2s_allgather_returns(B2SWorld* w, void* nccl_comm, float* out_dev, void* stream) {
+  NEED_READY(w);
+  if (!nccl_comm || !out_dev) return fail(B2S_E_INVALID, "b2s_allgather_returns: NULL argument");
+  typedef int (*allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+  static allgather_fn fn = nullptr;
+  if (!fn) {
+    fn = (allgather_fn)dlsym(RTLD_DEFAULT, "ncclAllGather");
+    if (!fn) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) fn = (allgather_fn)dlsym(h, "ncclAllGather");
+    }
+    if (!fn) return fail(B2S_E_UNSUPPORTED, "b2s_allgather_returns: ncclAllGather not found in this process");
+  }
+  const int ncclFloat32 = 7;
+  int rc = fn(w->d.buf.episode_return, out_dev, (size_t)w->d.B, ncclFloat32, nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) return fail(B2S_E_CUDA, "ncclAllGather failed with %d", rc);
+  return 0;
+}
+
+int b2s_array(B2SWorld* w, int which, void** dev_ptr, int64_t* bytes) {
+  NEED(w);
+  if (!w->scene_loaded) return fail(B2S_E_STATE, "b2s_array: call b2s_load_scene first");
+  if (which < 0 || which >= B2S_ARR_COUNT || !dev_ptr || !bytes) return fail(B2S_E_INVALID, "b2s_array: bad id %d", which);
+  if (which == B2S_ARR_MANIFOLD_KEYS || which == B2S_ARR_MANIFOLD_NPTS || which == B2S_ARR_MANIFOLD_PTS) {
+    // gather the current ping-pong side into the export arrays (default stream, synchronous)
+    CU(cudaSetDevice(w->device));
+    CU(cudaDeviceSynchronize());
+    b2s_launch_export_manifolds(w->d, w->exp_keys, w->exp_npts, w->exp_pts, 0);
+    int rc = check_launch(w, "export_manifolds");
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+  }
+  *dev_ptr = w->arr_ptr[which];
+  *bytes = (int64_t)w->arr_bytes[which];
+  return 0;
+}
+
+int64_t b2s_launch_count(const B2SWorld* w) { return w ? w->launches : 0; }
+
+int64_t b2s_substeps_executed(B2SWorld* w, void* stream) {
+  if (!w || !w->scene_loaded) return -1;
+  unsigned long long v = 0;
+  cudaStreamSynchronize((cudaStream_t)stream);
+  if (cudaMemcpy(&v, w->d.substeps, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
+}
+
+static int se3(int op, const float* a, const float* b, float* out, int n, void* stream) {
+  if (!a || !out || n < 0) return fail(B2S_E_INVALID, "b2s_se3: bad argument");
+  if (n == 0) return 0;
+  b2s_launch_se3(op, a, b, out, n, (cudaStream_t)stream);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(B2S_E_CUDA, "se3 launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+int b2s_se3_quat_from_euler(const float* e, float* q, int n, void* s) { return se3(0, e, nullptr, q, n, s); }
+int b2s_se3_euler_from_quat(const float* q, float* e, int n, void* s) { return se3(1, q, nullptr, e, n, s); }
+int b2s_se3_matrix_from_quat(const float* q, float* m, int n, void* s) { return se3(2, q, nullptr, m, n, s); }
+int b2s_se3_quat_multiply(const float* a, const float* b, float* o, int n, void* s) { if (!b) return fail(B2S_E_INVALID, "b2s_se3: NULL"); return se3(3, a, b, o, n, s); }
+int b2s_se3_pose_inverse(const float* p, float* o, int n, void* s) { return se3(4, p, nullptr, o, n, s); }
+int b2s_se3_pose_transform(const float* a, const float* b, float* o, int n, void* s) { if (!b) return fail(B2S_E_INVALID, "b2s_se3: NULL"); return se3(5, a, b, o, n, s); }
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// b2s_dev.cuh -- device-side world description shared by the kernels and the host API.
+//
+// Data layout in HBM (all SoA over environments, env index fastest where one
+// thread handles one env, env-major blocks where one warp handles one env):
+//   body_state  float [13][B][Nmax]   px py pz qx qy qz qw vx vy vz wx wy wz  (torch-owned)
+//   joint_state float [2][7][B]       q, qdot                                   (torch-owned)
+//   manifolds   ping-pong  keys int32 [2][B][M], npts int32 [2][B][M],
+//               pts float [2][B][M][4][16]; parity int32 [B]
+//   scene       verts float4 [V], hull table, asset table, statics: read-only
+// One environment is stepped by one warp; all per-substep intermediates (body
+// table, collider table, AABBs, pair list, contact rows) live in that warp's
+// slice of shared memory and never touch HBM.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2s.h"
+#include "../../include/b2s_geom.h"
+#include "../../include/b2s_math.h"
+
+typedef b2s_v3 V3;
+typedef b2s_q4 Q4;
+typedef b2s_m3 M3;
+
+#define B2S_TYPE_STATIC 0
+#define B2S_TYPE_KINEMATIC 1
+#define B2S_TYPE_DYNAMIC 2
+
+#define EPA_MAXV 48
+#define EPA_MAXF 192
+#define FULL 0xffffffffu
+
+struct DHull {
+  int voff, vcnt;
+  float margin, rad;
+  float lc[3], lh[3];
+  int poff, pcnt;
+};
+
+struct DAsset {
+  int hoff, hcnt;
+  float half[3];
+  float pad;
+};
+
+// scalar scene data small enough to sit in the kernel parameter block / constant bank
+struct DArm {
+  float base[7];
+  float joint_origin[B2S_NUM_JOINTS][7];
+  float joint_axis[B2S_NUM_JOINTS][3];
+  float lower[B2S_NUM_JOINTS], upper[B2S_NUM_JOINTS], max_vel[B2S_NUM_JOINTS];
+  float ee[7];
+  int num_links;
+  int link_joint[B2S_MAX_LINKS];
+  int link_asset[B2S_MAX_LINKS];
+  float link_pose[B2S_MAX_LINKS][7];
+  float friction;
+};
+
+struct DLayout {
+  float tile_size, tile_offset[2];
+  int num_region, num_goal, num_target, num_obstacle;
+  float region[B2S_MAX_TILES][2], goal[B2S_MAX_TILES][2], target[B2S_MAX_TILES][2], obstacle[B2S_MAX_TILES][2];
+  float scale_range[2], mass_range[2], friction_range[2];
+  float pose_x[2], pose_y[2], pose_z[2], pose_roll[2], pose_pitch[2], pose_yaw[2];
+  float placement_margin;
+  int min_movables;
+  float table_height_range[2], safe_drop_height;
+  int num_movable_assets, num_target_assets;
+};
+
+// per-warp shared-memory carve-up (offsets in 4-byte words from the warp's base)
+struct SmemLayout {
+  int body, col, pairs, oldkeys, cmk, con, order, colstart, used, stage, fk, simplex, words;
+};
+
+#define BODY_STRIDE 35   // pos3 R9 vel3 ang3 invm1 invI9 fric1 type1 quat4 = 34 (+1 pad, odd stride)
+#define COL_STRIDE 13    // hull slot type|flags scale margin rad amin3 amax3 = 12 (+1)
+#define CON_STRIDE 65    // see k_contacts: 3 rows x 19 + slotA slotB mu m|k colour = 62 (+pad, odd)
+#define ROW_WORDS 19     // dir3 angA3 angB3 iangA3 iangB3 inv_d d bias lambda
+#define FK_WORDS 96      // frames 7x7, axes 7x3, origins 7x3 = 91
+
+struct DWorld {
+  B2SParams P;
+  int B, Nmax, Ns, L, NB, Hmax;
+  // scene (device, read-only)
+  const float4* verts;
+  const DHull* hulls;
+  const DAsset* assets;
+  const float4* planes;
+  const int* static_asset;
+  const float* static_pose;      // [Ns][7]
+  const float* static_friction;
+  const uint32_t* static_flags;
+  const int* movable_assets;
+  const int* target_assets;
+  const DArm* arm;
+  const DLayout* layout;
+  // caller-owned buffers
+  B2SBuffers buf;
+  // world-owned arrays
+  int32_t* man_keys;   // [2][B][M]
+  int32_t* man_npts;   // [2][B][M]
+  float* man_pts;      // [2][B][M][4][16]
+  int32_t* man_parity; // [B]
+  int32_t* num_manifolds;
+  int32_t* pair_keys;
+  int32_t* num_pairs;
+  int32_t* phase;
+  int32_t* num_steps;
+  float* ctrl;
+  int32_t* ctrl_flags;
+  double* ctrl_time;
+  float* link_poses;
+  float* link_vel;
+  float* mov_params;
+  float* table_dz;
+  int32_t* error_flags;
+  float* waypoints;
+  float* status;
+  int32_t* contact_flags;
+  int32_t* phase_state;
+  int32_t* solver_stats;
+  int32_t* ncol;
+  int32_t* col_slot;
+  int32_t* col_hull;
+  int32_t* reset_count;
+  float* prev_xy;
+  float* cam;            // [B][21]
+  unsigned long long* substeps;   // device counter: total env-substeps executed
+  int32_t* unfinished;            // device counter used by env_substeps
+  // staged-mode scratch: contact rows / body velocities dumped between kernels
+  float* stage_rows;     // [B][max_contacts][CON_STRIDE]
+  float* stage_body;     // [B][NB][BODY_STRIDE]
+  int32_t* stage_meta;   // [B][4 + max_contacts + 65]   nc, ncolours, pad, pad, order[], colstart[]
+  SmemLayout sm;
+};
+
+enum { MODE_RAW = 0, MODE_ENV = 1, MODE_SETTLE = 2 };
+enum { SPLIT_NONE = 0, SPLIT_PRE = 1, SPLIT_POST = 2 };   // staged mode: stop before / resume after PGS
+
+// host launchers (defined next to their kernels)
+void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, cudaStream_t s);
+void b2s_launch_staged(const DWorld& W, int n, cudaStream_t s, int64_t* launches);
+void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s);
+void b2s_launch_set_action(const DWorld& W, cudaStream_t s);
+void b2s_launch_observe(const DWorld& W, cudaStream_t s);
+void b2s_launch_reward(const DWorld& W, const float* prev_xy, const float* next_xy, cudaStream_t s);
+void b2s_launch_arm_cmd(const DWorld& W, int cmd, const float* data, const uint8_t* mask, uint8_t* out, cudaStream_t s);
+void b2s_launch_ik(const DWorld& W, const float* pose, const float* q_start, float* q_out, cudaStream_t s);
+void b2s_launch_fk(const DWorld& W, cudaStream_t s);
+void b2s_launch_query_contacts(const DWorld& W, uint8_t* arm_table, uint8_t* arm_movable, cudaStream_t s);
+void b2s_launch_export_manifolds(const DWorld& W, int32_t* keys, int32_t* npts, float* pts, cudaStream_t s);
+void b2s_launch_render(const DWorld& W, cudaStream_t s);
+void b2s_launch_point_cloud(const DWorld& W, uint64_t seed, cudaStream_t s);
+void b2s_launch_se3(int op, const float* a, const float* b, float* out, int n, cudaStream_t s);
+size_t b2s_smem_bytes(const DWorld& W);

@@ -1,0 +1,1432 @@
+// b2s_step.cu -- the per-substep hot path, one environment per warp.
+//
+// Replaces, for B environments at once, what the reference does per substep in
+// Python + pybullet: Simulator.step (simulator.py:94-103),
+// ControllableBody.update (controllable_body.py:387-413), pybullet.stepSimulation
+// (bullet_physics.py:106-109: gravity, AABB broad phase, GJK/EPA narrow phase,
+// persistent manifolds, PGS contact/friction solve, integration) and the PushEnv
+// phase machine (push_env.py:631-937).
+//
+// Design: a warp owns one environment for the whole launch and loops over the
+// requested substeps with every intermediate (body table, collider AABBs, pair
+// list, contact rows) in its slice of shared memory; only the persistent state
+// (13 floats per movable, 14 per arm, the <=4-point manifolds) goes back to HBM.
+// Lanes split the work inside a stage: one hull vertex per lane in the GJK/EPA
+// support function (exact warp max via redux on order-preserving keys), one
+// collider per lane for AABBs, ballot-compacted pair lists, one contact per lane
+// for Jacobian rows, and the PGS sweep runs one colour of body-disjoint contacts
+// per step so Gauss-Seidel order is preserved exactly.  The residual test is a
+// warp reduce.  All fp32 arithmetic is ordered exactly as in oracle/ (no FMA
+// contraction) so integer outputs match bit for bit.
+#include "b2s_dev.cuh"
+
+#define LD3(p) v3((p)[0], (p)[1], (p)[2])
+#define ST3(p, v) { (p)[0] = (v).x; (p)[1] = (v).y; (p)[2] = (v).z; }
+
+__device__ __forceinline__ M3 ldm3(const float* p) { M3 m; m.r0 = LD3(p); m.r1 = LD3(p + 3); m.r2 = LD3(p + 6); return m; }
+__device__ __forceinline__ void stm3(float* p, M3 m) { ST3(p, m.r0); ST3(p + 3, m.r1); ST3(p + 6, m.r2); }
+
+// body record offsets
+#define BO_POS 0
+#define BO_R 3
+#define BO_VEL 12
+#define BO_ANG 15
+#define BO_INVM 18
+#define BO_INVI 19
+#define BO_FRIC 28
+#define BO_TYPE 29
+#define BO_QUAT 30
+// collider record offsets
+#define CO_HULL 0
+#define CO_SLOT 1
+#define CO_TYPE 2
+#define CO_SCALE 3
+#define CO_MARGIN 4
+#define CO_RAD 5
+#define CO_AMIN 6
+#define CO_AMAX 9
+// contact record offsets
+#define CN_SLOTA 57
+#define CN_SLOTB 58
+#define CN_MU 59
+#define CN_MK 60
+#define CN_COLOUR 61
+#define CN_INVMA 62
+#define CN_INVMB 63
+// row offsets
+#define RW_DIR 0
+#define RW_ANGA 3
+#define RW_ANGB 6
+#define RW_IANGA 9
+#define RW_IANGB 12
+#define RW_INVD 15
+#define RW_D 16
+#define RW_BIAS 17
+#define RW_LAMBDA 18
+
+struct Xf { V3 p; Q4 q; };
+__device__ __forceinline__ Xf xf_from(const float* a) { Xf t; t.p = v3(a[0], a[1], a[2]); t.q = q4(a[3], a[4], a[5], a[6]); return t; }
+__device__ __forceinline__ Xf xf_mul(Xf a, Xf b) { Xf t; t.p = a.p + qrot(a.q, b.p); t.q = qmul(a.q, b.q); return t; }
+__device__ __forceinline__ void xf_store(Xf t, float* o) { o[0] = t.p.x; o[1] = t.p.y; o[2] = t.p.z; o[3] = t.q.x; o[4] = t.q.y; o[5] = t.q.z; o[6] = t.q.w; }
+
+__device__ __forceinline__ M3 inv_inertia_world(M3 R, V3 d) {
+  V3 a0 = vmul(R.r0, d), a1 = vmul(R.r1, d), a2 = vmul(R.r2, d);
+  M3 m;
+  m.r0 = v3(dot(a0, R.r0), dot(a0, R.r1), dot(a0, R.r2));
+  m.r1 = v3(dot(a1, R.r0), dot(a1, R.r1), dot(a1, R.r2));
+  m.r2 = v3(dot(a2, R.r0), dot(a2, R.r1), dot(a2, R.r2));
+  return m;
+}
+
+// ----------------------------------------------------------------- arm ------
+
+// serial chain: frames after each joint, world joint axes and origins (uniform over the warp)
+__device__ __forceinline__ void fk_chain(const DArm* __restrict__ arm, const float* q, Xf* frame, V3* ax, V3* org) {
+  Xf T = xf_from(arm->base);
+#pragma unroll
+  for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
+    Xf Tj = xf_mul(T, xf_from(arm->joint_origin[j]));
+    V3 a = v3(arm->joint_axis[j][0], arm->joint_axis[j][1], arm->joint_axis[j][2]);
+    ax[j] = qrot(Tj.q, a);
+    org[j] = Tj.p;
+    T.p = Tj.p;
+    T.q = qmul(Tj.q, q_axis_angle(a, q[j]));
+    frame[j] = T;
+  }
+}
+
+// damped-least-squares IK, uniform over the warp (every lane computes the same values)
+__device__ void arm_ik(const DWorld& W, const float* target, const float* q_start, float* q_out) {
+  const DArm* arm = W.arm;
+  const B2SParams& P = W.P;
+  float q[B2S_NUM_JOINTS];
+#pragma unroll
+  for (int j = 0; j < B2S_NUM_JOINTS; ++j) q[j] = q_start[j];
+  Xf tgt = xf_from(target);
+  Xf eel = xf_from(arm->ee);
+  const float res2 = P.ik_residual * P.ik_residual;
+  for (int it = 0; it < P.ik_max_iters; ++it) {
+    Xf frame[B2S_NUM_JOINTS];
+    V3 ax[B2S_NUM_JOINTS], org[B2S_NUM_JOINTS];
+    fk_chain(arm, q, frame, ax, org);
+    Xf ee = xf_mul(frame[B2S_NUM_JOINTS - 1], eel);
+    V3 ep = tgt.p - ee.p;
+    V3 er = q_to_rotvec(qmul(tgt.q, qconj(ee.q)));
+    if (len2(ep) < res2 && len2(er) < res2) break;
+    float J[6][B2S_NUM_JOINTS];
+#pragma unroll
+    for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
+      V3 jv = cross(ax[j], ee.p - org[j]);
+      J[0][j] = jv.x; J[1][j] = jv.y; J[2][j] = jv.z;
+      J[3][j] = ax[j].x; J[4][j] = ax[j].y; J[5][j] = ax[j].z;
+    }
+    float A[36], y[6] = {ep.x, ep.y, ep.z, er.x, er.y, er.z};
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < B2S_NUM_JOINTS; ++j) s = s + J[r][j] * J[c][j];
+        if (r == c) s = s + P.ik_damping * P.ik_damping;
+        A[r * 6 + c] = s;
+      }
+    if (!b2s_chol6_solve(A, y)) break;
+    float dq[B2S_NUM_JOINTS], m = 0.0f;
+#pragma unroll
+    for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) s = s + J[r][j] * y[r];
+      dq[j] = s;
+      m = fmaxf(m, fabsf(s));
+    }
+    float k = (m > P.ik_max_step) ? (P.ik_max_step / m) : 1.0f;
+#pragma unroll
+    for (int j = 0; j < B2S_NUM_JOINTS; ++j) q[j] = q[j] + dq[j] * k;
+  }
+#pragma unroll
+  for (int j = 0; j < B2S_NUM_JOINTS; ++j) q_out[j] = fminf(arm->upper[j], fmaxf(arm->lower[j], q[j]));
+}
+
+// FK of all collision links + end effector into global link_poses/link_vel and (optionally) the
+// shared body table.  Chain is uniform; links are spread over lanes.
+__device__ void arm_fk_links(const DWorld& W, int e, int lane, const float* q, const float* qd, float* fk /*smem*/,
+                             float* body /*smem or NULL*/) {
+  const DArm* arm = W.arm;
+  {
+    Xf frame[B2S_NUM_JOINTS];
+    V3 ax[B2S_NUM_JOINTS], org[B2S_NUM_JOINTS];
+    fk_chain(arm, q, frame, ax, org);
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
+        xf_store(frame[j], fk + j * 7);
+        ST3(fk + 49 + j * 3, ax[j]);
+        ST3(fk + 70 + j * 3, org[j]);
+      }
+    }
+    __syncwarp();
+  }
+  const int L = W.L;
+  if (lane < L) {
+    int k = lane;
+    int jj = arm->link_joint[k];
+    Xf base = (jj < 0) ? xf_from(arm->base) : xf_from(fk + jj * 7);
+    Xf T = xf_mul(base, xf_from(arm->link_pose[k]));
+    V3 v = v3(0, 0, 0), om = v3(0, 0, 0);
+    for (int i = 0; i <= jj; ++i) {
+      V3 a = LD3(fk + 49 + i * 3), o = LD3(fk + 70 + i * 3);
+      v = v + cross(a, T.p - o) * qd[i];
+      om = om + a * qd[i];
+    }
+    float* lp = W.link_poses + ((size_t)e * (L + 1) + k) * 7;
+    xf_store(T, lp);
+    float* lv = W.link_vel + ((size_t)e * L + k) * 6;
+    lv[0] = v.x; lv[1] = v.y; lv[2] = v.z; lv[3] = om.x; lv[4] = om.y; lv[5] = om.z;
+    if (body) {
+      float* b = body + (W.Ns + k) * BODY_STRIDE;
+      ST3(b + BO_POS, T.p);
+      stm3(b + BO_R, q_to_m3(T.q));
+      ST3(b + BO_VEL, v); ST3(b + BO_ANG, om);
+      b[BO_INVM] = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) b[BO_INVI + i] = 0.0f;
+      b[BO_FRIC] = arm->friction;
+      b[BO_TYPE] = __int_as_float(B2S_TYPE_KINEMATIC);
+      b[BO_QUAT] = T.q.x; b[BO_QUAT + 1] = T.q.y; b[BO_QUAT + 2] = T.q.z; b[BO_QUAT + 3] = T.q.w;
+    }
+  } else if (lane == L) {
+    Xf T = xf_mul(xf_from(fk + 6 * 7), xf_from(arm->ee));
+    xf_store(T, W.link_poses + ((size_t)e * (L + 1) + L) * 7);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ bool joints_reached(const DWorld& W, int e, int lane, const float* c, int f1, int f2) {
+  if (!f1) return true;
+  bool ok = true;
+  if (lane < 7) {
+    float q = W.buf.joint_state[(0 * 7 + lane) * W.B + e], qd = W.buf.joint_state[(1 * 7 + lane) * W.B + e];
+    bool pr = fabsf(c[9 + lane] - q) < c[16];
+    bool vr = f2 ? true : (fabsf(0.0f - qd) < c[17]);
+    ok = pr && vr;
+  }
+  return __all_sync(FULL, ok);
+}
+
+// ControllableBody.update + POSITION_CONTROL motor (oracle/b2o_arm.cpp arm_update)
+__device__ void stage_arm(const DWorld& W, int e, int lane) {
+  const B2SParams& P = W.P;
+  float* c = W.ctrl + (size_t)e * B2S_CTRL_FLOATS;
+  int32_t* f = W.ctrl_flags + (size_t)e * 4;
+  double* T = W.ctrl_time + (size_t)e * 5;
+  int f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3];
+  const int n = W.num_steps[e];
+  const double now = P.time_step * (double)n;
+  bool ik_updated = false;
+  __syncwarp();
+  if (f0 && n % P.check_done_interval == 0) { if (now >= T[1]) f0 = 0; }
+  if (f0 && (n % P.ik_interval == 0 || !f1)) {
+    float q[7], qo[7], tgt[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { q[j] = W.buf.joint_state[(0 * 7 + j) * W.B + e]; tgt[j] = c[j]; }
+    arm_ik(W, tgt, q, qo);
+    double t0 = T[0], t1 = T[1];
+    float th0 = c[7], th1 = c[8];
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 7; ++j) c[9 + j] = qo[j];
+      c[16] = th0; c[17] = th1;
+      T[2] = t0; T[3] = t1;
+    }
+    __syncwarp();
+    f1 = 1; f2 = 0;
+    ik_updated = true;
+    if (joints_reached(W, e, lane, c, f1, f2)) f0 = 0;
+  }
+  if (f1 && (n % P.check_done_interval == 0 || ik_updated)) {
+    bool done = (now >= T[3]);
+    bool reached = joints_reached(W, e, lane, c, f1, f2);
+    if (done || reached) f1 = 0;
+  }
+  if (f1) {
+    if (lane < 7) { c[18 + lane] = c[9 + lane]; c[25 + lane] = 0.0f; }
+    f3 = 1;
+  }
+  __syncwarp();
+  const float dt = (float)P.time_step;
+  if (lane < 7) {
+    const int j = lane;
+    float q = W.buf.joint_state[(0 * 7 + j) * W.B + e], qd = W.buf.joint_state[(1 * 7 + j) * W.B + e];
+    float v = 0.0f;
+    if (f3) {
+      v = (P.position_gain * (c[18 + j] - q) / dt + qd) + P.velocity_gain * (c[25 + j] - qd);
+      if (P.clamp_joint_velocity) {
+        float vm = P.limb_velocity_ratio * W.arm->max_vel[j];
+        v = fminf(vm, fmaxf(-vm, v));
+      }
+      float qn = q + v * dt;
+      if (qn > W.arm->upper[j]) v = (W.arm->upper[j] - q) / dt;
+      if (qn < W.arm->lower[j]) v = (W.arm->lower[j] - q) / dt;
+    }
+    W.buf.joint_state[(1 * 7 + j) * W.B + e] = v;
+  }
+  if (lane == 0) { f[0] = f0; f[1] = f1; f[2] = f2; f[3] = f3; }
+  __syncwarp();
+}
+
+// SawyerSim.is_limb_ready with its side effects (oracle arm_is_ready)
+__device__ int arm_is_ready(const DWorld& W, int e, int lane) {
+  float* c = W.ctrl + (size_t)e * B2S_CTRL_FLOATS;
+  int32_t* f = W.ctrl_flags + (size_t)e * 4;
+  double* T = W.ctrl_time + (size_t)e * 5;
+  __syncwarp();
+  int f0 = f[0], f1 = f[1], f2 = f[2];
+  const double now = W.P.time_step * (double)W.num_steps[e];
+  if (!f0 || now >= T[1]) f0 = 0;
+  bool jd = (!f1) || (now >= T[3]) || joints_reached(W, e, lane, c, f1, f2);
+  if (jd) f1 = 0;
+  __syncwarp();
+  if (lane == 0) { f[0] = f0; f[1] = f1; }
+  __syncwarp();
+  return (!f0 && !f1) ? 1 : 0;
+}
+
+__device__ void arm_set_link_target(const DWorld& W, int e, int lane, const float* pose) {
+  float* c = W.ctrl + (size_t)e * B2S_CTRL_FLOATS;
+  double* T = W.ctrl_time + (size_t)e * 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c[k] = pose[k];
+    c[7] = W.P.joint_pos_threshold; c[8] = W.P.joint_vel_threshold;
+    double now = W.P.time_step * (double)W.num_steps[e];
+    T[0] = now; T[1] = now + (double)W.P.limb_timeout;
+    W.ctrl_flags[(size_t)e * 4 + 0] = 1;
+    W.ctrl_flags[(size_t)e * 4 + 1] = 0;          // reset_targets() precedes every set
+  }
+  __syncwarp();
+}
+__device__ void arm_set_joint_target(const DWorld& W, int e, int lane, const float* q) {
+  float* c = W.ctrl + (size_t)e * B2S_CTRL_FLOATS;
+  double* T = W.ctrl_time + (size_t)e * 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c[9 + k] = q[k];
+    c[16] = W.P.joint_pos_threshold; c[17] = W.P.joint_vel_threshold;
+    double now = W.P.time_step * (double)W.num_steps[e];
+    T[2] = now; T[3] = now + (double)W.P.limb_timeout;
+    W.ctrl_flags[(size_t)e * 4 + 0] = 0;
+    W.ctrl_flags[(size_t)e * 4 + 1] = 1;
+    W.ctrl_flags[(size_t)e * 4 + 2] = 0;
+  }
+  __syncwarp();
+}
+
+// -------------------------------------------------------------- support ----
+
+struct ColRef { V3 pos; M3 R; float scale, margin; int voff, vcnt; V3 cen; };
+
+__device__ __forceinline__ ColRef col_ref(const DWorld& W, const float* col, const float* body, int c) {
+  const float* cr = col + c * COL_STRIDE;
+  const float* b = body + __float_as_int(cr[CO_SLOT]) * BODY_STRIDE;
+  ColRef r;
+  r.pos = LD3(b + BO_POS); r.R = ldm3(b + BO_R);
+  r.scale = cr[CO_SCALE]; r.margin = cr[CO_MARGIN];
+  const DHull* H = W.hulls + __float_as_int(cr[CO_HULL]);
+  r.voff = H->voff; r.vcnt = H->vcnt;
+  r.cen = (LD3(cr + CO_AMIN) + LD3(cr + CO_AMAX)) * 0.5f;
+  return r;
+}
+
+// argmax_i v_i . d over the hull's vertices (first maximum), one or two vertices per lane
+__device__ __forceinline__ int support(const DWorld& W, const ColRef& c, V3 d, V3* p, int lane) {
+  V3 dl = mtmul(c.R, d);
+  float best = 0.0f;
+  int bi = 0x7fffffff;
+  bool has = false;
+  if (lane < c.vcnt) {
+    float4 v = __ldg(W.verts + c.voff + lane);
+    best = dot(v3(v.x, v.y, v.z), dl); bi = lane; has = true;
+  }
+  if (lane + 32 < c.vcnt) {
+    float4 v = __ldg(W.verts + c.voff + lane + 32);
+    float t = dot(v3(v.x, v.y, v.z), dl);
+    if (t > best) { best = t; bi = lane + 32; }
+  }
+  unsigned key = has ? f2ord(best + 0.0f) : 0u;
+  unsigned m = __reduce_max_sync(FULL, key);
+  unsigned cand = (has && key == m) ? (unsigned)bi : 0x7fffffffu;
+  int idx = (int)__reduce_min_sync(FULL, cand);
+  float4 v = __ldg(W.verts + c.voff + idx);
+  *p = c.pos + mmul(c.R, v3(v.x, v.y, v.z) * c.scale);
+  return idx;
+}
+
+// ------------------------------------------------------------------ GJK ----
+// simplex in shared memory: w[4][3] a[4][3] b[4][3] ia[4] ib[4] n  (45 words)
+#define SX_W 0
+#define SX_A 12
+#define SX_B 24
+#define SX_IA 36
+#define SX_IB 40
+#define SX_N 44
+
+__device__ int gjk(const DWorld& W, const ColRef& A, const ColRef& B, float limit, float* sx, V3* v_out, V3* pa,
+                   V3* pb, int lane) {
+  V3 v = A.cen - B.cen;
+  if (len2(v) < 1e-12f) v = v3(1.0f, 0.0f, 0.0f);
+  int n = 0;
+  bool have = false;
+  float bary[4] = {0, 0, 0, 0};
+  int status = 1;
+  for (int it = 0; it < W.P.gjk_max_iters; ++it) {
+    V3 a, b;
+    int ia = support(W, A, -v, &a, lane);
+    int ib = support(W, B, v, &b, lane);
+    V3 ww = a - b;
+    float vv = dot(v, v), vw = dot(v, ww);
+    if (vw > 0.0f && vw * vw > (limit * limit) * vv) return 0;
+    bool dup = false;
+    for (int k = 0; k < n; ++k) if (__float_as_int(sx[SX_IA + k]) == ia && __float_as_int(sx[SX_IB + k]) == ib) dup = true;
+    if (dup) break;
+    if (have && (vv - vw) <= vv * 1e-6f) break;
+    __syncwarp();
+    if (lane == 0) {
+      ST3(sx + SX_W + n * 3, ww); ST3(sx + SX_A + n * 3, a); ST3(sx + SX_B + n * 3, b);
+      sx[SX_IA + n] = __int_as_float(ia); sx[SX_IB + n] = __int_as_float(ib);
+    }
+    __syncwarp();
+    n = n + 1;
+    V3 wl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wl[k] = LD3(sx + SX_W + k * 3);
+    b2s_simplex_result r;
+    b2s_closest_simplex(wl, n, &r);
+    if (r.inside) { status = 2; break; }
+    // compact to the vertices that support the closest point
+    float rec[4][11];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t) { rec[k][t] = sx[SX_W + k * 3 + t]; rec[k][3 + t] = sx[SX_A + k * 3 + t]; rec[k][6 + t] = sx[SX_B + k * 3 + t]; }
+      rec[k][9] = sx[SX_IA + k]; rec[k][10] = sx[SX_IB + k];
+    }
+    __syncwarp();
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < n && (r.used & (1 << k))) {
+        if (lane == 0) {
+#pragma unroll
+          for (int t = 0; t < 3; ++t) { sx[SX_W + m * 3 + t] = rec[k][t]; sx[SX_A + m * 3 + t] = rec[k][3 + t]; sx[SX_B + m * 3 + t] = rec[k][6 + t]; }
+          sx[SX_IA + m] = rec[k][9]; sx[SX_IB + m] = rec[k][10];
+        }
+        float bk = r.bary[k];
+        if (m == 0) bary[0] = bk; else if (m == 1) bary[1] = bk; else if (m == 2) bary[2] = bk; else bary[3] = bk;
+        ++m;
+      }
+    }
+    __syncwarp();
+    n = m;
+    float nv = len2(r.v);
+    if (nv < 1e-14f) { status = 2; break; }
+    if (have && nv >= vv) { v = r.v; break; }
+    v = r.v;
+    have = true;
+  }
+  __syncwarp();
+  if (lane == 0) sx[SX_N] = __int_as_float(n);
+  __syncwarp();
+  if (status == 2) return 2;
+  if (!have) return 0;
+  V3 xa = v3(0, 0, 0), xb = v3(0, 0, 0);
+  for (int k = 0; k < n; ++k) {
+    float bk = (k == 0) ? bary[0] : (k == 1) ? bary[1] : (k == 2) ? bary[2] : bary[3];
+    xa = xa + LD3(sx + SX_A + k * 3) * bk;
+    xb = xb + LD3(sx + SX_B + k * 3) * bk;
+  }
+  *pa = xa; *pb = xb; *v_out = v;
+  return 1;
+}
+
+// ------------------------------------------------------------------ EPA ----
+// scratch (aliases the contact-row area): W[48][3] PA[48][3] PB[48][3] IA[48] IB[48]
+//   faces: idx[192] (i0 | i1<<8 | i2<<16 | alive<<24), n[192][3], d[192]; edges[192]; newfaces n/d staged in place
+#define EP_W 0
+#define EP_PA (EPA_MAXV * 3)
+#define EP_PB (EPA_MAXV * 6)
+#define EP_IA (EPA_MAXV * 9)
+#define EP_IB (EPA_MAXV * 10)
+#define EP_FI (EPA_MAXV * 11)
+#define EP_FN (EP_FI + EPA_MAXF)
+#define EP_FD (EP_FN + EPA_MAXF * 3)
+#define EP_ED (EP_FD + EPA_MAXF)
+#define EP_VIS (EP_ED + EPA_MAXF)
+#define EP_WORDS (EP_VIS + EPA_MAXF)
+
+__device__ __forceinline__ bool epa_face_plane(const float* ep, int i0, int i1, int i2, V3* n, float* d) {
+  V3 p0 = LD3(ep + EP_W + i0 * 3);
+  V3 nn = cross(LD3(ep + EP_W + i1 * 3) - p0, LD3(ep + EP_W + i2 * 3) - p0);
+  float l2 = len2(nn);
+  if (l2 < 1e-20f) return false;
+  nn = nn * (1.0f / sqrtf(l2));
+  *n = nn; *d = dot(nn, p0);
+  return true;
+}
+
+// add a support point to the GJK simplex (uniform); returns false when it is already there
+__device__ bool sx_add(const DWorld& W, const ColRef& A, const ColRef& B, float* sx, int* n, V3 d, int lane) {
+  V3 a, b;
+  int ia = support(W, A, d, &a, lane);
+  int ib = support(W, B, -d, &b, lane);
+  for (int k = 0; k < *n; ++k) if (__float_as_int(sx[SX_IA + k]) == ia && __float_as_int(sx[SX_IB + k]) == ib) return false;
+  __syncwarp();
+  if (lane == 0) {
+    int k = *n;
+    ST3(sx + SX_W + k * 3, a - b); ST3(sx + SX_A + k * 3, a); ST3(sx + SX_B + k * 3, b);
+    sx[SX_IA + k] = __int_as_float(ia); sx[SX_IB + k] = __int_as_float(ib);
+  }
+  __syncwarp();
+  *n = *n + 1;
+  return true;
+}
+
+__device__ bool epa_complete(const DWorld& W, const ColRef& A, const ColRef& B, float* sx, int* np, int lane) {
+  int n = *np;
+  if (n == 1) {
+    for (int k = 0; k < 6 && n == 1; ++k) {
+      V3 d = v3(k == 0 ? 1.f : k == 1 ? -1.f : 0.f, k == 2 ? 1.f : k == 3 ? -1.f : 0.f, k == 4 ? 1.f : k == 5 ? -1.f : 0.f);
+      sx_add(W, A, B, sx, &n, d, lane);
+    }
+    if (n == 1) { *np = n; return false; }
+  }
+  if (n == 2) {
+    V3 d = LD3(sx + SX_W + 3) - LD3(sx + SX_W);
+    for (int k = 0; k < 6 && n == 2; k += 2) {
+      V3 axis = v3(k == 0 ? 1.f : 0.f, k == 2 ? 1.f : 0.f, k == 4 ? 1.f : 0.f);
+      V3 dir = cross(d, axis);
+      if (len2(dir) < 1e-12f * len2(d)) continue;
+      if (!sx_add(W, A, B, sx, &n, dir, lane)) sx_add(W, A, B, sx, &n, -dir, lane);
+      if (n == 3) {
+        V3 w0 = LD3(sx + SX_W);
+        V3 nn = cross(LD3(sx + SX_W + 3) - w0, LD3(sx + SX_W + 6) - w0);
+        if (len2(nn) < 1e-20f) n = 2;
+      }
+    }
+    if (n == 2) { *np = n; return false; }
+  }
+  if (n == 3) {
+    V3 w0 = LD3(sx + SX_W);
+    V3 nn = cross(LD3(sx + SX_W + 3) - w0, LD3(sx + SX_W + 6) - w0);
+    if (len2(nn) < 1e-20f) { *np = n; return false; }
+    if (!sx_add(W, A, B, sx, &n, nn, lane)) { if (!sx_add(W, A, B, sx, &n, -nn, lane)) { *np = n; return false; } }
+    V3 e3 = LD3(sx + SX_W + 9) - w0;
+    float vol = dot(e3, nn);
+    if (vol * vol < 1e-12f * len2(nn) * len2(e3)) {
+      n = 3;
+      if (!sx_add(W, A, B, sx, &n, -nn, lane)) { *np = n; return false; }
+      e3 = LD3(sx + SX_W + 9) - w0;
+      vol = dot(e3, nn);
+      if (vol * vol < 1e-12f * len2(nn) * len2(e3)) { *np = n; return false; }
+    }
+  }
+  *np = n;
+  return n == 4;
+}
+
+__device__ int epa(const DWorld& W, const ColRef& A, const ColRef& B, float* sx, float* ep, V3* n_out, float* depth,
+                   V3* pa, V3* pb, int lane) {
+  int sn = __float_as_int(sx[SX_N]);
+  if (sn < 4 && !epa_complete(W, A, B, sx, &sn, lane)) return 0;
+  __syncwarp();
+  if (lane < 4) {
+    ST3(ep + EP_W + lane * 3, LD3(sx + SX_W + lane * 3));
+    ST3(ep + EP_PA + lane * 3, LD3(sx + SX_A + lane * 3));
+    ST3(ep + EP_PB + lane * 3, LD3(sx + SX_B + lane * 3));
+    ep[EP_IA + lane] = sx[SX_IA + lane]; ep[EP_IB + lane] = sx[SX_IB + lane];
+  }
+  __syncwarp();
+  int nv = 4, nf = 4;
+  bool bad = false;
+  if (lane < 4) {
+    const int t0 = (lane == 3) ? 1 : 0, t1 = (lane == 0) ? 1 : (lane == 1) ? 3 : (lane == 2) ? 2 : 3;
+    const int t2 = (lane == 0) ? 2 : (lane == 1) ? 1 : (lane == 2) ? 3 : 2, t3 = (lane == 0) ? 3 : (lane == 1) ? 2 : (lane == 2) ? 1 : 0;
+    V3 n; float d;
+    int i0 = t0, i1 = t1, i2 = t2;
+    if (!epa_face_plane(ep, i0, i1, i2, &n, &d)) bad = true;
+    else {
+      if (dot(n, LD3(ep + EP_W + t3 * 3)) - d > 0.0f) { int t = i1; i1 = i2; i2 = t; n = -n; d = -d; }
+      ep[EP_FI + lane] = __int_as_float(i0 | (i1 << 8) | (i2 << 16) | (1 << 24));
+      ST3(ep + EP_FN + lane * 3, n); ep[EP_FD + lane] = d;
+    }
+  }
+  if (__any_sync(FULL, bad)) return 0;
+  __syncwarp();
+  int best = 0;
+  for (int it = 0; it < W.P.epa_max_iters; ++it) {
+    // closest alive face (first minimum)
+    float bd = 3e38f; int bf = 0x7fffffff;
+    for (int f = lane; f < nf; f += 32) {
+      int fi = __float_as_int(ep[EP_FI + f]);
+      float d = ep[EP_FD + f];
+      if ((fi >> 24) && d < bd) { bd = d; bf = f; }
+    }
+    unsigned key = (bf != 0x7fffffff) ? f2ord(bd + 0.0f) : 0xffffffffu;
+    unsigned mk = __reduce_min_sync(FULL, key);
+    if (mk == 0xffffffffu) return 0;
+    unsigned cand = (key == mk && bf != 0x7fffffff) ? (unsigned)bf : 0x7fffffffu;
+    best = (int)__reduce_min_sync(FULL, cand);
+    bd = ep[EP_FD + best];
+    V3 n = LD3(ep + EP_FN + best * 3);
+    V3 a, b;
+    int ia = support(W, A, n, &a, lane);
+    int ib = support(W, B, -n, &b, lane);
+    V3 ww = a - b;
+    float s = dot(ww, n);
+    if (s - bd < 1e-6f) break;
+    bool dup = false;
+    for (int k = lane; k < nv; k += 32) if (__float_as_int(ep[EP_IA + k]) == ia && __float_as_int(ep[EP_IB + k]) == ib) dup = true;
+    if (__any_sync(FULL, dup) || nv >= EPA_MAXV) break;
+    // visibility
+    for (int f = lane; f < nf; f += 32) {
+      int fi = __float_as_int(ep[EP_FI + f]);
+      int vis = (fi >> 24) && (dot(LD3(ep + EP_FN + f * 3), ww) - ep[EP_FD + f] > 0.0f);
+      ep[EP_VIS + f] = __int_as_float(vis);
+    }
+    __syncwarp();
+    // horizon (sequential, lane 0)
+    int ne = 0;
+    if (lane == 0) {
+      for (int f = 0; f < nf; ++f) {
+        if (!__float_as_int(ep[EP_VIS + f])) continue;
+        int fi = __float_as_int(ep[EP_FI + f]);
+        int i0 = fi & 255, i1 = (fi >> 8) & 255, i2 = (fi >> 16) & 255;
+        int e0[3] = {i0, i1, i2}, e1[3] = {i1, i2, i0};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          int rev = e1[k] | (e0[k] << 8);
+          int found = -1;
+          for (int j = 0; j < ne; ++j) if (__float_as_int(ep[EP_ED + j]) == rev) { found = j; break; }
+          if (found >= 0) { for (int j = found; j + 1 < ne; ++j) ep[EP_ED + j] = ep[EP_ED + j + 1]; --ne; }
+          else if (ne < EPA_MAXF) { ep[EP_ED + ne] = __int_as_float(e0[k] | (e1[k] << 8)); ++ne; }
+        }
+      }
+    }
+    ne = __shfl_sync(FULL, ne, 0);
+    __syncwarp();
+    if (ne < 3 || nf + ne > EPA_MAXF) break;
+    if (lane == 0) {
+      ST3(ep + EP_W + nv * 3, ww); ST3(ep + EP_PA + nv * 3, a); ST3(ep + EP_PB + nv * 3, b);
+      ep[EP_IA + nv] = __int_as_float(ia); ep[EP_IB + nv] = __int_as_float(ib);
+    }
+    __syncwarp();
+    // new faces: one horizon edge per lane; staged after the current faces, committed only if all are sound
+    bool ok = true;
+    for (int j = lane; j < ne; j += 32) {
+      int ed = __float_as_int(ep[EP_ED + j]);
+      int u = ed & 255, vtx = (ed >> 8) & 255;
+      V3 fn; float fd;
+      if (!epa_face_plane(ep, u, vtx, nv, &fn, &fd)) ok = false;
+      else {
+        ep[EP_FI + nf + j] = __int_as_float(u | (vtx << 8) | (nv << 16) | (1 << 24));
+        ST3(ep + EP_FN + (nf + j) * 3, fn); ep[EP_FD + nf + j] = fd;
+      }
+    }
+    if (!__all_sync(FULL, ok)) break;
+    for (int f = lane; f < nf; f += 32)
+      if (__float_as_int(ep[EP_VIS + f])) ep[EP_FI + f] = __int_as_float(__float_as_int(ep[EP_FI + f]) & 0x00ffffff);
+    __syncwarp();
+    nf += ne;
+    ++nv;
+  }
+  __syncwarp();
+  int fi = __float_as_int(ep[EP_FI + best]);
+  int i0 = fi & 255, i1 = (fi >> 8) & 255, i2 = (fi >> 16) & 255;
+  V3 fn = LD3(ep + EP_FN + best * 3);
+  float fd = ep[EP_FD + best];
+  V3 p = fn * fd;
+  b2s_simplex_result r;
+  b2s_closest_triangle(LD3(ep + EP_W + i0 * 3) - p, LD3(ep + EP_W + i1 * 3) - p, LD3(ep + EP_W + i2 * 3) - p, 0, 1, 2, &r);
+  *pa = (LD3(ep + EP_PA + i0 * 3) * r.bary[0] + LD3(ep + EP_PA + i1 * 3) * r.bary[1]) + LD3(ep + EP_PA + i2 * 3) * r.bary[2];
+  *pb = (LD3(ep + EP_PB + i0 * 3) * r.bary[0] + LD3(ep + EP_PB + i1 * 3) * r.bary[1]) + LD3(ep + EP_PB + i2 * 3) * r.bary[2];
+  *n_out = fn;
+  *depth = fd;
+  __syncwarp();
+  return 1;
+}
+
+__device__ int collide_pair(const DWorld& W, const ColRef& A, const ColRef& B, float threshold, float* sx, float* ep,
+                            V3* pA, V3* pB, V3* normal, float* distance, int lane) {
+  float msum = A.margin + B.margin;
+  V3 v, pa, pb;
+  int st = gjk(W, A, B, msum + threshold, sx, &v, &pa, &pb, lane);
+  if (st == 0) return 0;
+  V3 n;
+  float dist;
+  if (st == 1) {
+    float l = len(v);
+    n = v * (1.0f / l);
+    dist = l - msum;
+  } else {
+    V3 no;
+    float depth;
+    if (!epa(W, A, B, sx, ep, &no, &depth, &pa, &pb, lane)) {
+      V3 c = A.cen - B.cen;
+      float l2 = len2(c);
+      n = (l2 < 1e-12f) ? v3(0.0f, 0.0f, 1.0f) : c * (1.0f / sqrtf(l2));
+      pa = A.cen; pb = pa;
+      dist = -msum;
+    } else {
+      n = -no;
+      dist = -depth - msum;
+    }
+  }
+  if (!(dist < threshold)) return 0;
+  *pA = pa - n * A.margin;
+  *pB = pb + n * B.margin;
+  *normal = n;
+  *distance = dist;
+  return 1;
+}
+
+// ------------------------------------------------------------ substep -------
+
+struct WarpSmem {
+  float* body; float* col; int* pairs; int* oldkeys; int* cmk; float* con; int* order; int* colstart;
+  unsigned long long* used; float* stage; float* fk; float* sx;
+};
+
+__device__ __forceinline__ WarpSmem carve(const DWorld& W, float* base) {
+  WarpSmem s;
+  s.body = base + W.sm.body; s.col = base + W.sm.col; s.pairs = (int*)(base + W.sm.pairs);
+  s.oldkeys = (int*)(base + W.sm.oldkeys); s.cmk = (int*)(base + W.sm.cmk); s.con = base + W.sm.con;
+  s.order = (int*)(base + W.sm.order); s.colstart = (int*)(base + W.sm.colstart);
+  s.used = (unsigned long long*)(base + W.sm.used); s.stage = base + W.sm.stage; s.fk = base + W.sm.fk;
+  s.sx = base + W.sm.simplex;
+  return s;
+}
+
+#define BS(c, i) W.buf.body_state[((size_t)(c) * W.B + e) * W.Nmax + (i)]
+#define MPAR(c, i) W.mov_params[((size_t)(c) * W.B + e) * W.Nmax + (i)]
+
+// stages 1-6 of oracle substep(): controller, body table, colliders, broad phase, narrow phase, rows
+__device__ void substep_pre(const DWorld& W, int e, int lane, const WarpSmem& S, int* nc_out, int* newn_out) {
+  const B2SParams& P = W.P;
+  const float dt = (float)P.time_step;
+  const int Ns = W.Ns, L = W.L, NB = W.NB, Nmax = W.Nmax;
+  const int nm = W.buf.num_movables[e];
+
+  stage_arm(W, e, lane);
+  {
+    float q[7], qd[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { q[j] = W.buf.joint_state[(0 * 7 + j) * W.B + e]; qd[j] = W.buf.joint_state[(1 * 7 + j) * W.B + e]; }
+    arm_fk_links(W, e, lane, q, qd, S.fk, S.body);
+  }
+  // body table: statics + movables (links were written by arm_fk_links)
+  const V3 g = v3(P.gravity[0], P.gravity[1], P.gravity[2]);
+  const float ld = fmaxf(0.0f, 1.0f - P.linear_damping * dt), ad = fmaxf(0.0f, 1.0f - P.angular_damping * dt);
+  for (int s = lane; s < NB; s += 32) {
+    float* b = S.body + s * BODY_STRIDE;
+    if (s < Ns) {
+      const float* sp = W.static_pose + s * 7;
+      float dz = (W.static_flags[s] & B2S_STATIC_ON_TABLE) ? W.table_dz[e] : 0.0f;
+      Q4 qq = q4(sp[3], sp[4], sp[5], sp[6]);
+      ST3(b + BO_POS, v3(sp[0], sp[1], sp[2] + dz));
+      stm3(b + BO_R, q_to_m3(qq));
+      ST3(b + BO_VEL, v3(0, 0, 0)); ST3(b + BO_ANG, v3(0, 0, 0));
+      b[BO_INVM] = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) b[BO_INVI + i] = 0.0f;
+      b[BO_FRIC] = W.static_friction[s];
+      b[BO_TYPE] = __int_as_float(B2S_TYPE_STATIC);
+      b[BO_QUAT] = qq.x; b[BO_QUAT + 1] = qq.y; b[BO_QUAT + 2] = qq.z; b[BO_QUAT + 3] = qq.w;
+    } else if (s >= Ns + L) {
+      const int i = s - Ns - L;
+      if (i >= nm) {
+        ST3(b + BO_POS, v3(0, 0, 0));
+        M3 I3; I3.r0 = v3(1, 0, 0); I3.r1 = v3(0, 1, 0); I3.r2 = v3(0, 0, 1);
+        stm3(b + BO_R, I3);
+        ST3(b + BO_VEL, v3(0, 0, 0)); ST3(b + BO_ANG, v3(0, 0, 0));
+        b[BO_INVM] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) b[BO_INVI + k] = 0.0f;
+        b[BO_FRIC] = 0.0f; b[BO_TYPE] = __int_as_float(B2S_TYPE_STATIC);
+        b[BO_QUAT] = 0; b[BO_QUAT + 1] = 0; b[BO_QUAT + 2] = 0; b[BO_QUAT + 3] = 1;
+      } else {
+        V3 pos = v3(BS(0, i), BS(1, i), BS(2, i));
+        Q4 qq = q4(BS(3, i), BS(4, i), BS(5, i), BS(6, i));
+        V3 v = v3(BS(7, i), BS(8, i), BS(9, i));
+        V3 om = v3(BS(10, i), BS(11, i), BS(12, i));
+        V3 vel = (v + g * dt) * ld;
+        V3 ang = om * ad;
+        int asset = __float_as_int(MPAR(0, i));
+        float sc = MPAR(1, i), mass = MPAR(2, i);
+        const DAsset* As = W.assets + asset;
+        V3 h = v3(As->half[0], As->half[1], As->half[2]) * sc;
+        float k3 = mass * (1.0f / 3.0f);
+        V3 I = v3(k3 * (h.y * h.y + h.z * h.z), k3 * (h.x * h.x + h.z * h.z), k3 * (h.x * h.x + h.y * h.y));
+        M3 R = q_to_m3(qq);
+        ST3(b + BO_POS, pos); stm3(b + BO_R, R);
+        ST3(b + BO_VEL, vel); ST3(b + BO_ANG, ang);
+        b[BO_INVM] = 1.0f / mass;
+        stm3(b + BO_INVI, inv_inertia_world(R, v3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z)));
+        b[BO_FRIC] = MPAR(3, i);
+        b[BO_TYPE] = __int_as_float(B2S_TYPE_DYNAMIC);
+        b[BO_QUAT] = qq.x; b[BO_QUAT + 1] = qq.y; b[BO_QUAT + 2] = qq.z; b[BO_QUAT + 3] = qq.w;
+      }
+    }
+  }
+  __syncwarp();
+
+  // colliders + AABBs (one collider per lane)
+  const int nc = W.ncol[e];
+  int first_dyn = nc, arm0 = nc, arm1 = 0;
+  for (int c0 = 0; c0 < nc; c0 += 32) {
+    int c = c0 + lane;
+    int lfd = nc, la0 = nc, la1 = 0;
+    if (c < nc) {
+      float* cr = S.col + c * COL_STRIDE;
+      int slot = W.col_slot[(size_t)e * W.Hmax + c], hull = W.col_hull[(size_t)e * W.Hmax + c];
+      const DHull* H = W.hulls + hull;
+      const float* b = S.body + slot * BODY_STRIDE;
+      int type = __float_as_int(b[BO_TYPE]);
+      unsigned flags = (slot < Ns) ? W.static_flags[slot] : 0u;
+      V3 pos = LD3(b + BO_POS);
+      M3 R = ldm3(b + BO_R);
+      float scale = (slot >= Ns + L) ? MPAR(1, slot - Ns - L) : 1.0f;
+      float rad = H->rad * scale + H->margin;
+      V3 cen = pos + mmul(R, v3(H->lc[0], H->lc[1], H->lc[2]) * scale);
+      V3 hs = v3(H->lh[0], H->lh[1], H->lh[2]) * scale;
+      float pad = H->margin + P.breaking_factor * rad;
+      V3 ext = v3((fabsf(R.r0.x) * hs.x + fabsf(R.r0.y) * hs.y) + fabsf(R.r0.z) * hs.z + pad,
+                  (fabsf(R.r1.x) * hs.x + fabsf(R.r1.y) * hs.y) + fabsf(R.r1.z) * hs.z + pad,
+                  (fabsf(R.r2.x) * hs.x + fabsf(R.r2.y) * hs.y) + fabsf(R.r2.z) * hs.z + pad);
+      cr[CO_HULL] = __int_as_float(hull); cr[CO_SLOT] = __int_as_float(slot);
+      cr[CO_TYPE] = __int_as_float(type | ((int)flags << 8));
+      cr[CO_SCALE] = scale; cr[CO_MARGIN] = H->margin; cr[CO_RAD] = rad;
+      ST3(cr + CO_AMIN, cen - ext); ST3(cr + CO_AMAX, cen + ext);
+      if (type == B2S_TYPE_DYNAMIC) lfd = c;
+      if (type == B2S_TYPE_KINEMATIC) { la0 = c; la1 = c + 1; }
+    }
+    first_dyn = min(first_dyn, (int)__reduce_min_sync(FULL, (unsigned)lfd));
+    arm0 = min(arm0, (int)__reduce_min_sync(FULL, (unsigned)la0));
+    arm1 = max(arm1, (int)__reduce_max_sync(FULL, (unsigned)la1));
+  }
+  __syncwarp();
+
+  // broad phase: sorted pair keys, ballot compaction keeps the sequential order
+  int np = 0;
+  bool pair_over = false;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int a = arm0; a < arm1; ++a) {
+    const float* ca = S.col + a * COL_STRIDE;
+    V3 amin = LD3(ca + CO_AMIN), amax = LD3(ca + CO_AMAX);
+    for (int b0 = 0; b0 < a; b0 += 32) {
+      int b = b0 + lane;
+      bool pred = false;
+      if (b < a) {
+        const float* cb = S.col + b * COL_STRIDE;
+        int tf = __float_as_int(cb[CO_TYPE]);
+        if ((tf & 255) == B2S_TYPE_STATIC && ((tf >> 8) & B2S_STATIC_IS_TABLE)) {
+          V3 bmin = LD3(cb + CO_AMIN), bmax = LD3(cb + CO_AMAX);
+          pred = amin.x <= bmax.x && bmin.x <= amax.x && amin.y <= bmax.y && bmin.y <= amax.y && amin.z <= bmax.z && bmin.z <= amax.z;
+        }
+      }
+      unsigned m = __ballot_sync(FULL, pred);
+      if (pred) { int pos = np + __popc(m & lt); if (pos < P.max_pairs) S.pairs[pos] = (a << 16) | b; }
+      np += __popc(m);
+    }
+  }
+  for (int a = first_dyn; a < nc; ++a) {
+    const float* ca = S.col + a * COL_STRIDE;
+    V3 amin = LD3(ca + CO_AMIN), amax = LD3(ca + CO_AMAX);
+    int sa = __float_as_int(ca[CO_SLOT]);
+    for (int b0 = 0; b0 < a; b0 += 32) {
+      int b = b0 + lane;
+      bool pred = false;
+      if (b < a) {
+        const float* cb = S.col + b * COL_STRIDE;
+        if (__float_as_int(cb[CO_SLOT]) != sa) {
+          V3 bmin = LD3(cb + CO_AMIN), bmax = LD3(cb + CO_AMAX);
+          pred = amin.x <= bmax.x && bmin.x <= amax.x && amin.y <= bmax.y && bmin.y <= amax.y && amin.z <= bmax.z && bmin.z <= amax.z;
+        }
+      }
+      unsigned m = __ballot_sync(FULL, pred);
+      if (pred) { int pos = np + __popc(m & lt); if (pos < P.max_pairs) S.pairs[pos] = (a << 16) | b; }
+      np += __popc(m);
+    }
+  }
+  if (np > P.max_pairs) { pair_over = true; np = P.max_pairs; }
+  __syncwarp();
+  for (int p = lane; p < np; p += 32) W.pair_keys[(size_t)e * P.max_pairs + p] = S.pairs[p];
+  if (lane == 0) { W.num_pairs[e] = np; if (pair_over) W.error_flags[e] |= 1; }
+
+  // narrow phase + persistent manifolds (ping-pong buffers in HBM/L2)
+  const int M = P.max_manifolds;
+  const int par = W.man_parity[e];
+  const size_t obase = ((size_t)par * W.B + e) * M, nbase = ((size_t)(par ^ 1) * W.B + e) * M;
+  const int old_n = W.num_manifolds[e];
+  for (int k = lane; k < old_n; k += 32) S.oldkeys[k] = W.man_keys[obase + k];
+  __syncwarp();
+  int newn = 0, ncon = 0, cflags = 0;
+  bool man_over = false, con_over = false;
+  float* stg = S.stage;   // [4][16]
+  for (int p = 0; p < np; ++p) {
+    const int key = S.pairs[p];
+    const int a = key >> 16, b = key & 0xffff;
+    ColRef A = col_ref(W, S.col, S.body, a), Bc = col_ref(W, S.col, S.body, b);
+    const float* ca = S.col + a * COL_STRIDE;
+    const float* cb = S.col + b * COL_STRIDE;
+    const float threshold = P.breaking_factor * fminf(ca[CO_RAD], cb[CO_RAD]);
+    const int sA = __float_as_int(ca[CO_SLOT]), sB = __float_as_int(cb[CO_SLOT]);
+    // old manifold lookup
+    int found = 0x7fffffff;
+    for (int k = lane; k < old_n; k += 32) if (S.oldkeys[k] == key) found = min(found, k);
+    found = (int)__reduce_min_sync(FULL, (unsigned)found);
+    int n = 0;
+    __syncwarp();
+    if (found != 0x7fffffff) {
+      n = W.man_npts[obase + found];
+      const float* src = W.man_pts + (obase + found) * 4 * B2S_CP_FLOATS;
+      stg[lane] = src[lane]; stg[lane + 32] = src[lane + 32];
+    }
+    __syncwarp();
+    // refresh (one point per lane), compaction keeps the order
+    {
+      float pt[B2S_CP_FLOATS];
+      bool keep = false;
+      if (lane < n) {
+#pragma unroll
+        for (int t = 0; t < B2S_CP_FLOATS; ++t) pt[t] = stg[lane * B2S_CP_FLOATS + t];
+        V3 wA = A.pos + mmul(A.R, v3(pt[0], pt[1], pt[2]));
+        V3 wB = Bc.pos + mmul(Bc.R, v3(pt[3], pt[4], pt[5]));
+        V3 nn = v3(pt[6], pt[7], pt[8]);
+        float dist = dot(wA - wB, nn);
+        if (!(dist > threshold)) {
+          V3 proj = wA - nn * dist;
+          V3 dd = wB - proj;
+          if (!(len2(dd) > threshold * threshold)) { keep = true; pt[9] = dist; }
+        }
+      }
+      unsigned km = __ballot_sync(FULL, keep);
+      __syncwarp();
+      if (keep) {
+        int dst = __popc(km & lt);
+#pragma unroll
+        for (int t = 0; t < B2S_CP_FLOATS; ++t) stg[dst * B2S_CP_FLOATS + t] = pt[t];
+      }
+      n = __popc(km);
+      __syncwarp();
+    }
+    V3 pA, pB, nrm;
+    float dist;
+    if (collide_pair(W, A, Bc, threshold, S.sx, S.con, &pA, &pB, &nrm, &dist, lane)) {
+      V3 lA = mtmul(A.R, pA - A.pos);
+      V3 lB = mtmul(Bc.R, pB - Bc.pos);
+      // manifold_add (uniform decisions, lane 0 writes)
+      int nearest = -1;
+      float shortest = threshold * threshold;
+      for (int k = 0; k < n; ++k) {
+        V3 d = LD3(stg + k * B2S_CP_FLOATS) - lA;
+        float dd = len2(d);
+        if (dd < shortest) { shortest = dd; nearest = k; }
+      }
+      int idx; bool keepl = false;
+      if (nearest >= 0) { idx = nearest; keepl = true; }
+      else if (n < 4) { idx = n; n = n + 1; }
+      else {
+        V3 PP[4]; float DD[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { PP[k] = LD3(stg + k * B2S_CP_FLOATS); DD[k] = stg[k * B2S_CP_FLOATS + 9]; }
+        idx = b2s_manifold_replace_index(PP, DD, lA, dist);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        float* pp = stg + idx * B2S_CP_FLOATS;
+        pp[0] = lA.x; pp[1] = lA.y; pp[2] = lA.z; pp[3] = lB.x; pp[4] = lB.y; pp[5] = lB.z;
+        pp[6] = nrm.x; pp[7] = nrm.y; pp[8] = nrm.z; pp[9] = dist;
+        if (!keepl) { pp[10] = 0.0f; pp[11] = 0.0f; pp[12] = 0.0f; }
+        pp[13] = 0.0f; pp[14] = 0.0f; pp[15] = 0.0f;
+      }
+      __syncwarp();
+    }
+    if (n > 0) {
+      if (newn < M) {
+        float* dst = W.man_pts + (nbase + newn) * 4 * B2S_CP_FLOATS;
+        dst[lane] = (lane < n * B2S_CP_FLOATS) ? stg[lane] : 0.0f;
+        dst[lane + 32] = (lane + 32 < n * B2S_CP_FLOATS) ? stg[lane + 32] : 0.0f;
+        if (lane == 0) { W.man_keys[nbase + newn] = key; W.man_npts[nbase + newn] = n; }
+        const int tA = __float_as_int(ca[CO_TYPE]) & 255, tfB = __float_as_int(cb[CO_TYPE]);
+        const int tB = tfB & 255;
+        if (tA == B2S_TYPE_KINEMATIC && ((tfB >> 8) & B2S_STATIC_IS_TABLE)) cflags |= 1;
+        if (tA == B2S_TYPE_DYNAMIC && tB == B2S_TYPE_KINEMATIC) cflags |= 2;
+        if (tA == B2S_TYPE_DYNAMIC || tB == B2S_TYPE_DYNAMIC) {
+          if (lane < n) { if (ncon + lane < P.max_contacts) S.cmk[ncon + lane] = (newn << 2) | lane; }
+          if (ncon + n > P.max_contacts) { con_over = true; ncon = P.max_contacts; } else ncon += n;
+        }
+        ++newn;
+      } else man_over = true;
+    }
+    (void)sA; (void)sB;
+  }
+  __syncwarp();
+  for (int k = newn + lane; k < M; k += 32) { W.man_keys[nbase + k] = -1; W.man_npts[nbase + k] = 0; }
+  if (lane == 0) {
+    W.num_manifolds[e] = newn;
+    W.man_parity[e] = par ^ 1;
+    W.contact_flags[e] = cflags;
+    int ef = (man_over ? 2 : 0) | (con_over ? 8 : 0);
+    if (ef) W.error_flags[e] |= ef;
+  }
+  __syncwarp();
+
+  // contact rows, one contact per lane
+  const int nrows = 1 + P.friction_dirs;
+  for (int c = lane; c < ncon; c += 32) {
+    const int mk = S.cmk[c];
+    const int m = mk >> 2, k = mk & 3;
+    const int key = W.man_keys[nbase + m];
+    const int a = key >> 16, b = key & 0xffff;
+    const int sA = __float_as_int(S.col[a * COL_STRIDE + CO_SLOT]), sB = __float_as_int(S.col[b * COL_STRIDE + CO_SLOT]);
+    const float* bA = S.body + sA * BODY_STRIDE;
+    const float* bB = S.body + sB * BODY_STRIDE;
+    const float* p = W.man_pts + ((nbase + m) * 4 + k) * B2S_CP_FLOATS;
+    float* cn = S.con + c * CON_STRIDE;
+    V3 posA = LD3(bA + BO_POS), posB = LD3(bB + BO_POS);
+    V3 wA = posA + mmul(ldm3(bA + BO_R), v3(p[0], p[1], p[2]));
+    V3 wB = posB + mmul(ldm3(bB + BO_R), v3(p[3], p[4], p[5]));
+    V3 n = v3(p[6], p[7], p[8]);
+    V3 rA = wA - posA, rB = wB - posB;
+    V3 t1, t2;
+    plane_space(n, &t1, &t2);
+    if (P.friction_dirs == 1) {
+      V3 rel = (LD3(bA + BO_VEL) + cross(LD3(bA + BO_ANG), rA)) - (LD3(bB + BO_VEL) + cross(LD3(bB + BO_ANG), rB));
+      V3 lat = rel - n * dot(rel, n);
+      float l2 = len2(lat);
+      if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
+    }
+    const float imA = bA[BO_INVM], imB = bB[BO_INVM];
+    const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float* row = cn + r * ROW_WORDS;
+      V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
+      V3 angA = cross(rA, dir), angB = cross(rB, dir);
+      V3 iangA = mmul(iA, angA), iangB = mmul(iB, angB);
+      float d = ((imA + imB) + dot(iangA, angA)) + dot(iangB, angB);
+      ST3(row + RW_DIR, dir); ST3(row + RW_ANGA, angA); ST3(row + RW_ANGB, angB);
+      ST3(row + RW_IANGA, iangA); ST3(row + RW_IANGB, iangB);
+      row[RW_INVD] = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
+      row[RW_D] = d;
+      row[RW_BIAS] = 0.0f;
+      float lam = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
+      if (r >= nrows) lam = 0.0f;
+      row[RW_LAMBDA] = lam;
+    }
+    float pen = p[9] + P.linear_slop;
+    cn[RW_BIAS] = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
+    cn[CN_SLOTA] = __int_as_float(sA); cn[CN_SLOTB] = __int_as_float(sB);
+    cn[CN_MU] = bA[BO_FRIC] * bB[BO_FRIC];
+    cn[CN_MK] = __int_as_float(mk);
+    cn[CN_COLOUR] = __int_as_float(-1);
+    cn[CN_INVMA] = (__float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC) ? imA : 0.0f;
+    cn[CN_INVMB] = (__float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC) ? imB : 0.0f;
+  }
+  __syncwarp();
+  *nc_out = ncon;
+  *newn_out = newn;
+  (void)Nmax;
+}
+
+// greedy colouring in contact order + stable sort by colour (oracle step 7)
+__device__ int colour_contacts(const DWorld& W, int e, int lane, const WarpSmem& S, int C) {
+  for (int s = lane; s < W.NB; s += 32) S.used[s] = 0ull;
+  __syncwarp();
+  int ncolours = 0;
+  if (lane == 0) {
+    bool over = false;
+    for (int i = 0; i < C; ++i) {
+      float* cn = S.con + i * CON_STRIDE;
+      int sA = __float_as_int(cn[CN_SLOTA]), sB = __float_as_int(cn[CN_SLOTB]);
+      bool dA = __float_as_int(S.body[sA * BODY_STRIDE + BO_TYPE]) == B2S_TYPE_DYNAMIC;
+      bool dB = __float_as_int(S.body[sB * BODY_STRIDE + BO_TYPE]) == B2S_TYPE_DYNAMIC;
+      unsigned long long mask = (dA ? S.used[sA] : 0ull) | (dB ? S.used[sB] : 0ull);
+      if (mask == ~0ull) { over = true; cn[CN_COLOUR] = __int_as_float(-1); continue; }
+      int k = __ffsll((long long)~mask) - 1;
+      cn[CN_COLOUR] = __int_as_float(k);
+      if (k + 1 > ncolours) ncolours = k + 1;
+      if (dA) S.used[sA] |= 1ull << k;
+      if (dB) S.used[sB] |= 1ull << k;
+    }
+    if (over) W.error_flags[e] |= 16;
+  }
+  ncolours = __shfl_sync(FULL, ncolours, 0);
+  __syncwarp();
+  for (int c = lane; c < C; c += 32) {
+    int my = __float_as_int(S.con[c * CON_STRIDE + CN_COLOUR]);
+    if (my < 0) continue;
+    int pos = 0;
+    for (int o = 0; o < C; ++o) {
+      int oc = __float_as_int(S.con[o * CON_STRIDE + CN_COLOUR]);
+      pos += (oc >= 0 && (oc < my || (oc == my && o < c))) ? 1 : 0;
+    }
+    S.order[pos] = c;
+  }
+  for (int k = lane; k <= ncolours; k += 32) {
+    int cnt = 0;
+    for (int o = 0; o < C; ++o) {
+      int oc = __float_as_int(S.con[o * CON_STRIDE + CN_COLOUR]);
+      cnt += (oc >= 0 && oc < k) ? 1 : 0;
+    }
+    S.colstart[k] = cnt;
+  }
+  __syncwarp();
+  return ncolours;
+}
+
+__device__ __forceinline__ float row_jv(const float* row, const float* bA, const float* bB) {
+  return ((dot(LD3(row + RW_DIR), LD3(bA + BO_VEL)) + dot(LD3(row + RW_ANGA), LD3(bA + BO_ANG))) -
+          dot(LD3(row + RW_DIR), LD3(bB + BO_VEL))) - dot(LD3(row + RW_ANGB), LD3(bB + BO_ANG));
+}
+__device__ __forceinline__ void row_apply(const float* row, float* bA, float* bB, float imA, float imB, bool dA, bool dB, float dl) {
+  V3 dir = LD3(row + RW_DIR);
+  if (dA) {
+    ST3(bA + BO_VEL, LD3(bA + BO_VEL) + dir * (imA * dl));
+    ST3(bA + BO_ANG, LD3(bA + BO_ANG) + LD3(row + RW_IANGA) * dl);
+  }
+  if (dB) {
+    ST3(bB + BO_VEL, LD3(bB + BO_VEL) - dir * (imB * dl));
+    ST3(bB + BO_ANG, LD3(bB + BO_ANG) - LD3(row + RW_IANGB) * dl);
+  }
+}
+
+// projected Gauss-Seidel over the colour-ordered rows held in shared memory (oracle step 8)
+__device__ int pgs_solve(const DWorld& W, int lane, float* body, float* con, const int* order, const int* colstart,
+                         int C, int ncolours) {
+  const B2SParams& P = W.P;
+  const int nrows = 1 + P.friction_dirs;
+  // warm start
+  for (int k = 0; k < ncolours; ++k) {
+    for (int idx = colstart[k] + lane; idx < colstart[k + 1]; idx += 32) {
+      float* cn = con + order[idx] * CON_STRIDE;
+      int sA = __float_as_int(cn[CN_SLOTA]), sB = __float_as_int(cn[CN_SLOTB]);
+      float* bA = body + sA * BODY_STRIDE; float* bB = body + sB * BODY_STRIDE;
+      bool dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC, dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
+      for (int r = 0; r < nrows; ++r) row_apply(cn + r * ROW_WORDS, bA, bB, bA[BO_INVM], bB[BO_INVM], dA, dB, cn[r * ROW_WORDS + RW_LAMBDA]);
+    }
+    __syncwarp();
+  }
+  int iters_used = 0;
+  for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
+    float maxres = 0.0f;
+    for (int k = 0; k < ncolours; ++k) {
+      for (int idx = colstart[k] + lane; idx < colstart[k + 1]; idx += 32) {
+        float* cn = con + order[idx] * CON_STRIDE;
+        int sA = __float_as_int(cn[CN_SLOTA]), sB = __float_as_int(cn[CN_SLOTB]);
+        float* bA = body + sA * BODY_STRIDE; float* bB = body + sB * BODY_STRIDE;
+        bool dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC, dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
+        float* row = cn;
+        float dl = (row[RW_BIAS] - row_jv(row, bA, bB)) * row[RW_INVD];
+        float nl = fmaxf(0.0f, row[RW_LAMBDA] + dl);
+        dl = nl - row[RW_LAMBDA];
+        row[RW_LAMBDA] = nl;
+        row_apply(row, bA, bB, bA[BO_INVM], bB[BO_INVM], dA, dB, dl);
+        float res = dl * row[RW_D];
+        maxres = fmaxf(maxres, res * res);
+      }
+      __syncwarp();
+    }
+    for (int k = 0; k < ncolours; ++k) {
+      for (int idx = colstart[k] + lane; idx < colstart[k + 1]; idx += 32) {
+        float* cn = con + order[idx] * CON_STRIDE;
+        int sA = __float_as_int(cn[CN_SLOTA]), sB = __float_as_int(cn[CN_SLOTB]);
+        float* bA = body + sA * BODY_STRIDE; float* bB = body + sB * BODY_STRIDE;
+        bool dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC, dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
+        float lim = cn[CN_MU] * cn[RW_LAMBDA];
+        for (int r = 1; r < nrows; ++r) {
+          float* row = cn + r * ROW_WORDS;
+          float dl = (0.0f - row_jv(row, bA, bB)) * row[RW_INVD];
+          float nl = fminf(lim, fmaxf(-lim, row[RW_LAMBDA] + dl));
+          dl = nl - row[RW_LAMBDA];
+          row[RW_LAMBDA] = nl;
+          row_apply(row, bA, bB, bA[BO_INVM], bB[BO_INVM], dA, dB, dl);
+          float res = dl * row[RW_D];
+          maxres = fmaxf(maxres, res * res);
+        }
+      }
+      __syncwarp();
+    }
+    iters_used = it + 1;
+    unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));   // residuals are >= 0: bit order == value order
+    if (__uint_as_float(mx) <= P.residual_threshold) break;
+  }
+  return iters_used;
+}
+
+// stages 7-9: colour, solve, write back impulses, integrate
+__device__ void substep_post(const DWorld& W, int e, int lane, const WarpSmem& S, int C, int newn) {
+  const B2SParams& P = W.P;
+  const float dt = (float)P.time_step;
+  const int Ns = W.Ns, L = W.L;
+  const int nm = W.buf.num_movables[e];
+  const int par = W.man_parity[e];          // already flipped: current buffer
+  const size_t nbase = ((size_t)par * W.B + e) * P.max_manifolds;
+  int ncolours = colour_contacts(W, e, lane, S, C);
+  int iters = pgs_solve(W, lane, S.body, S.con, S.order, S.colstart, C, ncolours);
+  for (int c = lane; c < C; c += 32) {
+    const float* cn = S.con + c * CON_STRIDE;
+    int mk = __float_as_int(cn[CN_MK]);
+    float* p = W.man_pts + ((nbase + (mk >> 2)) * 4 + (mk & 3)) * B2S_CP_FLOATS;
+    p[10] = cn[RW_LAMBDA]; p[11] = cn[ROW_WORDS + RW_LAMBDA]; p[12] = cn[2 * ROW_WORDS + RW_LAMBDA];
+  }
+  if (lane == 0) {
+    int32_t* st = W.solver_stats + (size_t)e * 4;
+    st[0] = C * (1 + P.friction_dirs); st[1] = ncolours; st[2] = iters; st[3] = C;
+  }
+  __syncwarp();
+  bool bad = false;
+  for (int i = lane; i < nm; i += 32) {
+    const float* b = S.body + (Ns + L + i) * BODY_STRIDE;
+    V3 ang = LD3(b + BO_ANG), vel = LD3(b + BO_VEL);
+    float wl = len(ang);
+    if (wl * dt > B2S_HALF_PI) ang = ang * (B2S_HALF_PI / (wl * dt));
+    V3 pos = LD3(b + BO_POS) + vel * dt;
+    Q4 qq = q_integrate(q4(b[BO_QUAT], b[BO_QUAT + 1], b[BO_QUAT + 2], b[BO_QUAT + 3]), ang, dt);
+    BS(0, i) = pos.x; BS(1, i) = pos.y; BS(2, i) = pos.z;
+    BS(3, i) = qq.x; BS(4, i) = qq.y; BS(5, i) = qq.z; BS(6, i) = qq.w;
+    BS(7, i) = vel.x; BS(8, i) = vel.y; BS(9, i) = vel.z;
+    BS(10, i) = ang.x; BS(11, i) = ang.y; BS(12, i) = ang.z;
+    float chk = (pos.x + pos.y) + pos.z;
+    if (!(fabsf(chk) < 1e6f)) bad = true;
+  }
+  if (__any_sync(FULL, bad) && lane == 0) W.error_flags[e] |= 4;
+  if (lane < 7) {
+    float q = W.buf.joint_state[(0 * 7 + lane) * W.B + e], qd = W.buf.joint_state[(1 * 7 + lane) * W.B + e];
+    W.buf.joint_state[(0 * 7 + lane) * W.B + e] = q + qd * dt;
+  }
+  __syncwarp();
+  if (lane == 0) W.num_steps[e] += 1;
+  __syncwarp();
+  (void)newn;
+}
+
+// -------------------------------------------------------- phase machine -----
+
+__device__ void movable_status(const DWorld& W, int e, int lane, int which) {
+  for (int i = lane; i < W.Nmax; i += 32) {
+    float* s = W.status + (((size_t)e * 2 + which) * W.Nmax + i) * 4;
+    if (i < W.buf.num_movables[e]) {
+      s[0] = BS(0, i); s[1] = BS(1, i); s[2] = BS(2, i);
+      s[3] = yaw_from_q(q4(BS(3, i), BS(4, i), BS(5, i), BS(6, i)));
+    } else { s[0] = s[1] = s[2] = s[3] = 0.0f; }
+  }
+  __syncwarp();
+}
+
+__device__ void phase_logic(const DWorld& W, int e, int lane, float* fk) {
+  const B2SParams& P = W.P;
+  int32_t* ps = W.phase_state + (size_t)e * 8;
+  int ph = W.phase[e];
+  const int nsteps = W.num_steps[e];
+  bool interrupt = ps[5] != 0;
+  const int ps0 = ps[0];
+  bool ready, reset_t = false;
+  if (interrupt) ready = true;
+  else {
+    int lr = arm_is_ready(W, e, lane);
+    if (lr && (P.time_step * (double)nsteps >= W.ctrl_time[(size_t)e * 5 + 4])) { reset_t = true; ready = true; }
+    else if (ps0 < 0) ready = true;
+    else if (nsteps >= ps0) { reset_t = true; ready = true; }
+    else ready = false;
+  }
+  if (reset_t && lane == 0) { W.ctrl_flags[(size_t)e * 4] = 0; W.ctrl_flags[(size_t)e * 4 + 1] = 0; }
+  __syncwarp();
+  float ee[7];
+  {
+    float q[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) q[j] = W.buf.joint_state[(0 * 7 + j) * W.B + e];
+    Xf frame[B2S_NUM_JOINTS];
+    V3 ax[B2S_NUM_JOINTS], org[B2S_NUM_JOINTS];
+    fk_chain(W.arm, q, frame, ax, org);
+    xf_store(xf_mul(frame[B2S_NUM_JOINTS - 1], xf_from(W.arm->ee)), ee);
+  }
+  int ps1 = ps[1];
+  int new_ps0 = ps0;
+  if (ready) {
+    if (interrupt && ph != B2S_PHASE_POST && ph != B2S_PHASE_OFFSTAGE && ph != B2S_PHASE_DONE) ph = B2S_PHASE_POST;
+    else ph = ph + 1;
+    new_ps0 = nsteps + (ph == B2S_PHASE_MOTION ? P.max_motion_steps : ph == B2S_PHASE_OFFSTAGE ? P.max_offstage_steps : P.max_phase_steps);
+    const float* wp = W.waypoints + (size_t)e * 14;
+    float pose[7];
+    if (ph == B2S_PHASE_PRE) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) pose[k] = wp[k];
+      pose[2] = P.gripper_safe_height;
+      arm_set_link_target(W, e, lane, pose);
+    } else if (ph == B2S_PHASE_START) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) pose[k] = wp[k];
+      arm_set_link_target(W, e, lane, pose);
+    } else if (ph == B2S_PHASE_MOTION) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) pose[k] = wp[7 + k];
+      arm_set_link_target(W, e, lane, pose);
+    } else if (ph == B2S_PHASE_POST) {
+      ps1 += 1;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) pose[k] = ee[k];
+      pose[2] = P.gripper_safe_height;
+      arm_set_link_target(W, e, lane, pose);
+    } else if (ph == B2S_PHASE_OFFSTAGE) {
+      float q[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) q[k] = P.offstage_positions[k];
+      arm_set_joint_target(W, e, lane, q);
+    }
+  }
+  interrupt = false;
+  const int cf = W.contact_flags[e];
+  if (ph == B2S_PHASE_MOTION && (cf & 1)) interrupt = true;
+  bool safe = true;
+  if (ph == B2S_PHASE_PRE) { if (cf & 2) safe = false; }
+  else if (ph == B2S_PHASE_START) {
+    if (cf & 2) {
+      float start_z = P.finger_tip_offset + 0.5f * (P.cspace_high[2] + P.cspace_low[2]);
+      float dist = ee[2] - start_z;
+      if (!(fabsf(dist) <= 0.01f)) safe = false;
+    }
+  } else if (ph == B2S_PHASE_DONE) {
+    if (cf & 2) safe = false;
+    else {
+      bool out = false;
+      for (int i = lane; i < W.buf.num_movables[e]; i += 32) {
+        float x = BS(0, i), y = BS(1, i);
+        if (x < P.table_workspace_low[0] || x > P.table_workspace_high[0] || y < P.table_workspace_low[1] || y > P.table_workspace_high[1]) out = true;
+      }
+      if (__any_sync(FULL, out)) safe = false;
+    }
+  }
+  if (!safe) interrupt = true;
+  __syncwarp();
+  if (lane == 0) {
+    if (!safe) W.buf.is_safe[e] = 0;
+    if (interrupt && ph == B2S_PHASE_DONE) ps[4] = 1;
+    ps[0] = new_ps0; ps[1] = ps1; ps[5] = interrupt ? 1 : 0;
+    W.phase[e] = ph;
+  }
+  __syncwarp();
+  (void)fk;
+}
+
+__device__ bool all_stable(const DWorld& W, int e, int lane, float lin, float ang) {
+  bool moving = false;
+  for (int i = lane; i < W.buf.num_movables[e]; i += 32) {
+    float lv = len(v3(BS(7, i), BS(8, i), BS(9, i)));
+    float av = len(v3(BS(10, i), BS(11, i), BS(12, i)));
+    if (lv >= lin || av >= ang) moving = true;
+  }
+  return !__any_sync(FULL, moving);
+}
+
+__device__ void finish_action(const DWorld& W, int e, int lane) {
+  const B2SParams& P = W.P;
+  movable_status(W, e, lane, 1);
+  // sums are sequential over bodies in the oracle: lane 0 does them (Nmax is small)
+  if (lane == 0) {
+    float dp = 0.0f, da = 0.0f;
+    for (int i = 0; i < W.buf.num_movables[e]; ++i) {
+      const float* s0 = W.status + (((size_t)e * 2 + 0) * W.Nmax + i) * 4;
+      const float* s1 = W.status + (((size_t)e * 2 + 1) * W.Nmax + i) * 4;
+      dp = dp + len(v3(s1[0] - s0[0], s1[1] - s0[1], s1[2] - s0[2]));
+      da = da + fabsf(b2s_wrap_pi(s1[3] - s0[3]));
+    }
+    W.buf.is_effective[e] = (dp <= P.min_delta_position && da <= P.min_delta_angle) ? 0 : 1;
+    W.phase[e] = B2S_PHASE_IDLE;
+  }
+  __syncwarp();
+}
+
+// ----------------------------------------------------------- the kernel -----
+
+extern __shared__ float b2s_smem[];
+
+__global__ void __launch_bounds__(128) k_substeps(const __grid_constant__ DWorld W, int n, int mode, float lin, float ang,
+                                                  int max_steps) {
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (e >= W.B) return;
+  WarpSmem S = carve(W, b2s_smem + (size_t)wib * W.sm.words);
+  const B2SParams& P = W.P;
+  int done_steps = 0;
+  if (mode == MODE_RAW) {
+    for (int s = 0; s < n; ++s) {
+      int C, newn;
+      substep_pre(W, e, lane, S, &C, &newn);
+      substep_post(W, e, lane, S, C, newn);
+      ++done_steps;
+    }
+  } else if (mode == MODE_ENV) {
+    for (int s = 0; s < n; ++s) {
+      int ph = W.phase[e];
+      if (ph == B2S_PHASE_IDLE) break;
+      int32_t* ps = W.phase_state + (size_t)e * 8;
+      int C, newn;
+      substep_pre(W, e, lane, S, &C, &newn);
+      substep_post(W, e, lane, S, C, newn);
+      ++done_steps;
+      if (ph < B2S_PHASE_DONE) {
+        if (W.num_steps[e] % P.steps_check != 0) continue;
+        phase_logic(W, e, lane, S.fk);
+        if (W.phase[e] == B2S_PHASE_DONE) {
+          if (lane == 0) { W.phase[e] = B2S_PHASE_SETTLE; ps[2] = 0; ps[3] = 0; }
+          __syncwarp();
+        }
+      } else {
+        int s2 = ps[2] + 1, s3 = ps[3];
+        __syncwarp();
+        bool fin = false;
+        if (s2 >= P.stable_check_after) {
+          if (all_stable(W, e, lane, P.stable_lin_threshold, P.stable_ang_threshold)) s3 += 1;
+          if (s3 >= P.stable_min_steps || s2 >= P.stable_max_steps) fin = true;
+        }
+        if (lane == 0) { ps[2] = s2; ps[3] = s3; }
+        __syncwarp();
+        if (fin) finish_action(W, e, lane);
+      }
+    }
+    if (lane == 0 && W.phase[e] != B2S_PHASE_IDLE) atomicAdd(W.unfinished, 1);
+  } else {   // MODE_SETTLE: Simulator.wait_until_stable for this env
+    int steps = 0, stable = 0;
+    while (true) {
+      int C, newn;
+      substep_pre(W, e, lane, S, &C, &newn);
+      substep_post(W, e, lane, S, C, newn);
+      ++done_steps;
+      ++steps;
+      if (steps < P.stable_check_after) continue;
+      if (all_stable(W, e, lane, lin, ang)) ++stable;
+      if (stable >= P.stable_min_steps || steps >= max_steps) break;
+    }
+  }
+  if (lane == 0 && done_steps) atomicAdd(W.substeps, (unsigned long long)done_steps);
+}
+
+void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, cudaStream_t s) {
+  const int wpb = W.P.warps_per_block;
+  const int blocks = (W.B + wpb - 1) / wpb;
+  size_t smem = b2s_smem_bytes(W);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  k_substeps<<<blocks, wpb * 32, smem, s>>>(W, n, mode, lin, ang, max_steps);
+}
+
+size_t b2s_smem_bytes(const DWorld& W) { return (size_t)W.sm.words * 4 * W.P.warps_per_block; }
