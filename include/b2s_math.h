@@ -42,9 +42,12 @@ B2S_HD b2s_v3 operator-(b2s_v3 a, b2s_v3 b) { return v3(a.x - b.x, a.y - b.y, a.
 B2S_HD b2s_v3 operator-(b2s_v3 a) { return v3(-a.x, -a.y, -a.z); }
 B2S_HD b2s_v3 operator*(b2s_v3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
 B2S_HD b2s_v3 operator*(float s, b2s_v3 a) { return v3(a.x * s, a.y * s, a.z * s); }
-B2S_HD float dot(b2s_v3 a, b2s_v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+/* a + b * s */
+B2S_HD b2s_v3 vmad(b2s_v3 a, b2s_v3 b, float s) { return v3(fmaf(b.x, s, a.x), fmaf(b.y, s, a.y), fmaf(b.z, s, a.z)); }
+/* explicit fused multiply-adds: one IEEE rounding each, identical on host (-mfma / libm fmaf) and device */
+B2S_HD float dot(b2s_v3 a, b2s_v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 B2S_HD b2s_v3 cross(b2s_v3 a, b2s_v3 b) {
-  return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+  return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 B2S_HD float len2(b2s_v3 a) { return dot(a, a); }
 B2S_HD float len(b2s_v3 a) { return sqrtf(dot(a, a)); }
@@ -111,10 +114,10 @@ B2S_HD b2s_q4 q4(float x, float y, float z, float w) { b2s_q4 r; r.x = x; r.y = 
 /* Hamilton product a*b (same component formulas as
  * transformations.quaternion_multiply, third_party/transformations.py:1362). */
 B2S_HD b2s_q4 qmul(b2s_q4 a, b2s_q4 b) {
-  return q4(((a.w * b.x + a.x * b.w) + a.y * b.z) - a.z * b.y,
-            ((a.w * b.y - a.x * b.z) + a.y * b.w) + a.z * b.x,
-            ((a.w * b.z + a.x * b.y) - a.y * b.x) + a.z * b.w,
-            ((a.w * b.w - a.x * b.x) - a.y * b.y) - a.z * b.z);
+  return q4(fmaf(-a.z, b.y, fmaf(a.y, b.z, fmaf(a.x, b.w, a.w * b.x))),
+            fmaf(a.z, b.x, fmaf(a.y, b.w, fmaf(-a.x, b.z, a.w * b.y))),
+            fmaf(a.z, b.w, fmaf(-a.y, b.x, fmaf(a.x, b.y, a.w * b.z))),
+            fmaf(-a.z, b.z, fmaf(-a.y, b.y, fmaf(-a.x, b.x, a.w * b.w))));
 }
 B2S_HD b2s_q4 qconj(b2s_q4 a) { return q4(-a.x, -a.y, -a.z, a.w); }
 B2S_HD b2s_q4 qnormalize(b2s_q4 a) {
@@ -137,9 +140,9 @@ B2S_HD b2s_m3 q_to_m3(b2s_q4 q) {
 B2S_HD b2s_v3 mmul(b2s_m3 m, b2s_v3 v) { return v3(dot(m.r0, v), dot(m.r1, v), dot(m.r2, v)); }
 /* M^T v */
 B2S_HD b2s_v3 mtmul(b2s_m3 m, b2s_v3 v) {
-  return v3((m.r0.x * v.x + m.r1.x * v.y) + m.r2.x * v.z,
-            (m.r0.y * v.x + m.r1.y * v.y) + m.r2.y * v.z,
-            (m.r0.z * v.x + m.r1.z * v.y) + m.r2.z * v.z);
+  return v3(fmaf(m.r2.x, v.z, fmaf(m.r1.x, v.y, m.r0.x * v.x)),
+            fmaf(m.r2.y, v.z, fmaf(m.r1.y, v.y, m.r0.y * v.x)),
+            fmaf(m.r2.z, v.z, fmaf(m.r1.z, v.y, m.r0.z * v.x)));
 }
 B2S_HD b2s_m3 mmulm(b2s_m3 a, b2s_m3 b) {
   b2s_v3 c0 = v3(b.r0.x, b.r1.x, b.r2.x), c1 = v3(b.r0.y, b.r1.y, b.r2.y), c2 = v3(b.r0.z, b.r1.z, b.r2.z);

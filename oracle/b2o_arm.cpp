@@ -188,15 +188,25 @@ void arm_update(World& w, int e) {
   }
   /* motor: persists with its last command, like a pybullet joint motor */
   const float dt = (float)P.time_step;
+  float vj[7], scale = 1.0f;
   for (int j = 0; j < 7; ++j) {
     float q = w.joint_state[(0 * 7 + j) * w.B + e], qd = w.joint_state[(1 * 7 + j) * w.B + e];
     float v = 0.0f;
     if (f[3]) {
       v = (P.position_gain * (c[18 + j] - q) / dt + qd) + P.velocity_gain * (c[25 + j] - qd);
       if (P.clamp_joint_velocity) {
+        /* one common scale for all joints keeps the joint-space direction of the move */
         float vm = P.limb_velocity_ratio * d.joint_max_velocity[j];
-        v = fminf(vm, fmaxf(-vm, v));
+        float a = fabsf(v);
+        if (a > vm) scale = fminf(scale, vm / a);
       }
+    }
+    vj[j] = v;
+  }
+  for (int j = 0; j < 7; ++j) {
+    float q = w.joint_state[(0 * 7 + j) * w.B + e];
+    float v = vj[j] * scale;
+    if (f[3]) {
       float qn = q + v * dt;
       if (qn > d.joint_upper[j]) v = (d.joint_upper[j] - q) / dt;
       if (qn < d.joint_lower[j]) v = (d.joint_lower[j] - q) / dt;

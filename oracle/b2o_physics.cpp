@@ -605,8 +605,8 @@ void substep(World& w, int e) {
   auto apply = [&](Contact& c, const ContactRow& row, float dl) {
     BodyX& bA = body[c.slotA];
     BodyX& bB = body[c.slotB];
-    if (bA.type == TYPE_DYNAMIC) { bA.vel = bA.vel + row.dir * (bA.inv_mass * dl); bA.ang = bA.ang + row.iangA * dl; }
-    if (bB.type == TYPE_DYNAMIC) { bB.vel = bB.vel - row.dir * (bB.inv_mass * dl); bB.ang = bB.ang - row.iangB * dl; }
+    if (bA.type == TYPE_DYNAMIC) { bA.vel = vmad(bA.vel, row.dir, bA.inv_mass * dl); bA.ang = vmad(bA.ang, row.iangA, dl); }
+    if (bB.type == TYPE_DYNAMIC) { bB.vel = vmad(bB.vel, row.dir, -(bB.inv_mass * dl)); bB.ang = vmad(bB.ang, row.iangB, -dl); }
   };
   auto jv = [&](const Contact& c, const ContactRow& row) {
     const BodyX& bA = body[c.slotA];

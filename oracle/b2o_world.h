@@ -36,7 +36,7 @@ typedef b2s_q4 Q4;
 typedef b2s_m3 M3;
 
 enum { TYPE_STATIC = 0, TYPE_KINEMATIC = 1, TYPE_DYNAMIC = 2 };
-enum { EPA_MAXV = 48, EPA_MAXF = 192, MAX_COLOURS = 64 };
+enum { EPA_MAXV = 32, EPA_MAXF = 96, MAX_COLOURS = 64 };
 
 struct Hull {
   int voff, vcnt;

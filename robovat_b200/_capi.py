@@ -167,7 +167,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get('B2S_LIB') or LIB_PATH      # B2S_LIB: try another build of the same library
     if not os.path.exists(path):
         raise OSError('%s not found: build it with `python -c "import __graft_entry__ as g; '
                       'g.build()"` (there is no CPU fallback)' % path)

@@ -8,6 +8,7 @@ commented with the hint it was derived from.  `AttrDict` stands for easydict
 (robovat/utils/yaml_config.py:21-153) for user overrides.
 """
 import copy
+import os
 import math
 
 import numpy as np
@@ -226,8 +227,10 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     movable_hulls = nmax * scene.max_movable_hulls
     p.max_colliders = scene.fixed_colliders + movable_hulls
     p.max_manifolds = max(32, 6 * movable_hulls)
-    p.max_pairs = max(64, 4 * p.max_manifolds)
-    p.max_contacts = max(48, 8 * movable_hulls)
+    p.max_pairs = max(64, 2 * p.max_manifolds)
+    p.reserved_i[0] = int(os.environ.get('B2S_EPB', 0))      # envs per block (0 = library default)
+    # <= 32 contact points keeps the solver's Jacobian rows in registers (one contact per lane)
+    p.max_contacts = max(32, 8 * movable_hulls)
     p.solver_iterations, p.friction_dirs = int(phys.SOLVER_ITERATIONS), int(phys.FRICTION_DIRS)
     p.gjk_max_iters, p.epa_max_iters, p.ik_max_iters = 32, 32, 20
     p.ik_interval, p.check_done_interval = 10, 100
@@ -239,7 +242,7 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     p.cam_height, p.cam_width = int(cfg.KINECT2.DEPTH.HEIGHT), int(cfg.KINECT2.DEPTH.WIDTH)
     p.num_points = int(cfg.OBS.NUM_POINTS)
     p.task = _capi.TASK_IDS[cfg.TASK_NAME]
-    p.warps_per_block = 4
+    p.warps_per_block = int(os.environ.get('B2S_WARPS', 16))   # one 512-thread block per SM
     p.time_step = float(cfg.SIM.TIME_STEP)
     p.gravity[:] = phys.GRAVITY
     p.erp2, p.linear_slop, p.warmstart = phys.ERP2, phys.LINEAR_SLOP, phys.WARMSTART

@@ -92,7 +92,7 @@ int b2s_default_params(B2SParams* p) {
   p->ik_max_iters = 20; p->ik_interval = 10; p->check_done_interval = 100;
   p->steps_check = 20; p->max_phase_steps = 3000; p->max_motion_steps = 4000; p->max_offstage_steps = 4000;
   p->stable_check_after = 100; p->stable_min_steps = 100; p->stable_max_steps = 2000;
-  p->clamp_joint_velocity = 1; p->warps_per_block = 4;
+  p->clamp_joint_velocity = 1; p->warps_per_block = B2S_BLOCK_THREADS / 32;
   p->time_step = 1e-3;
   p->gravity[0] = 0; p->gravity[1] = 0; p->gravity[2] = -9.8f;
   p->erp2 = 0.08f; p->linear_slop = 1e-5f; p->warmstart = 0.85f; p->residual_threshold = 1e-7f;
@@ -111,7 +111,7 @@ int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
   if (p->max_pairs <= 0 || p->max_manifolds <= 0 || p->max_contacts <= 0 || p->max_colliders <= 0)
     return fail(B2S_E_INVALID, "b2s_create: capacities must be positive");
   if (p->max_colliders > 65535) return fail(B2S_E_INVALID, "b2s_create: max_colliders > 65535");
-  if (p->warps_per_block < 1 || p->warps_per_block > 4) return fail(B2S_E_INVALID, "b2s_create: warps_per_block must be 1..4");
+  if (p->warps_per_block < 1 || p->warps_per_block * 32 > B2S_BLOCK_THREADS) return fail(B2S_E_INVALID, "b2s_create: warps_per_block must be 1..%d for this build", B2S_BLOCK_THREADS / 32);
   if (p->friction_dirs != 1 && p->friction_dirs != 2) return fail(B2S_E_INVALID, "b2s_create: friction_dirs must be 1 or 2");
   if (!(p->time_step > 0)) return fail(B2S_E_INVALID, "b2s_create: time_step must be > 0");
   int ndev = 0;
@@ -265,19 +265,43 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   SmemLayout& sm = d.sm;
   int o = 0;
   auto take = [&](int words) { int at = o; o += (words + 1) & ~1; return at; };   // keep 8-byte alignment
+  d.reg_rows = (P.max_contacts <= 32 && d.NB <= 32) ? 1 : 0;
   sm.body = take(d.NB * BODY_STRIDE);
   sm.col = take(d.Hmax * COL_STRIDE);
   sm.pairs = take(P.max_pairs);
-  sm.oldkeys = take(P.max_manifolds);
   sm.cmk = take(P.max_contacts);
-  sm.con = take(std::max(P.max_contacts * CON_STRIDE, (int)(EPA_MAXV * 11 + EPA_MAXF * 7)));
+  sm.used = take(d.NB * 2);
+  sm.meta = take(META_WORDS);
+  sm.words_env = o;
+  o = 0;
+  sm.oldkeys = take(P.max_manifolds);
+  sm.con = take(std::max(d.reg_rows ? 0 : P.max_contacts * CON_STRIDE, (int)(EPA_MAXV * 11 + EPA_MAXF * 7)));
   sm.order = take(P.max_contacts);
   sm.colstart = take(66);
-  sm.used = take(d.NB * 2);
   sm.stage = take(4 * B2S_CP_FLOATS);
   sm.fk = take(FK_WORDS);
   sm.simplex = take(48);
-  sm.words = o;
+  sm.words_warp = o;
+  // environments per block: with register-resident rows any warp can run any stage of any environment of
+  // its block, so a block owns more environments than warps (dynamic hand-out); otherwise one per warp
+  {
+    const int wpb = P.warps_per_block;
+    int maxE = d.reg_rows ? 2 * wpb : wpb;
+    while (maxE > wpb && ((size_t)maxE * sm.words_env + (size_t)wpb * sm.words_warp) * 4 > 220 * 1024) --maxE;
+    int E = maxE;
+    if (P.reserved_i[0] > 0) E = P.reserved_i[0];
+    else {
+      // fill whole waves of 148 SMs (one block per SM): B = 4096 -> E = 28 -> 147 blocks
+      int dev_sms = 148;
+      cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, w->device);
+      const int waves = (d.B + dev_sms * maxE - 1) / (dev_sms * maxE);
+      E = (d.B + dev_sms * waves - 1) / (dev_sms * waves);
+    }
+    if (!d.reg_rows) E = wpb;
+    if (E < wpb) E = wpb;
+    if (E > maxE) E = maxE;
+    d.envs_per_block = E;
+  }
   size_t smem = b2s_smem_bytes(d);
   if (smem > 227 * 1024) return fail(B2S_E_CAPACITY, "b2s_load_scene: %zu bytes of shared memory per block exceed 227 KB; lower warps_per_block or the capacities", smem);
   // arrays exposed through b2s_array

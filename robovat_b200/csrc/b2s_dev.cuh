@@ -27,8 +27,8 @@ typedef b2s_m3 M3;
 #define B2S_TYPE_KINEMATIC 1
 #define B2S_TYPE_DYNAMIC 2
 
-#define EPA_MAXV 48
-#define EPA_MAXF 192
+#define EPA_MAXV 32
+#define EPA_MAXF 96
 #define FULL 0xffffffffu
 
 struct DHull {
@@ -71,9 +71,22 @@ struct DLayout {
 };
 
 // per-warp shared-memory carve-up (offsets in 4-byte words from the warp's base)
+// Shared memory of a block = E per-environment regions followed by one scratch region per warp.
+// A warp may pick up any environment of its block in any stage, so everything that has to survive from
+// one stage to the next (body table, colliders, pair list, contact list) is per environment; GJK/EPA,
+// manifold staging and FK scratch are per warp.
 struct SmemLayout {
-  int body, col, pairs, oldkeys, cmk, con, order, colstart, used, stage, fk, simplex, words;
+  int body, col, pairs, cmk, used, meta, words_env;                        // per environment
+  int oldkeys, con, order, colstart, stage, fk, simplex, words_warp;       // per warp
 };
+#define META_ACTIVE 0
+#define META_NP 1
+#define META_C 2
+#define META_NEWN 3
+#define META_SETTLE_STEPS 4
+#define META_SETTLE_STABLE 5
+#define META_FINISHED 6
+#define META_WORDS 8
 
 #define BODY_STRIDE 35   // pos3 R9 vel3 ang3 invm1 invI9 fric1 type1 quat4 = 34 (+1 pad, odd stride)
 #define COL_STRIDE 13    // hull slot type|flags scale margin rad amin3 amax3 = 12 (+1)
@@ -135,6 +148,8 @@ struct DWorld {
   float* stage_body;     // [B][NB][BODY_STRIDE]
   int32_t* stage_meta;   // [B][4 + max_contacts + 65]   nc, ncolours, pad, pad, order[], colstart[]
   SmemLayout sm;
+  int envs_per_block;    // E: environments a block steps together (E >= warps_per_block)
+  int reg_rows;          // 1: contacts fit one per lane (max_contacts <= 32, NB <= 32): rows live in registers
 };
 
 enum { MODE_RAW = 0, MODE_ENV = 1, MODE_SETTLE = 2 };

@@ -64,10 +64,36 @@ __device__ __forceinline__ void stm3(float* p, M3 m) { ST3(p, m.r0); ST3(p + 3, 
 #define RW_BIAS 17
 #define RW_LAMBDA 18
 
+extern __shared__ float b2s_smem[];
+
+// The world description lives in constant memory (uploaded before every launch): device functions read
+// it through the constant bank instead of chasing a generic pointer to the kernel parameter block.
+__constant__ DWorld g_W;
+#define W g_W
+
 struct Xf { V3 p; Q4 q; };
 __device__ __forceinline__ Xf xf_from(const float* a) { Xf t; t.p = v3(a[0], a[1], a[2]); t.q = q4(a[3], a[4], a[5], a[6]); return t; }
 __device__ __forceinline__ Xf xf_mul(Xf a, Xf b) { Xf t; t.p = a.p + qrot(a.q, b.p); t.q = qmul(a.q, b.q); return t; }
 __device__ __forceinline__ void xf_store(Xf t, float* o) { o[0] = t.p.x; o[1] = t.p.y; o[2] = t.p.z; o[3] = t.q.x; o[4] = t.q.y; o[5] = t.q.z; o[6] = t.q.w; }
+
+struct WarpSmem {
+  float* body; float* col; int* pairs; int* oldkeys; int* cmk; float* con; int* order; int* colstart;
+  unsigned long long* used; float* stage; float* fk; float* sx;
+};
+
+// `sw` packs (environment slot of the block) | (warp in block) << 16
+__device__ __forceinline__ int* env_meta(int slot) { return (int*)(b2s_smem + (size_t)slot * W.sm.words_env + W.sm.meta); }
+__device__ __forceinline__ WarpSmem carve(int sw) {
+  // both bases derive from the __shared__ array, so accesses compile to LDS/STS, not generic LD/ST
+  float* eb = b2s_smem + (size_t)(sw & 0xffff) * W.sm.words_env;
+  float* wb = b2s_smem + (size_t)W.envs_per_block * W.sm.words_env + (size_t)(sw >> 16) * W.sm.words_warp;
+  WarpSmem s;
+  s.body = eb + W.sm.body; s.col = eb + W.sm.col; s.pairs = (int*)(eb + W.sm.pairs); s.cmk = (int*)(eb + W.sm.cmk);
+  s.used = (unsigned long long*)(eb + W.sm.used);
+  s.oldkeys = (int*)(wb + W.sm.oldkeys); s.con = wb + W.sm.con; s.order = (int*)(wb + W.sm.order);
+  s.colstart = (int*)(wb + W.sm.colstart); s.stage = wb + W.sm.stage; s.fk = wb + W.sm.fk; s.sx = wb + W.sm.simplex;
+  return s;
+}
 
 __device__ __forceinline__ M3 inv_inertia_world(M3 R, V3 d) {
   V3 a0 = vmul(R.r0, d), a1 = vmul(R.r1, d), a2 = vmul(R.r2, d);
@@ -80,95 +106,76 @@ __device__ __forceinline__ M3 inv_inertia_world(M3 R, V3 d) {
 
 // ----------------------------------------------------------------- arm ------
 
-// serial chain: frames after each joint, world joint axes and origins (uniform over the warp)
-__device__ __forceinline__ void fk_chain(const DArm* __restrict__ arm, const float* q, Xf* frame, V3* ax, V3* org) {
+// serial chain (uniform over the warp): frames after each joint, world joint axes and origins, written
+// to the warp's shared FK area  fk[0..49) frames 7x7, fk[49..70) axes, fk[70..91) origins
+__device__ __noinline__ void fk_chain(const DArm* __restrict__ arm, const float* q, int lane, int wib) {
+  float* fk = carve(wib).fk;
   Xf T = xf_from(arm->base);
-#pragma unroll
+  __syncwarp();
   for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
     Xf Tj = xf_mul(T, xf_from(arm->joint_origin[j]));
     V3 a = v3(arm->joint_axis[j][0], arm->joint_axis[j][1], arm->joint_axis[j][2]);
-    ax[j] = qrot(Tj.q, a);
-    org[j] = Tj.p;
+    V3 axw = qrot(Tj.q, a);
     T.p = Tj.p;
     T.q = qmul(Tj.q, q_axis_angle(a, q[j]));
-    frame[j] = T;
+    if (lane == 0) { xf_store(T, fk + j * 7); ST3(fk + 49 + j * 3, axw); ST3(fk + 70 + j * 3, Tj.p); }
   }
+  __syncwarp();
 }
 
 // damped-least-squares IK, uniform over the warp (every lane computes the same values)
-__device__ void arm_ik(const DWorld& W, const float* target, const float* q_start, float* q_out) {
+__device__ __noinline__ void arm_ik(const float* target, const float* q_start, float* q_out, int lane, int wib) {
+  const float* fk = carve(wib).fk;
   const DArm* arm = W.arm;
   const B2SParams& P = W.P;
   float q[B2S_NUM_JOINTS];
-#pragma unroll
   for (int j = 0; j < B2S_NUM_JOINTS; ++j) q[j] = q_start[j];
   Xf tgt = xf_from(target);
   Xf eel = xf_from(arm->ee);
   const float res2 = P.ik_residual * P.ik_residual;
   for (int it = 0; it < P.ik_max_iters; ++it) {
-    Xf frame[B2S_NUM_JOINTS];
-    V3 ax[B2S_NUM_JOINTS], org[B2S_NUM_JOINTS];
-    fk_chain(arm, q, frame, ax, org);
-    Xf ee = xf_mul(frame[B2S_NUM_JOINTS - 1], eel);
+    fk_chain(arm, q, lane, wib);
+    Xf ee = xf_mul(xf_from(fk + 6 * 7), eel);
     V3 ep = tgt.p - ee.p;
     V3 er = q_to_rotvec(qmul(tgt.q, qconj(ee.q)));
     if (len2(ep) < res2 && len2(er) < res2) break;
     float J[6][B2S_NUM_JOINTS];
-#pragma unroll
     for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
-      V3 jv = cross(ax[j], ee.p - org[j]);
+      V3 axj = LD3(fk + 49 + j * 3);
+      V3 jv = cross(axj, ee.p - LD3(fk + 70 + j * 3));
       J[0][j] = jv.x; J[1][j] = jv.y; J[2][j] = jv.z;
-      J[3][j] = ax[j].x; J[4][j] = ax[j].y; J[5][j] = ax[j].z;
+      J[3][j] = axj.x; J[4][j] = axj.y; J[5][j] = axj.z;
     }
     float A[36], y[6] = {ep.x, ep.y, ep.z, er.x, er.y, er.z};
-#pragma unroll
     for (int r = 0; r < 6; ++r)
-#pragma unroll
       for (int c = 0; c < 6; ++c) {
         float s = 0.0f;
-#pragma unroll
         for (int j = 0; j < B2S_NUM_JOINTS; ++j) s = s + J[r][j] * J[c][j];
         if (r == c) s = s + P.ik_damping * P.ik_damping;
         A[r * 6 + c] = s;
       }
     if (!b2s_chol6_solve(A, y)) break;
     float dq[B2S_NUM_JOINTS], m = 0.0f;
-#pragma unroll
     for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
       float s = 0.0f;
-#pragma unroll
       for (int r = 0; r < 6; ++r) s = s + J[r][j] * y[r];
       dq[j] = s;
       m = fmaxf(m, fabsf(s));
     }
     float k = (m > P.ik_max_step) ? (P.ik_max_step / m) : 1.0f;
-#pragma unroll
     for (int j = 0; j < B2S_NUM_JOINTS; ++j) q[j] = q[j] + dq[j] * k;
   }
-#pragma unroll
   for (int j = 0; j < B2S_NUM_JOINTS; ++j) q_out[j] = fminf(arm->upper[j], fmaxf(arm->lower[j], q[j]));
 }
 
 // FK of all collision links + end effector into global link_poses/link_vel and (optionally) the
 // shared body table.  Chain is uniform; links are spread over lanes.
-__device__ void arm_fk_links(const DWorld& W, int e, int lane, const float* q, const float* qd, float* fk /*smem*/,
-                             float* body /*smem or NULL*/) {
+__device__ __noinline__ void arm_fk_links(int e, int lane, const float* q, const float* qd, int wib) {
+  const WarpSmem S_ = carve(wib);
+  float* fk = S_.fk;
+  float* body = S_.body;
   const DArm* arm = W.arm;
-  {
-    Xf frame[B2S_NUM_JOINTS];
-    V3 ax[B2S_NUM_JOINTS], org[B2S_NUM_JOINTS];
-    fk_chain(arm, q, frame, ax, org);
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
-        xf_store(frame[j], fk + j * 7);
-        ST3(fk + 49 + j * 3, ax[j]);
-        ST3(fk + 70 + j * 3, org[j]);
-      }
-    }
-    __syncwarp();
-  }
+  fk_chain(arm, q, lane, wib);
   const int L = W.L;
   if (lane < L) {
     int k = lane;
@@ -204,7 +211,7 @@ __device__ void arm_fk_links(const DWorld& W, int e, int lane, const float* q, c
   __syncwarp();
 }
 
-__device__ __forceinline__ bool joints_reached(const DWorld& W, int e, int lane, const float* c, int f1, int f2) {
+__device__ __forceinline__ bool joints_reached(int e, int lane, const float* c, int f1, int f2) {
   if (!f1) return true;
   bool ok = true;
   if (lane < 7) {
@@ -217,7 +224,7 @@ __device__ __forceinline__ bool joints_reached(const DWorld& W, int e, int lane,
 }
 
 // ControllableBody.update + POSITION_CONTROL motor (oracle/b2o_arm.cpp arm_update)
-__device__ void stage_arm(const DWorld& W, int e, int lane) {
+__device__ __noinline__ void stage_arm(int e, int lane, int wib) {
   const B2SParams& P = W.P;
   float* c = W.ctrl + (size_t)e * B2S_CTRL_FLOATS;
   int32_t* f = W.ctrl_flags + (size_t)e * 4;
@@ -232,7 +239,7 @@ __device__ void stage_arm(const DWorld& W, int e, int lane) {
     float q[7], qo[7], tgt[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) { q[j] = W.buf.joint_state[(0 * 7 + j) * W.B + e]; tgt[j] = c[j]; }
-    arm_ik(W, tgt, q, qo);
+    arm_ik(tgt, q, qo, lane, wib);
     double t0 = T[0], t1 = T[1];
     float th0 = c[7], th1 = c[8];
     __syncwarp();
@@ -245,11 +252,11 @@ __device__ void stage_arm(const DWorld& W, int e, int lane) {
     __syncwarp();
     f1 = 1; f2 = 0;
     ik_updated = true;
-    if (joints_reached(W, e, lane, c, f1, f2)) f0 = 0;
+    if (joints_reached(e, lane, c, f1, f2)) f0 = 0;
   }
   if (f1 && (n % P.check_done_interval == 0 || ik_updated)) {
     bool done = (now >= T[3]);
-    bool reached = joints_reached(W, e, lane, c, f1, f2);
+    bool reached = joints_reached(e, lane, c, f1, f2);
     if (done || reached) f1 = 0;
   }
   if (f1) {
@@ -258,28 +265,34 @@ __device__ void stage_arm(const DWorld& W, int e, int lane) {
   }
   __syncwarp();
   const float dt = (float)P.time_step;
-  if (lane < 7) {
-    const int j = lane;
+  {
+    const int j = lane < 7 ? lane : 0;
     float q = W.buf.joint_state[(0 * 7 + j) * W.B + e], qd = W.buf.joint_state[(1 * 7 + j) * W.B + e];
-    float v = 0.0f;
-    if (f3) {
+    float v = 0.0f, ratio = 1.0f;
+    if (f3 && lane < 7) {
       v = (P.position_gain * (c[18 + j] - q) / dt + qd) + P.velocity_gain * (c[25 + j] - qd);
       if (P.clamp_joint_velocity) {
         float vm = P.limb_velocity_ratio * W.arm->max_vel[j];
-        v = fminf(vm, fmaxf(-vm, v));
+        float a = fabsf(v);
+        if (a > vm) ratio = vm / a;
       }
+    }
+    // common scale = min over joints (ratios are positive: bit order == value order)
+    float scale = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(ratio)));
+    v = v * scale;
+    if (f3 && lane < 7) {
       float qn = q + v * dt;
       if (qn > W.arm->upper[j]) v = (W.arm->upper[j] - q) / dt;
       if (qn < W.arm->lower[j]) v = (W.arm->lower[j] - q) / dt;
     }
-    W.buf.joint_state[(1 * 7 + j) * W.B + e] = v;
+    if (lane < 7) W.buf.joint_state[(1 * 7 + j) * W.B + e] = v;
   }
   if (lane == 0) { f[0] = f0; f[1] = f1; f[2] = f2; f[3] = f3; }
   __syncwarp();
 }
 
 // SawyerSim.is_limb_ready with its side effects (oracle arm_is_ready)
-__device__ int arm_is_ready(const DWorld& W, int e, int lane) {
+__device__ __noinline__ int arm_is_ready(int e, int lane) {
   float* c = W.ctrl + (size_t)e * B2S_CTRL_FLOATS;
   int32_t* f = W.ctrl_flags + (size_t)e * 4;
   double* T = W.ctrl_time + (size_t)e * 5;
@@ -287,7 +300,7 @@ __device__ int arm_is_ready(const DWorld& W, int e, int lane) {
   int f0 = f[0], f1 = f[1], f2 = f[2];
   const double now = W.P.time_step * (double)W.num_steps[e];
   if (!f0 || now >= T[1]) f0 = 0;
-  bool jd = (!f1) || (now >= T[3]) || joints_reached(W, e, lane, c, f1, f2);
+  bool jd = (!f1) || (now >= T[3]) || joints_reached(e, lane, c, f1, f2);
   if (jd) f1 = 0;
   __syncwarp();
   if (lane == 0) { f[0] = f0; f[1] = f1; }
@@ -295,7 +308,7 @@ __device__ int arm_is_ready(const DWorld& W, int e, int lane) {
   return (!f0 && !f1) ? 1 : 0;
 }
 
-__device__ void arm_set_link_target(const DWorld& W, int e, int lane, const float* pose) {
+__device__ void arm_set_link_target(int e, int lane, const float* pose) {
   float* c = W.ctrl + (size_t)e * B2S_CTRL_FLOATS;
   double* T = W.ctrl_time + (size_t)e * 5;
   if (lane == 0) {
@@ -309,7 +322,7 @@ __device__ void arm_set_link_target(const DWorld& W, int e, int lane, const floa
   }
   __syncwarp();
 }
-__device__ void arm_set_joint_target(const DWorld& W, int e, int lane, const float* q) {
+__device__ void arm_set_joint_target(int e, int lane, const float* q) {
   float* c = W.ctrl + (size_t)e * B2S_CTRL_FLOATS;
   double* T = W.ctrl_time + (size_t)e * 5;
   if (lane == 0) {
@@ -329,7 +342,7 @@ __device__ void arm_set_joint_target(const DWorld& W, int e, int lane, const flo
 
 struct ColRef { V3 pos; M3 R; float scale, margin; int voff, vcnt; V3 cen; };
 
-__device__ __forceinline__ ColRef col_ref(const DWorld& W, const float* col, const float* body, int c) {
+__device__ __forceinline__ ColRef col_ref(const float* col, const float* body, int c) {
   const float* cr = col + c * COL_STRIDE;
   const float* b = body + __float_as_int(cr[CO_SLOT]) * BODY_STRIDE;
   ColRef r;
@@ -342,7 +355,7 @@ __device__ __forceinline__ ColRef col_ref(const DWorld& W, const float* col, con
 }
 
 // argmax_i v_i . d over the hull's vertices (first maximum), one or two vertices per lane
-__device__ __forceinline__ int support(const DWorld& W, const ColRef& c, V3 d, V3* p, int lane) {
+__device__ __forceinline__ int support(const ColRef& c, V3 d, V3* p, int lane) {
   V3 dl = mtmul(c.R, d);
   float best = 0.0f;
   int bi = 0x7fffffff;
@@ -374,79 +387,106 @@ __device__ __forceinline__ int support(const DWorld& W, const ColRef& c, V3 d, V
 #define SX_IB 40
 #define SX_N 44
 
-__device__ int gjk(const DWorld& W, const ColRef& A, const ColRef& B, float limit, float* sx, V3* v_out, V3* pa,
+__device__ __noinline__ void closest_simplex_dev(const V3* w, int n, b2s_simplex_result* r) { b2s_closest_simplex(w, n, r); }
+
+// The simplex lives in shared memory in PHYSICAL slots that never move; `perm` (2 bits per entry) maps
+// the logical order (= the oracle's compacted order) to physical slots and `ids` packs (ia | ib << 8)
+// of the logical entries, so the duplicate test and the compaction are register-only integer work.
+__device__ int gjk(const ColRef& A, const ColRef& B, float limit, float* sx, V3* v_out, V3* pa,
                    V3* pb, int lane) {
   V3 v = A.cen - B.cen;
   if (len2(v) < 1e-12f) v = v3(1.0f, 0.0f, 0.0f);
   int n = 0;
+  unsigned perm = 0;
+  unsigned long long ids = 0ull;
   bool have = false;
-  float bary[4] = {0, 0, 0, 0};
+  float bary0 = 0, bary1 = 0, bary2 = 0, bary3 = 0;
   int status = 1;
   for (int it = 0; it < W.P.gjk_max_iters; ++it) {
     V3 a, b;
-    int ia = support(W, A, -v, &a, lane);
-    int ib = support(W, B, v, &b, lane);
+    int ia = support(A, -v, &a, lane);
+    int ib = support(B, v, &b, lane);
     V3 ww = a - b;
     float vv = dot(v, v), vw = dot(v, ww);
     if (vw > 0.0f && vw * vw > (limit * limit) * vv) return 0;
+    const unsigned id = (unsigned)ia | ((unsigned)ib << 8);
     bool dup = false;
-    for (int k = 0; k < n; ++k) if (__float_as_int(sx[SX_IA + k]) == ia && __float_as_int(sx[SX_IB + k]) == ib) dup = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < n && (unsigned)((ids >> (16 * k)) & 0xffffu) == id) dup = true;
     if (dup) break;
     if (have && (vv - vw) <= vv * 1e-6f) break;
+    // lowest free physical slot
+    unsigned usedp = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < n) usedp |= 1u << ((perm >> (2 * k)) & 3u);
+    const int ps = __ffs(~usedp) - 1;
     __syncwarp();
     if (lane == 0) {
-      ST3(sx + SX_W + n * 3, ww); ST3(sx + SX_A + n * 3, a); ST3(sx + SX_B + n * 3, b);
-      sx[SX_IA + n] = __int_as_float(ia); sx[SX_IB + n] = __int_as_float(ib);
+      ST3(sx + SX_W + ps * 3, ww); ST3(sx + SX_A + ps * 3, a); ST3(sx + SX_B + ps * 3, b);
+      sx[SX_IA + ps] = __int_as_float(ia); sx[SX_IB + ps] = __int_as_float(ib);
     }
     __syncwarp();
+    perm = (perm & ~(3u << (2 * n))) | ((unsigned)ps << (2 * n));
+    ids = (ids & ~(0xffffull << (16 * n))) | ((unsigned long long)id << (16 * n));
     n = n + 1;
     V3 wl[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) wl[k] = LD3(sx + SX_W + k * 3);
+    for (int k = 0; k < 4; ++k) wl[k] = LD3(sx + SX_W + ((perm >> (2 * k)) & 3u) * 3);
     b2s_simplex_result r;
-    b2s_closest_simplex(wl, n, &r);
+    closest_simplex_dev(wl, n, &r);
     if (r.inside) { status = 2; break; }
-    // compact to the vertices that support the closest point
-    float rec[4][11];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-      for (int t = 0; t < 3; ++t) { rec[k][t] = sx[SX_W + k * 3 + t]; rec[k][3 + t] = sx[SX_A + k * 3 + t]; rec[k][6 + t] = sx[SX_B + k * 3 + t]; }
-      rec[k][9] = sx[SX_IA + k]; rec[k][10] = sx[SX_IB + k];
-    }
-    __syncwarp();
+    // logical compaction (order preserving): registers only
+    unsigned nperm = 0; unsigned long long nids = 0ull;
+    float nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0;
     int m = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < n && (r.used & (1 << k))) {
-        if (lane == 0) {
-#pragma unroll
-          for (int t = 0; t < 3; ++t) { sx[SX_W + m * 3 + t] = rec[k][t]; sx[SX_A + m * 3 + t] = rec[k][3 + t]; sx[SX_B + m * 3 + t] = rec[k][6 + t]; }
-          sx[SX_IA + m] = rec[k][9]; sx[SX_IB + m] = rec[k][10];
-        }
+        nperm |= ((perm >> (2 * k)) & 3u) << (2 * m);
+        nids |= ((ids >> (16 * k)) & 0xffffull) << (16 * m);
         float bk = r.bary[k];
-        if (m == 0) bary[0] = bk; else if (m == 1) bary[1] = bk; else if (m == 2) bary[2] = bk; else bary[3] = bk;
+        if (m == 0) nb0 = bk; else if (m == 1) nb1 = bk; else if (m == 2) nb2 = bk; else nb3 = bk;
         ++m;
       }
     }
-    __syncwarp();
-    n = m;
+    perm = nperm; ids = nids; n = m;
+    bary0 = nb0; bary1 = nb1; bary2 = nb2; bary3 = nb3;
     float nv = len2(r.v);
     if (nv < 1e-14f) { status = 2; break; }
     if (have && nv >= vv) { v = r.v; break; }
     v = r.v;
     have = true;
   }
-  __syncwarp();
-  if (lane == 0) sx[SX_N] = __int_as_float(n);
-  __syncwarp();
-  if (status == 2) return 2;
+  if (status == 2) {
+    // EPA wants the simplex in logical order at slots 0..n-1
+    float rec[11];
+    const int src = (lane < 4) ? (int)((perm >> (2 * lane)) & 3u) : 0;
+    __syncwarp();
+    if (lane < 4) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t) { rec[t] = sx[SX_W + src * 3 + t]; rec[3 + t] = sx[SX_A + src * 3 + t]; rec[6 + t] = sx[SX_B + src * 3 + t]; }
+      rec[9] = sx[SX_IA + src]; rec[10] = sx[SX_IB + src];
+    }
+    __syncwarp();
+    if (lane < 4) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t) { sx[SX_W + lane * 3 + t] = rec[t]; sx[SX_A + lane * 3 + t] = rec[3 + t]; sx[SX_B + lane * 3 + t] = rec[6 + t]; }
+      sx[SX_IA + lane] = rec[9]; sx[SX_IB + lane] = rec[10];
+    }
+    if (lane == 0) sx[SX_N] = __int_as_float(n);
+    __syncwarp();
+    return 2;
+  }
   if (!have) return 0;
   V3 xa = v3(0, 0, 0), xb = v3(0, 0, 0);
-  for (int k = 0; k < n; ++k) {
-    float bk = (k == 0) ? bary[0] : (k == 1) ? bary[1] : (k == 2) ? bary[2] : bary[3];
-    xa = xa + LD3(sx + SX_A + k * 3) * bk;
-    xb = xb + LD3(sx + SX_B + k * 3) * bk;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < n) {
+      const int ph = (perm >> (2 * k)) & 3u;
+      float bk = (k == 0) ? bary0 : (k == 1) ? bary1 : (k == 2) ? bary2 : bary3;
+      xa = xa + LD3(sx + SX_A + ph * 3) * bk;
+      xb = xb + LD3(sx + SX_B + ph * 3) * bk;
+    }
   }
   *pa = xa; *pb = xb; *v_out = v;
   return 1;
@@ -478,10 +518,10 @@ __device__ __forceinline__ bool epa_face_plane(const float* ep, int i0, int i1, 
 }
 
 // add a support point to the GJK simplex (uniform); returns false when it is already there
-__device__ bool sx_add(const DWorld& W, const ColRef& A, const ColRef& B, float* sx, int* n, V3 d, int lane) {
+__device__ __noinline__ bool sx_add(const ColRef& A, const ColRef& B, float* sx, int* n, V3 d, int lane) {
   V3 a, b;
-  int ia = support(W, A, d, &a, lane);
-  int ib = support(W, B, -d, &b, lane);
+  int ia = support(A, d, &a, lane);
+  int ib = support(B, -d, &b, lane);
   for (int k = 0; k < *n; ++k) if (__float_as_int(sx[SX_IA + k]) == ia && __float_as_int(sx[SX_IB + k]) == ib) return false;
   __syncwarp();
   if (lane == 0) {
@@ -494,12 +534,12 @@ __device__ bool sx_add(const DWorld& W, const ColRef& A, const ColRef& B, float*
   return true;
 }
 
-__device__ bool epa_complete(const DWorld& W, const ColRef& A, const ColRef& B, float* sx, int* np, int lane) {
+__device__ __noinline__ bool epa_complete(const ColRef& A, const ColRef& B, float* sx, int* np, int lane) {
   int n = *np;
   if (n == 1) {
     for (int k = 0; k < 6 && n == 1; ++k) {
       V3 d = v3(k == 0 ? 1.f : k == 1 ? -1.f : 0.f, k == 2 ? 1.f : k == 3 ? -1.f : 0.f, k == 4 ? 1.f : k == 5 ? -1.f : 0.f);
-      sx_add(W, A, B, sx, &n, d, lane);
+      sx_add(A, B, sx, &n, d, lane);
     }
     if (n == 1) { *np = n; return false; }
   }
@@ -509,7 +549,7 @@ __device__ bool epa_complete(const DWorld& W, const ColRef& A, const ColRef& B, 
       V3 axis = v3(k == 0 ? 1.f : 0.f, k == 2 ? 1.f : 0.f, k == 4 ? 1.f : 0.f);
       V3 dir = cross(d, axis);
       if (len2(dir) < 1e-12f * len2(d)) continue;
-      if (!sx_add(W, A, B, sx, &n, dir, lane)) sx_add(W, A, B, sx, &n, -dir, lane);
+      if (!sx_add(A, B, sx, &n, dir, lane)) sx_add(A, B, sx, &n, -dir, lane);
       if (n == 3) {
         V3 w0 = LD3(sx + SX_W);
         V3 nn = cross(LD3(sx + SX_W + 3) - w0, LD3(sx + SX_W + 6) - w0);
@@ -522,12 +562,12 @@ __device__ bool epa_complete(const DWorld& W, const ColRef& A, const ColRef& B, 
     V3 w0 = LD3(sx + SX_W);
     V3 nn = cross(LD3(sx + SX_W + 3) - w0, LD3(sx + SX_W + 6) - w0);
     if (len2(nn) < 1e-20f) { *np = n; return false; }
-    if (!sx_add(W, A, B, sx, &n, nn, lane)) { if (!sx_add(W, A, B, sx, &n, -nn, lane)) { *np = n; return false; } }
+    if (!sx_add(A, B, sx, &n, nn, lane)) { if (!sx_add(A, B, sx, &n, -nn, lane)) { *np = n; return false; } }
     V3 e3 = LD3(sx + SX_W + 9) - w0;
     float vol = dot(e3, nn);
     if (vol * vol < 1e-12f * len2(nn) * len2(e3)) {
       n = 3;
-      if (!sx_add(W, A, B, sx, &n, -nn, lane)) { *np = n; return false; }
+      if (!sx_add(A, B, sx, &n, -nn, lane)) { *np = n; return false; }
       e3 = LD3(sx + SX_W + 9) - w0;
       vol = dot(e3, nn);
       if (vol * vol < 1e-12f * len2(nn) * len2(e3)) { *np = n; return false; }
@@ -537,10 +577,10 @@ __device__ bool epa_complete(const DWorld& W, const ColRef& A, const ColRef& B, 
   return n == 4;
 }
 
-__device__ int epa(const DWorld& W, const ColRef& A, const ColRef& B, float* sx, float* ep, V3* n_out, float* depth,
+__device__ __noinline__ int epa(const ColRef& A, const ColRef& B, float* sx, float* ep, V3* n_out, float* depth,
                    V3* pa, V3* pb, int lane) {
   int sn = __float_as_int(sx[SX_N]);
-  if (sn < 4 && !epa_complete(W, A, B, sx, &sn, lane)) return 0;
+  if (sn < 4 && !epa_complete(A, B, sx, &sn, lane)) return 0;
   __syncwarp();
   if (lane < 4) {
     ST3(ep + EP_W + lane * 3, LD3(sx + SX_W + lane * 3));
@@ -582,8 +622,8 @@ __device__ int epa(const DWorld& W, const ColRef& A, const ColRef& B, float* sx,
     bd = ep[EP_FD + best];
     V3 n = LD3(ep + EP_FN + best * 3);
     V3 a, b;
-    int ia = support(W, A, n, &a, lane);
-    int ib = support(W, B, -n, &b, lane);
+    int ia = support(A, n, &a, lane);
+    int ib = support(B, -n, &b, lane);
     V3 ww = a - b;
     float s = dot(ww, n);
     if (s - bd < 1e-6f) break;
@@ -658,11 +698,11 @@ __device__ int epa(const DWorld& W, const ColRef& A, const ColRef& B, float* sx,
   return 1;
 }
 
-__device__ int collide_pair(const DWorld& W, const ColRef& A, const ColRef& B, float threshold, float* sx, float* ep,
+__device__ int collide_pair(const ColRef& A, const ColRef& B, float threshold, float* sx, float* ep,
                             V3* pA, V3* pB, V3* normal, float* distance, int lane) {
   float msum = A.margin + B.margin;
   V3 v, pa, pb;
-  int st = gjk(W, A, B, msum + threshold, sx, &v, &pa, &pb, lane);
+  int st = gjk(A, B, msum + threshold, sx, &v, &pa, &pb, lane);
   if (st == 0) return 0;
   V3 n;
   float dist;
@@ -673,7 +713,7 @@ __device__ int collide_pair(const DWorld& W, const ColRef& A, const ColRef& B, f
   } else {
     V3 no;
     float depth;
-    if (!epa(W, A, B, sx, ep, &no, &depth, &pa, &pb, lane)) {
+    if (!epa(A, B, sx, ep, &no, &depth, &pa, &pb, lane)) {
       V3 c = A.cen - B.cen;
       float l2 = len2(c);
       n = (l2 < 1e-12f) ? v3(0.0f, 0.0f, 1.0f) : c * (1.0f / sqrtf(l2));
@@ -694,37 +734,24 @@ __device__ int collide_pair(const DWorld& W, const ColRef& A, const ColRef& B, f
 
 // ------------------------------------------------------------ substep -------
 
-struct WarpSmem {
-  float* body; float* col; int* pairs; int* oldkeys; int* cmk; float* con; int* order; int* colstart;
-  unsigned long long* used; float* stage; float* fk; float* sx;
-};
-
-__device__ __forceinline__ WarpSmem carve(const DWorld& W, float* base) {
-  WarpSmem s;
-  s.body = base + W.sm.body; s.col = base + W.sm.col; s.pairs = (int*)(base + W.sm.pairs);
-  s.oldkeys = (int*)(base + W.sm.oldkeys); s.cmk = (int*)(base + W.sm.cmk); s.con = base + W.sm.con;
-  s.order = (int*)(base + W.sm.order); s.colstart = (int*)(base + W.sm.colstart);
-  s.used = (unsigned long long*)(base + W.sm.used); s.stage = base + W.sm.stage; s.fk = base + W.sm.fk;
-  s.sx = base + W.sm.simplex;
-  return s;
-}
-
 #define BS(c, i) W.buf.body_state[((size_t)(c) * W.B + e) * W.Nmax + (i)]
 #define MPAR(c, i) W.mov_params[((size_t)(c) * W.B + e) * W.Nmax + (i)]
 
 // stages 1-6 of oracle substep(): controller, body table, colliders, broad phase, narrow phase, rows
-__device__ void substep_pre(const DWorld& W, int e, int lane, const WarpSmem& S, int* nc_out, int* newn_out) {
+// stage A: controller + FK, body table, collider AABBs, broad phase -> number of candidate pairs
+__device__ __noinline__ int stage_scene(int e, int lane, int wib) {
+  const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
   const float dt = (float)P.time_step;
   const int Ns = W.Ns, L = W.L, NB = W.NB, Nmax = W.Nmax;
   const int nm = W.buf.num_movables[e];
 
-  stage_arm(W, e, lane);
+  stage_arm(e, lane, wib);
   {
     float q[7], qd[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) { q[j] = W.buf.joint_state[(0 * 7 + j) * W.B + e]; qd[j] = W.buf.joint_state[(1 * 7 + j) * W.B + e]; }
-    arm_fk_links(W, e, lane, q, qd, S.fk, S.body);
+    arm_fk_links(e, lane, q, qd, wib);
   }
   // body table: statics + movables (links were written by arm_fk_links)
   const V3 g = v3(P.gravity[0], P.gravity[1], P.gravity[2]);
@@ -864,8 +891,17 @@ __device__ void substep_pre(const DWorld& W, int e, int lane, const WarpSmem& S,
   __syncwarp();
   for (int p = lane; p < np; p += 32) W.pair_keys[(size_t)e * P.max_pairs + p] = S.pairs[p];
   if (lane == 0) { W.num_pairs[e] = np; if (pair_over) W.error_flags[e] |= 1; }
+  __syncwarp();
+  (void)Nmax;
+  return np;
+}
 
-  // narrow phase + persistent manifolds (ping-pong buffers in HBM/L2)
+// stage B: narrow phase + persistent manifolds (ping-pong buffers in HBM/L2) -> contact list
+__device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int* nc_out, int* newn_out, bool build_rows) {
+  const WarpSmem S = carve(wib);
+  const B2SParams& P = W.P;
+  const float dt = (float)P.time_step;
+  const unsigned lt = (1u << lane) - 1u;
   const int M = P.max_manifolds;
   const int par = W.man_parity[e];
   const size_t obase = ((size_t)par * W.B + e) * M, nbase = ((size_t)(par ^ 1) * W.B + e) * M;
@@ -878,7 +914,7 @@ __device__ void substep_pre(const DWorld& W, int e, int lane, const WarpSmem& S,
   for (int p = 0; p < np; ++p) {
     const int key = S.pairs[p];
     const int a = key >> 16, b = key & 0xffff;
-    ColRef A = col_ref(W, S.col, S.body, a), Bc = col_ref(W, S.col, S.body, b);
+    ColRef A = col_ref(S.col, S.body, a), Bc = col_ref(S.col, S.body, b);
     const float* ca = S.col + a * COL_STRIDE;
     const float* cb = S.col + b * COL_STRIDE;
     const float threshold = P.breaking_factor * fminf(ca[CO_RAD], cb[CO_RAD]);
@@ -924,7 +960,7 @@ __device__ void substep_pre(const DWorld& W, int e, int lane, const WarpSmem& S,
     }
     V3 pA, pB, nrm;
     float dist;
-    if (collide_pair(W, A, Bc, threshold, S.sx, S.con, &pA, &pB, &nrm, &dist, lane)) {
+    if (collide_pair(A, Bc, threshold, S.sx, S.con, &pA, &pB, &nrm, &dist, lane)) {
       V3 lA = mtmul(A.R, pA - A.pos);
       V3 lB = mtmul(Bc.R, pB - Bc.pos);
       // manifold_add (uniform decisions, lane 0 writes)
@@ -984,9 +1020,9 @@ __device__ void substep_pre(const DWorld& W, int e, int lane, const WarpSmem& S,
   }
   __syncwarp();
 
-  // contact rows, one contact per lane
+  // contact rows, one contact per lane (generic path: rows in shared memory)
   const int nrows = 1 + P.friction_dirs;
-  for (int c = lane; c < ncon; c += 32) {
+  for (int c = lane; build_rows && c < ncon; c += 32) {
     const int mk = S.cmk[c];
     const int m = mk >> 2, k = mk & 3;
     const int key = W.man_keys[nbase + m];
@@ -1039,11 +1075,11 @@ __device__ void substep_pre(const DWorld& W, int e, int lane, const WarpSmem& S,
   __syncwarp();
   *nc_out = ncon;
   *newn_out = newn;
-  (void)Nmax;
 }
 
 // greedy colouring in contact order + stable sort by colour (oracle step 7)
-__device__ int colour_contacts(const DWorld& W, int e, int lane, const WarpSmem& S, int C) {
+__device__ __noinline__ int colour_contacts(int e, int lane, int wib, int C) {
+  const WarpSmem S = carve(wib);
   for (int s = lane; s < W.NB; s += 32) S.used[s] = 0ull;
   __syncwarp();
   int ncolours = 0;
@@ -1094,18 +1130,12 @@ __device__ __forceinline__ float row_jv(const float* row, const float* bA, const
 }
 __device__ __forceinline__ void row_apply(const float* row, float* bA, float* bB, float imA, float imB, bool dA, bool dB, float dl) {
   V3 dir = LD3(row + RW_DIR);
-  if (dA) {
-    ST3(bA + BO_VEL, LD3(bA + BO_VEL) + dir * (imA * dl));
-    ST3(bA + BO_ANG, LD3(bA + BO_ANG) + LD3(row + RW_IANGA) * dl);
-  }
-  if (dB) {
-    ST3(bB + BO_VEL, LD3(bB + BO_VEL) - dir * (imB * dl));
-    ST3(bB + BO_ANG, LD3(bB + BO_ANG) - LD3(row + RW_IANGB) * dl);
-  }
+  if (dA) { ST3(bA + BO_VEL, vmad(LD3(bA + BO_VEL), dir, imA * dl)); ST3(bA + BO_ANG, vmad(LD3(bA + BO_ANG), LD3(row + RW_IANGA), dl)); }
+  if (dB) { ST3(bB + BO_VEL, vmad(LD3(bB + BO_VEL), dir, -(imB * dl))); ST3(bB + BO_ANG, vmad(LD3(bB + BO_ANG), LD3(row + RW_IANGB), -dl)); }
 }
 
 // projected Gauss-Seidel over the colour-ordered rows held in shared memory (oracle step 8)
-__device__ int pgs_solve(const DWorld& W, int lane, float* body, float* con, const int* order, const int* colstart,
+__device__ __noinline__ int pgs_solve(int lane, float* body, float* con, const int* order, const int* colstart,
                          int C, int ncolours) {
   const B2SParams& P = W.P;
   const int nrows = 1 + P.friction_dirs;
@@ -1168,15 +1198,16 @@ __device__ int pgs_solve(const DWorld& W, int lane, float* body, float* con, con
 }
 
 // stages 7-9: colour, solve, write back impulses, integrate
-__device__ void substep_post(const DWorld& W, int e, int lane, const WarpSmem& S, int C, int newn) {
+__device__ __noinline__ void substep_post(int e, int lane, int wib, int C, int newn) {
+  const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
   const float dt = (float)P.time_step;
   const int Ns = W.Ns, L = W.L;
   const int nm = W.buf.num_movables[e];
   const int par = W.man_parity[e];          // already flipped: current buffer
   const size_t nbase = ((size_t)par * W.B + e) * P.max_manifolds;
-  int ncolours = colour_contacts(W, e, lane, S, C);
-  int iters = pgs_solve(W, lane, S.body, S.con, S.order, S.colstart, C, ncolours);
+  int ncolours = colour_contacts(e, lane, wib, C);
+  int iters = pgs_solve(lane, S.body, S.con, S.order, S.colstart, C, ncolours);
   for (int c = lane; c < C; c += 32) {
     const float* cn = S.con + c * CON_STRIDE;
     int mk = __float_as_int(cn[CN_MK]);
@@ -1214,9 +1245,177 @@ __device__ void substep_post(const DWorld& W, int e, int lane, const WarpSmem& S
   (void)newn;
 }
 
+// ---- register-resident solve (max_contacts <= 32 and NB <= 32): one contact per lane ----------
+// Each lane builds the three Jacobian rows of its contact in registers, colours are assigned with
+// per-body 64-bit masks distributed over the lanes (lane s holds the mask of body slot s), and the
+// Gauss-Seidel sweep runs colour by colour with only the body velocities in shared memory.
+struct RowR { V3 dir, angA, angB, iangA, iangB; float inv_d, d, bias, lam; };
+
+__device__ __forceinline__ float rowr_jv(const RowR& r, const float* bA, const float* bB) {
+  return ((dot(r.dir, LD3(bA + BO_VEL)) + dot(r.angA, LD3(bA + BO_ANG))) - dot(r.dir, LD3(bB + BO_VEL))) - dot(r.angB, LD3(bB + BO_ANG));
+}
+__device__ __forceinline__ void rowr_apply(const RowR& r, float* bA, float* bB, float imA, float imB, bool dA, bool dB, float dl) {
+  if (dA) { ST3(bA + BO_VEL, vmad(LD3(bA + BO_VEL), r.dir, imA * dl)); ST3(bA + BO_ANG, vmad(LD3(bA + BO_ANG), r.iangA, dl)); }
+  if (dB) { ST3(bB + BO_VEL, vmad(LD3(bB + BO_VEL), r.dir, -(imB * dl))); ST3(bB + BO_ANG, vmad(LD3(bB + BO_ANG), r.iangB, -dl)); }
+}
+
+__device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, int newn) {
+  const WarpSmem S = carve(wib);
+  const B2SParams& P = W.P;
+  const float dt = (float)P.time_step;
+  const int Ns = W.Ns, L = W.L;
+  const int nm = W.buf.num_movables[e];
+  const int par = W.man_parity[e];          // already flipped: current buffer
+  const size_t nbase = ((size_t)par * W.B + e) * P.max_manifolds;
+  const int nrows = 1 + P.friction_dirs;
+  const bool act = lane < C;
+  RowR R[3];
+  int sA = 0, sB = 0, mk = 0;
+  float mu = 0.0f, imA = 0.0f, imB = 0.0f;
+  bool dA = false, dB = false;
+  float* bA = S.body; float* bB = S.body;
+  if (act) {
+    mk = S.cmk[lane];
+    const int m = mk >> 2, k = mk & 3;
+    const int key = W.man_keys[nbase + m];
+    const int a = key >> 16, b = key & 0xffff;
+    sA = __float_as_int(S.col[a * COL_STRIDE + CO_SLOT]); sB = __float_as_int(S.col[b * COL_STRIDE + CO_SLOT]);
+    bA = S.body + sA * BODY_STRIDE; bB = S.body + sB * BODY_STRIDE;
+    const float* p = W.man_pts + ((nbase + m) * 4 + k) * B2S_CP_FLOATS;
+    V3 posA = LD3(bA + BO_POS), posB = LD3(bB + BO_POS);
+    V3 wA = posA + mmul(ldm3(bA + BO_R), v3(p[0], p[1], p[2]));
+    V3 wB = posB + mmul(ldm3(bB + BO_R), v3(p[3], p[4], p[5]));
+    V3 n = v3(p[6], p[7], p[8]);
+    V3 rA = wA - posA, rB = wB - posB;
+    V3 t1, t2;
+    plane_space(n, &t1, &t2);
+    if (P.friction_dirs == 1) {
+      V3 rel = (LD3(bA + BO_VEL) + cross(LD3(bA + BO_ANG), rA)) - (LD3(bB + BO_VEL) + cross(LD3(bB + BO_ANG), rB));
+      V3 lat = rel - n * dot(rel, n);
+      float l2 = len2(lat);
+      if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
+    }
+    imA = bA[BO_INVM]; imB = bB[BO_INVM];
+    const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
+      R[r].dir = dir;
+      R[r].angA = cross(rA, dir); R[r].angB = cross(rB, dir);
+      R[r].iangA = mmul(iA, R[r].angA); R[r].iangB = mmul(iB, R[r].angB);
+      float d = ((imA + imB) + dot(R[r].iangA, R[r].angA)) + dot(R[r].iangB, R[r].angB);
+      R[r].inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
+      R[r].d = d;
+      R[r].bias = 0.0f;
+      float lam = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
+      if (r >= nrows) lam = 0.0f;
+      R[r].lam = lam;
+    }
+    float pen = p[9] + P.linear_slop;
+    R[0].bias = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
+    mu = bA[BO_FRIC] * bB[BO_FRIC];
+    dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC; dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
+  }
+  // greedy colouring in contact order; lane s keeps the colour mask of body slot s
+  unsigned long long used = 0ull;
+  int mycol = -1, ncolours = 0;
+  bool col_over = false;
+  for (int i = 0; i < C; ++i) {
+    const int isA = __shfl_sync(FULL, sA, i), isB = __shfl_sync(FULL, sB, i);
+    const bool idA = __shfl_sync(FULL, (int)dA, i) != 0, idB = __shfl_sync(FULL, (int)dB, i) != 0;
+    unsigned long long mA = __shfl_sync(FULL, used, isA), mB = __shfl_sync(FULL, used, isB);
+    unsigned long long mask = (idA ? mA : 0ull) | (idB ? mB : 0ull);
+    if (mask == ~0ull) { col_over = true; continue; }
+    const int k = __ffsll((long long)~mask) - 1;
+    if (lane == i) mycol = k;
+    if (k + 1 > ncolours) ncolours = k + 1;
+    if ((idA && lane == isA) || (idB && lane == isB)) used |= 1ull << k;
+  }
+  if (col_over && lane == 0) W.error_flags[e] |= 16;
+  const bool on = act && mycol >= 0;
+  // warm start
+  for (int k = 0; k < ncolours; ++k) {
+    if (on && mycol == k) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) if (r < nrows) rowr_apply(R[r], bA, bB, imA, imB, dA, dB, R[r].lam);
+    }
+    __syncwarp();
+  }
+  int iters = 0;
+  for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
+    float maxres = 0.0f;
+    for (int k = 0; k < ncolours; ++k) {
+      if (on && mycol == k) {
+        float dl = (R[0].bias - rowr_jv(R[0], bA, bB)) * R[0].inv_d;
+        float nl = fmaxf(0.0f, R[0].lam + dl);
+        dl = nl - R[0].lam;
+        R[0].lam = nl;
+        rowr_apply(R[0], bA, bB, imA, imB, dA, dB, dl);
+        float res = dl * R[0].d;
+        maxres = fmaxf(maxres, res * res);
+      }
+      __syncwarp();
+    }
+    for (int k = 0; k < ncolours; ++k) {
+      if (on && mycol == k) {
+        const float lim = mu * R[0].lam;
+#pragma unroll
+        for (int r = 1; r < 3; ++r) {
+          if (r < nrows) {
+            float dl = (0.0f - rowr_jv(R[r], bA, bB)) * R[r].inv_d;
+            float nl = fminf(lim, fmaxf(-lim, R[r].lam + dl));
+            dl = nl - R[r].lam;
+            R[r].lam = nl;
+            rowr_apply(R[r], bA, bB, imA, imB, dA, dB, dl);
+            float res = dl * R[r].d;
+            maxres = fmaxf(maxres, res * res);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    iters = it + 1;
+    unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
+    if (__uint_as_float(mx) <= P.residual_threshold) break;
+  }
+  if (act) {
+    float* p = W.man_pts + ((nbase + (mk >> 2)) * 4 + (mk & 3)) * B2S_CP_FLOATS;
+    p[10] = R[0].lam; p[11] = R[1].lam; p[12] = R[2].lam;
+  }
+  if (lane == 0) {
+    int32_t* st = W.solver_stats + (size_t)e * 4;
+    st[0] = C * nrows; st[1] = ncolours; st[2] = iters; st[3] = C;
+  }
+  __syncwarp();
+  bool bad = false;
+  for (int i = lane; i < nm; i += 32) {
+    const float* b = S.body + (Ns + L + i) * BODY_STRIDE;
+    V3 ang = LD3(b + BO_ANG), vel = LD3(b + BO_VEL);
+    float wl = len(ang);
+    if (wl * dt > B2S_HALF_PI) ang = ang * (B2S_HALF_PI / (wl * dt));
+    V3 pos = LD3(b + BO_POS) + vel * dt;
+    Q4 qq = q_integrate(q4(b[BO_QUAT], b[BO_QUAT + 1], b[BO_QUAT + 2], b[BO_QUAT + 3]), ang, dt);
+    BS(0, i) = pos.x; BS(1, i) = pos.y; BS(2, i) = pos.z;
+    BS(3, i) = qq.x; BS(4, i) = qq.y; BS(5, i) = qq.z; BS(6, i) = qq.w;
+    BS(7, i) = vel.x; BS(8, i) = vel.y; BS(9, i) = vel.z;
+    BS(10, i) = ang.x; BS(11, i) = ang.y; BS(12, i) = ang.z;
+    float chk = (pos.x + pos.y) + pos.z;
+    if (!(fabsf(chk) < 1e6f)) bad = true;
+  }
+  if (__any_sync(FULL, bad) && lane == 0) W.error_flags[e] |= 4;
+  if (lane < 7) {
+    float q = W.buf.joint_state[(0 * 7 + lane) * W.B + e], qd = W.buf.joint_state[(1 * 7 + lane) * W.B + e];
+    W.buf.joint_state[(0 * 7 + lane) * W.B + e] = q + qd * dt;
+  }
+  __syncwarp();
+  if (lane == 0) W.num_steps[e] += 1;
+  __syncwarp();
+  (void)newn;
+}
+
 // -------------------------------------------------------- phase machine -----
 
-__device__ void movable_status(const DWorld& W, int e, int lane, int which) {
+__device__ void movable_status(int e, int lane, int which) {
   for (int i = lane; i < W.Nmax; i += 32) {
     float* s = W.status + (((size_t)e * 2 + which) * W.Nmax + i) * 4;
     if (i < W.buf.num_movables[e]) {
@@ -1227,7 +1426,8 @@ __device__ void movable_status(const DWorld& W, int e, int lane, int which) {
   __syncwarp();
 }
 
-__device__ void phase_logic(const DWorld& W, int e, int lane, float* fk) {
+__device__ __noinline__ void phase_logic(int e, int lane, int wib) {
+  float* fk = carve(wib).fk;
   const B2SParams& P = W.P;
   int32_t* ps = W.phase_state + (size_t)e * 8;
   int ph = W.phase[e];
@@ -1237,7 +1437,7 @@ __device__ void phase_logic(const DWorld& W, int e, int lane, float* fk) {
   bool ready, reset_t = false;
   if (interrupt) ready = true;
   else {
-    int lr = arm_is_ready(W, e, lane);
+    int lr = arm_is_ready(e, lane);
     if (lr && (P.time_step * (double)nsteps >= W.ctrl_time[(size_t)e * 5 + 4])) { reset_t = true; ready = true; }
     else if (ps0 < 0) ready = true;
     else if (nsteps >= ps0) { reset_t = true; ready = true; }
@@ -1250,10 +1450,8 @@ __device__ void phase_logic(const DWorld& W, int e, int lane, float* fk) {
     float q[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) q[j] = W.buf.joint_state[(0 * 7 + j) * W.B + e];
-    Xf frame[B2S_NUM_JOINTS];
-    V3 ax[B2S_NUM_JOINTS], org[B2S_NUM_JOINTS];
-    fk_chain(W.arm, q, frame, ax, org);
-    xf_store(xf_mul(frame[B2S_NUM_JOINTS - 1], xf_from(W.arm->ee)), ee);
+    fk_chain(W.arm, q, lane, wib);
+    xf_store(xf_mul(xf_from(fk + 6 * 7), xf_from(W.arm->ee)), ee);
   }
   int ps1 = ps[1];
   int new_ps0 = ps0;
@@ -1267,26 +1465,26 @@ __device__ void phase_logic(const DWorld& W, int e, int lane, float* fk) {
 #pragma unroll
       for (int k = 0; k < 7; ++k) pose[k] = wp[k];
       pose[2] = P.gripper_safe_height;
-      arm_set_link_target(W, e, lane, pose);
+      arm_set_link_target(e, lane, pose);
     } else if (ph == B2S_PHASE_START) {
 #pragma unroll
       for (int k = 0; k < 7; ++k) pose[k] = wp[k];
-      arm_set_link_target(W, e, lane, pose);
+      arm_set_link_target(e, lane, pose);
     } else if (ph == B2S_PHASE_MOTION) {
 #pragma unroll
       for (int k = 0; k < 7; ++k) pose[k] = wp[7 + k];
-      arm_set_link_target(W, e, lane, pose);
+      arm_set_link_target(e, lane, pose);
     } else if (ph == B2S_PHASE_POST) {
       ps1 += 1;
 #pragma unroll
       for (int k = 0; k < 7; ++k) pose[k] = ee[k];
       pose[2] = P.gripper_safe_height;
-      arm_set_link_target(W, e, lane, pose);
+      arm_set_link_target(e, lane, pose);
     } else if (ph == B2S_PHASE_OFFSTAGE) {
       float q[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) q[k] = P.offstage_positions[k];
-      arm_set_joint_target(W, e, lane, q);
+      arm_set_joint_target(e, lane, q);
     }
   }
   interrupt = false;
@@ -1323,7 +1521,7 @@ __device__ void phase_logic(const DWorld& W, int e, int lane, float* fk) {
   (void)fk;
 }
 
-__device__ bool all_stable(const DWorld& W, int e, int lane, float lin, float ang) {
+__device__ bool all_stable(int e, int lane, float lin, float ang) {
   bool moving = false;
   for (int i = lane; i < W.buf.num_movables[e]; i += 32) {
     float lv = len(v3(BS(7, i), BS(8, i), BS(9, i)));
@@ -1333,9 +1531,9 @@ __device__ bool all_stable(const DWorld& W, int e, int lane, float lin, float an
   return !__any_sync(FULL, moving);
 }
 
-__device__ void finish_action(const DWorld& W, int e, int lane) {
+__device__ __noinline__ void finish_action(int e, int lane) {
   const B2SParams& P = W.P;
-  movable_status(W, e, lane, 1);
+  movable_status(e, lane, 1);
   // sums are sequential over bodies in the oracle: lane 0 does them (Nmax is small)
   if (lane == 0) {
     float dp = 0.0f, da = 0.0f;
@@ -1353,80 +1551,143 @@ __device__ void finish_action(const DWorld& W, int e, int lane) {
 
 // ----------------------------------------------------------- the kernel -----
 
-extern __shared__ float b2s_smem[];
-
-__global__ void __launch_bounds__(128) k_substeps(const __grid_constant__ DWorld W, int n, int mode, float lin, float ang,
-                                                  int max_steps) {
+// Block = Wn warps stepping E environments.  Every substep runs three stages separated by block barriers
+// (scene -> narrow phase -> solve/integrate/phase logic); inside a stage the warps take environments from
+// a shared counter, so a warp stuck on a long solve does not hold the others back, and all warps of the
+// block execute the same code region at the same time (the kernel is far larger than the instruction
+// cache; walking it together is what keeps instruction fetch from dominating).
+__global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps) {
+  __shared__ int s_cnt[3];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int e = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (e >= W.B) return;
-  WarpSmem S = carve(W, b2s_smem + (size_t)wib * W.sm.words);
+  const int Wn = blockDim.x >> 5;
+  const int E = W.envs_per_block;
+  const int e0 = blockIdx.x * E;
   const B2SParams& P = W.P;
+  for (int slot = wib; slot < E; slot += Wn)
+    if (lane < META_WORDS) env_meta(slot)[lane] = 0;
+  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
+  __syncthreads();
   int done_steps = 0;
-  if (mode == MODE_RAW) {
-    for (int s = 0; s < n; ++s) {
-      int C, newn;
-      substep_pre(W, e, lane, S, &C, &newn);
-      substep_post(W, e, lane, S, C, newn);
-      ++done_steps;
-    }
-  } else if (mode == MODE_ENV) {
-    for (int s = 0; s < n; ++s) {
-      int ph = W.phase[e];
-      if (ph == B2S_PHASE_IDLE) break;
-      int32_t* ps = W.phase_state + (size_t)e * 8;
-      int C, newn;
-      substep_pre(W, e, lane, S, &C, &newn);
-      substep_post(W, e, lane, S, C, newn);
-      ++done_steps;
-      if (ph < B2S_PHASE_DONE) {
-        if (W.num_steps[e] % P.steps_check != 0) continue;
-        phase_logic(W, e, lane, S.fk);
-        if (W.phase[e] == B2S_PHASE_DONE) {
-          if (lane == 0) { W.phase[e] = B2S_PHASE_SETTLE; ps[2] = 0; ps[3] = 0; }
-          __syncwarp();
-        }
-      } else {
-        int s2 = ps[2] + 1, s3 = ps[3];
-        __syncwarp();
-        bool fin = false;
-        if (s2 >= P.stable_check_after) {
-          if (all_stable(W, e, lane, P.stable_lin_threshold, P.stable_ang_threshold)) s3 += 1;
-          if (s3 >= P.stable_min_steps || s2 >= P.stable_max_steps) fin = true;
-        }
-        if (lane == 0) { ps[2] = s2; ps[3] = s3; }
-        __syncwarp();
-        if (fin) finish_action(W, e, lane);
+  int any_next = 0;
+  for (int s = 0;; ++s) {
+    int any = any_next;
+    if (s == 0) {
+      for (int slot = wib; slot < E; slot += Wn) {
+        const int e = e0 + slot;
+        const bool valid = e < W.B;
+        bool active;
+        if (mode == MODE_RAW) active = valid && n > 0;
+        else if (mode == MODE_ENV) active = valid && n > 0 && W.phase[valid ? e : 0] != B2S_PHASE_IDLE;
+        else active = valid;
+        if (lane == 0) env_meta(slot)[META_ACTIVE] = active ? 1 : 0;
+        any |= active ? 1 : 0;
       }
     }
-    if (lane == 0 && W.phase[e] != B2S_PHASE_IDLE) atomicAdd(W.unfinished, 1);
-  } else {   // MODE_SETTLE: Simulator.wait_until_stable for this env
-    int steps = 0, stable = 0;
-    while (true) {
-      int C, newn;
-      substep_pre(W, e, lane, S, &C, &newn);
-      substep_post(W, e, lane, S, C, newn);
+    any_next = 0;
+    if (!__syncthreads_or(any)) break;
+    if (threadIdx.x == 0) s_cnt[2] = 0;
+    // ---- stage A: controller + FK, body table, colliders, broad phase
+    for (;;) {
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&s_cnt[0], 1);
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot >= E) break;
+      int* meta = env_meta(slot);
+      if (!meta[META_ACTIVE]) continue;
+      const int np = stage_scene(e0 + slot, lane, slot | (wib << 16));
+      if (lane == 0) meta[META_NP] = np;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_cnt[0] = 0;
+    // ---- stage B: narrow phase + manifolds
+    for (;;) {
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&s_cnt[1], 1);
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot >= E) break;
+      int* meta = env_meta(slot);
+      if (!meta[META_ACTIVE]) continue;
+      int C = 0, newn = 0;
+      stage_narrow(e0 + slot, lane, slot | (wib << 16), meta[META_NP], &C, &newn, !W.reg_rows);
+      if (lane == 0) { meta[META_C] = C; meta[META_NEWN] = newn; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_cnt[1] = 0;
+    // ---- stage C: solve, integrate, phase machine / settle bookkeeping
+    for (;;) {
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&s_cnt[2], 1);
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot >= E) break;
+      int* meta = env_meta(slot);
+      if (!meta[META_ACTIVE]) continue;
+      const int e = e0 + slot;
+      const int sw = slot | (wib << 16);
+      const int ph = (mode == MODE_ENV) ? W.phase[e] : B2S_PHASE_IDLE;
+      if (W.reg_rows) substep_post_reg(e, lane, sw, meta[META_C], meta[META_NEWN]);
+      else substep_post(e, lane, sw, meta[META_C], meta[META_NEWN]);
       ++done_steps;
-      ++steps;
-      if (steps < P.stable_check_after) continue;
-      if (all_stable(W, e, lane, lin, ang)) ++stable;
-      if (stable >= P.stable_min_steps || steps >= max_steps) break;
+      bool nxt = (s + 1 < n);
+      if (mode == MODE_ENV) {
+        int32_t* ps = W.phase_state + (size_t)e * 8;
+        if (ph < B2S_PHASE_DONE) {
+          if (W.num_steps[e] % P.steps_check == 0) {
+          phase_logic(e, lane, sw);
+          if (W.phase[e] == B2S_PHASE_DONE) {
+            if (lane == 0) { W.phase[e] = B2S_PHASE_SETTLE; ps[2] = 0; ps[3] = 0; }
+            __syncwarp();
+          }
+          }
+        } else {
+          int s2 = ps[2] + 1, s3 = ps[3];
+          __syncwarp();
+          bool fin = false;
+          if (s2 >= P.stable_check_after) {
+            if (all_stable(e, lane, P.stable_lin_threshold, P.stable_ang_threshold)) s3 += 1;
+            if (s3 >= P.stable_min_steps || s2 >= P.stable_max_steps) fin = true;
+          }
+          if (lane == 0) { ps[2] = s2; ps[3] = s3; }
+          __syncwarp();
+          if (fin) finish_action(e, lane);
+        }
+        nxt = nxt && (W.phase[e] != B2S_PHASE_IDLE);
+      } else if (mode == MODE_SETTLE) {   // Simulator.wait_until_stable for this env
+        const int steps = meta[META_SETTLE_STEPS] + 1;
+        int stable = meta[META_SETTLE_STABLE];
+        __syncwarp();
+        bool fin = false;
+        if (steps >= P.stable_check_after) {
+          if (all_stable(e, lane, lin, ang)) ++stable;
+          if (stable >= P.stable_min_steps || steps >= max_steps) fin = true;
+        }
+        if (lane == 0) { meta[META_SETTLE_STEPS] = steps; meta[META_SETTLE_STABLE] = stable; meta[META_FINISHED] = fin ? 1 : 0; }
+        __syncwarp();
+        nxt = !fin;
+      }
+      // activity of this environment in the next substep, published by the warp that just stepped it
+      if (lane == 0) meta[META_ACTIVE] = nxt ? 1 : 0;
+      any_next |= nxt ? 1 : 0;
     }
   }
+  if (mode == MODE_ENV)
+    for (int slot = wib; slot < E; slot += Wn)
+      if (e0 + slot < W.B && lane == 0 && W.phase[e0 + slot] != B2S_PHASE_IDLE) atomicAdd(W.unfinished, 1);
   if (lane == 0 && done_steps) atomicAdd(W.substeps, (unsigned long long)done_steps);
 }
 
+#undef W
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, cudaStream_t s) {
   const int wpb = W.P.warps_per_block;
-  const int blocks = (W.B + wpb - 1) / wpb;
+  const int blocks = (W.B + W.envs_per_block - 1) / W.envs_per_block;
   size_t smem = b2s_smem_bytes(W);
   static size_t configured = 0;
   if (smem > configured) {
     cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  k_substeps<<<blocks, wpb * 32, smem, s>>>(W, n, mode, lin, ang, max_steps);
+  cudaMemcpyToSymbolAsync(g_W, &W, sizeof(DWorld), 0, cudaMemcpyHostToDevice, s);
+  k_substeps<<<blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps);
 }
 
-size_t b2s_smem_bytes(const DWorld& W) { return (size_t)W.sm.words * 4 * W.P.warps_per_block; }
+size_t b2s_smem_bytes(const DWorld& W) { return ((size_t)W.envs_per_block * W.sm.words_env + (size_t)W.P.warps_per_block * W.sm.words_warp) * 4; }

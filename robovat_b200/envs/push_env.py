@@ -1,0 +1,314 @@
+"""PushEnv over the batched CUDA world.
+
+Keeps the call surface of the reference environment
+(robovat/envs/push/push_env.py:32-937 on top of robovat/envs/robot_env.py:40-324):
+`reset() -> OrderedDict`, `step(action) -> (obs, reward, done, None)`, `observations`,
+`reward_fns`, `action_space`, `simulator`, `movable_bodies`, `robot`, `table`,
+`attributes`, the statistics counters and the step-after-done ValueError.  With
+`num_envs == 1` every observation has the reference's unbatched shape, so
+`HeuristicPushPolicy` (robovat/policies/push_policy.py:33-52) runs unchanged; with
+`num_envs > 1` every array gains a leading batch axis and `done` is a bool array.
+
+What runs where: the per-substep loop of `_execute_action` (phase machine, arm
+control, physics, settle) is `b2s_env_substeps`; `get_observation` is `b2s_observe`
+(+ `b2s_render`/`b2s_point_cloud` when the point-cloud observation is on);
+`get_reward` is `b2s_reward`.  Python only moves actions in and results out.
+"""
+import collections
+
+import numpy as np
+import torch
+
+from robovat_b200 import _capi, config as config_lib
+from robovat_b200.simulation.simulator import Simulator
+
+
+class Box(object):
+    """Stand-in for gym.spaces.Box (gym is not a dependency here)."""
+
+    def __init__(self, low, high, dtype=np.float32):
+        self.low = np.asarray(low, dtype=dtype)
+        self.high = np.asarray(high, dtype=dtype)
+        self.shape = self.low.shape
+        self.dtype = dtype
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape[-len(self.shape):] == self.shape and np.all(x >= self.low) and np.all(x <= self.high)
+
+
+class _Obs(object):
+    """One named observation (robovat/observations/observation.py:11-40)."""
+
+    def __init__(self, name, fn):
+        self.name = name
+        self._fn = fn
+        self.env = None
+
+    def initialize(self, env):
+        self.env = env
+
+    def on_episode_start(self):
+        pass
+
+    def on_episode_end(self):
+        pass
+
+    def get_observation(self):
+        return self._fn()
+
+
+class PushReward(object):
+    """robovat/reward_fns/push_reward.py:377-405 over the reward kernel."""
+
+    def __init__(self, name, task_name, layout_id, is_planning=False):
+        if is_planning:
+            raise NotImplementedError('is_planning=True is a model-based-planning path, not the env path')
+        self.name = name
+        self.task_name = task_name
+        self.layout_id = layout_id
+        self.env = None
+
+    def initialize(self, env):
+        self.env = env
+
+    def on_episode_start(self):
+        pass
+
+    def on_episode_end(self):
+        pass
+
+    def get_reward(self):
+        env = self.env
+        assert env.prev_obs_data is not None
+        assert env.obs_data is not None
+        reward, termination = env.world.reward()          # previous xy is kept on the device
+        reward = reward.cpu().numpy()
+        termination = termination.cpu().numpy().astype(bool)
+        if env.num_envs == 1:
+            return float(reward[0]), bool(termination[0])
+        return reward, termination
+
+
+class PushEnv(object):
+    """Pushing task environment, B copies stepped together on the GPU."""
+
+    def __init__(self, simulator=None, config=None, debug=False, num_envs=1, seed=0, device=0, env_id_offset=0):
+        self._config = config or config_lib.default_push_env_config()
+        self._debug = debug
+        self.num_envs = int(num_envs)
+        self.seed = int(seed)
+        cfg = self._config
+        self.task_name = cfg.TASK_NAME
+        self.layout_id = cfg.LAYOUT_ID
+        if self.task_name in (None, 'data_collection'):
+            self.layouts, self.num_layouts = None, 1
+        else:
+            from robovat_b200 import layouts
+            self.layouts = layouts.TASK_NAME_TO_LAYOUTS[self.task_name]
+            self.num_layouts = len(self.layouts)
+        self.num_goal_steps = cfg.NUM_GOAL_STEPS
+        if self.num_goal_steps is not None:
+            raise NotImplementedError('NUM_GOAL_STEPS (multi-waypoint actions) is not on the path yet')
+        self.cspace = Box(cfg.ACTION.CSPACE.LOW, cfg.ACTION.CSPACE.HIGH)
+        start_low = np.array(cfg.ACTION.CSPACE.LOW, dtype=np.float32)
+        start_high = np.array(cfg.ACTION.CSPACE.HIGH, dtype=np.float32)
+        self.start_offset = 0.5 * (start_high + start_low)
+        self.start_range = 0.5 * (start_high - start_low)
+        self.start_z = cfg.ARM.FINGER_TIP_OFFSET + self.start_offset[2]
+        self.min_movable_bodies = cfg.MIN_MOVABLE_BODIES
+        self.max_movable_bodies = cfg.MAX_MOVABLE_BODIES
+        self.phase_list = ['initial', 'pre', 'start', 'motion', 'post', 'offstage', 'done']
+
+        use_camera = bool(cfg.get('USE_POINT_CLOUD_OBS', False) or cfg.USE_VISUALIZATION_OBS)
+        if simulator is None or simulator is True:
+            simulator = Simulator(config=cfg, num_envs=self.num_envs, device=device, with_camera=use_camera,
+                                  env_id_offset=env_id_offset)
+        self._simulator = simulator
+        self.world = simulator.world
+        self.use_camera = use_camera
+        if use_camera:
+            self.camera = simulator.create_camera(cfg.KINECT2.DEPTH)
+        else:
+            self.camera = None
+        tx, ty = cfg.SIM.TABLE.POSE[0][0], cfg.SIM.TABLE.POSE[0][1]
+        self.table_workspace = Box([tx - 0.5 * cfg.TABLE.X_RANGE, ty - 0.5 * cfg.TABLE.Y_RANGE],
+                                   [tx + 0.5 * cfg.TABLE.X_RANGE, ty + 0.5 * cfg.TABLE.Y_RANGE])
+        B = self.num_envs
+        self._num_episodes = np.zeros(B, np.int64)
+        self._num_steps = np.zeros(B, np.int64)
+        self._episode_reward = np.zeros(B, np.float64)
+        self._total_reward = np.zeros(B, np.float64)
+        self._done = np.ones(B, bool)
+        self.num_total_steps = 0
+        self.num_unsafe = self.num_ineffective = self.num_useful = self.num_successes = 0
+        self.num_successes_by_step = [0] * int(cfg.MAX_STEPS + 1)
+        self.attributes = None
+        self._obs_data = self._prev_obs_data = None
+        self.substep_chunk = int(cfg.get('SUBSTEP_CHUNK', 250))
+        self.max_action_substeps = int(cfg.get('MAX_ACTION_SUBSTEPS', 60000))
+        self._pinned_action = torch.zeros(B, 4, dtype=torch.float32).pin_memory()
+        self._observations = self._create_observations()
+        for obs in self._observations:
+            obs.initialize(self)
+        self._reward_fns = [PushReward('reward', self.task_name, self.layout_id)]
+        for fn in self._reward_fns:
+            fn.initialize(self)
+        self._action_space = Box(-np.ones(4, np.float32), np.ones(4, np.float32))
+        self._reset_count = 0
+
+    # -- reference properties ---------------------------------------------------------------
+    simulator = property(lambda self: self._simulator)
+    config = property(lambda self: self._config)
+    debug = property(lambda self: self._debug)
+    is_simulation = property(lambda self: True)
+    observations = property(lambda self: self._observations)
+    reward_fns = property(lambda self: self._reward_fns)
+    action_space = property(lambda self: self._action_space)
+    obs_data = property(lambda self: self._obs_data)
+    prev_obs_data = property(lambda self: self._prev_obs_data)
+    robot = property(lambda self: self._simulator.robot)
+    table = property(lambda self: self._simulator.table)
+    movable_bodies = property(lambda self: self._simulator.movable_bodies)
+
+    def _scalar(self, a):
+        return a[0] if self.num_envs == 1 else a
+
+    num_episodes = property(lambda self: self._scalar(self._num_episodes))
+    num_steps = property(lambda self: self._scalar(self._num_steps))
+    episode_reward = property(lambda self: self._scalar(self._episode_reward))
+    total_reward = property(lambda self: self._scalar(self._total_reward))
+    done = property(lambda self: self._scalar(self._done))
+
+    # -- observations (push_env.py:163-236) ---------------------------------------------------
+    def _batched(self, a):
+        a = np.asarray(a)
+        return a[0] if self.num_envs == 1 else a
+
+    def _create_observations(self):
+        w = self.world
+        obs = [
+            _Obs('num_episodes', lambda: self._batched(self.attributes['num_episodes'])),
+            _Obs('num_steps', lambda: self._batched(self.attributes['num_steps'])),
+            _Obs('layout_id', lambda: np.array(self.layout_id, dtype=np.int64) if self.num_envs == 1
+                 else np.full(self.num_envs, self.layout_id, np.int64)),
+            _Obs('body_mask', lambda: self._batched(self.attributes['movable_body_mask'].astype(np.float32))),
+        ]
+        if self.use_camera:
+            obs.append(_Obs('point_cloud', lambda: self._batched(self._point_cloud())))
+        if self._config.USE_PRESTIGE_OBS:
+            obs += [
+                _Obs('position', lambda: self._batched(w.observe().cpu().numpy())),
+                _Obs('is_safe', lambda: self._batched(self.attributes['is_safe'].astype(np.int64))),
+                _Obs('is_effective', lambda: self._batched(self.attributes['is_effective'].astype(np.int64))),
+            ]
+        return obs
+
+    def _point_cloud(self):
+        self.world.render()
+        self._pc_seed = getattr(self, '_pc_seed', 0) + 1
+        return self.world.point_cloud(seed=self.seed * 7919 + self._pc_seed).cpu().numpy()
+
+    def _refresh_attributes(self):
+        w = self.world
+        self.attributes = {
+            'num_episodes': self._num_episodes.copy(),
+            'num_steps': self._num_steps.copy(),
+            'layout_id': self.layout_id,
+            'movable_body_mask': w.body_mask.cpu().numpy(),
+            'is_safe': w.is_safe.cpu().numpy().astype(bool),
+            'is_effective': w.is_effective.cpu().numpy().astype(bool),
+        }
+
+    # -- gym API (robot_env.py:202-310) -------------------------------------------------------
+    def reset(self, mask=None):
+        """Reset every env (or the envs in `mask`): new scene, movables dropped and settled."""
+        B = self.num_envs
+        m = np.ones(B, bool) if mask is None else np.asarray(mask, bool).reshape(B)
+        self._num_steps[m] = 0
+        self._episode_reward[m] = 0.0
+        self._done[m] = False
+        if self._config.MAX_STEPS is not None and self._config.MAX_STEPS == 0:
+            self._done[m] = True
+        self._simulator.reset_scene(seed=self.seed, mask=None if mask is None else m)
+        self._refresh_attributes()
+        self._obs_data = self._prev_obs_data = None
+        return self.get_observation(force=True)
+
+    def get_observation(self, force=False):
+        if force or self._obs_data is None:
+            data = collections.OrderedDict()
+            for obs in self._observations:
+                data[obs.name] = obs.get_observation()
+            self._prev_obs_data, self._obs_data = self._obs_data, data
+        return self._obs_data
+
+    def step(self, action):
+        if np.all(self._done):
+            raise ValueError('The environment is done. Forget to reset?')
+        active = ~self._done
+        self._execute_action(action)
+        self._num_steps[active] += 1
+        self._refresh_attributes()
+        observation = self.get_observation(force=True)
+        reward, termination = self._reward_fns[0].get_reward()
+        reward = np.atleast_1d(np.asarray(reward, np.float64))
+        termination = np.atleast_1d(np.asarray(termination, bool))
+        reward = np.where(active, reward, 0.0)
+        self._episode_reward += reward
+        env_done = self.world.array(_capi.ARR_PHASE_STATE).view(self.num_envs, 8)[:, 4].cpu().numpy() != 0
+        self._done = self._done | (active & (termination | env_done))
+        if self._config.MAX_STEPS is not None:
+            self._done |= self._num_steps >= self._config.MAX_STEPS
+        finished = active & self._done
+        if self.num_envs == 1 and finished[0] and reward[0] >= self._config.SUCCESS_THRESH:
+            self.num_successes += 1
+            self.num_successes_by_step[int(self._num_steps[0])] += 1
+        self._num_episodes[finished] += 1
+        self._total_reward[finished] += self._episode_reward[finished]
+        if self.num_envs == 1:
+            return observation, float(reward[0]), bool(self._done[0]), None
+        return observation, reward.astype(np.float32), self._done.copy(), None
+
+    def _execute_action(self, action):
+        """push_env.py:631-733: the whole loop runs on the device."""
+        a = np.asarray(action, dtype=np.float32).reshape(-1, 4)
+        if a.shape[0] != self.num_envs:
+            raise ValueError('action must have shape [%d, 4] (or [4] / [1, 4] for one env)' % self.num_envs)
+        self._pinned_action.copy_(torch.from_numpy(a))
+        self.world.action.copy_(self._pinned_action, non_blocking=True)
+        self.world.set_action()
+        if np.any(self._done):                     # finished envs do not execute (reference raises instead)
+            ph = self.world.array(_capi.ARR_PHASE)
+            ph[torch.from_numpy(self._done).to(ph.device)] = _capi.PHASE_IDLE
+        done_substeps = 0
+        while done_substeps < self.max_action_substeps:
+            unfinished = self.world.env_substeps(self.substep_chunk)
+            done_substeps += self.substep_chunk
+            if unfinished == 0:
+                break
+        safe = self.world.is_safe.cpu().numpy().astype(bool)
+        eff = self.world.is_effective.cpu().numpy().astype(bool)
+        active = ~self._done
+        self.num_total_steps += int(active.sum())
+        self.num_unsafe += int((~safe & active).sum())
+        self.num_ineffective += int((~eff & active).sum())
+        self.num_useful += int((safe & eff & active).sum())
+
+    # -- helpers kept from the reference --------------------------------------------------------
+    def _compute_waypoints(self, action):
+        """push_env.py:752-786 on the host (for policies/visualisation); the device twin is k_set_action."""
+        action = np.reshape(action, [2, 2])
+        start, motion = action[0, :], action[1, :]
+        x = start[0] * self.start_range[0] + self.start_offset[0]
+        y = start[1] * self.start_range[1] + self.start_offset[1]
+        z = self.start_z
+        x2 = np.clip(x + motion[0] * self._config.ACTION.MOTION.TRANSLATION_X, self.cspace.low[0], self.cspace.high[0])
+        y2 = np.clip(y + motion[1] * self._config.ACTION.MOTION.TRANSLATION_Y, self.cspace.low[1], self.cspace.high[1])
+        return [np.array([[x, y, z], [np.pi, 0, 0]]), np.array([[x2, y2, z], [np.pi, 0, 0]])]
+
+    def close(self):
+        self._simulator.close()
