@@ -276,6 +276,13 @@ int b2s_env_step(B2SWorld* world, int chunk, int max_substeps, void* stream);
 int b2s_arm_move_to_gripper_pose(B2SWorld* world, const float* pose_dev /*[B][7]*/, const uint8_t* env_mask_dev, void* stream);
 int b2s_arm_move_to_joint_positions(B2SWorld* world, const float* q_dev /*[B][7]*/, const uint8_t* env_mask_dev, void* stream);
 int b2s_arm_reset_targets(B2SWorld* world, const uint8_t* env_mask_dev, void* stream);
+/* BulletPhysics.position_control_array (bullet_physics.py:1061-1104): latch the POSITION_CONTROL motor
+ * targets of the 7 limb joints (q_dev, qd_dev: device [B][7]; qd_dev NULL = zero target velocity).  Used
+ * when the reference's own Python ControllableBody drives the arm substep by substep. */
+int b2s_set_motor_targets(B2SWorld* world, const float* q_dev, const float* qd_dev, const uint8_t* env_mask_dev, void* stream);
+/* re-derive the collider list after the host edited num_movables / the movable assets
+ * (BulletPhysics.add_body / remove_body of a movable, bullet_physics.py:143-195) */
+int b2s_rebuild_colliders(B2SWorld* world, void* stream);
 /* SawyerSim.is_limb_ready (sawyer_sim.py:394-400) -> uint8 [B] */
 int b2s_arm_is_ready(B2SWorld* world, uint8_t* out_dev, void* stream);
 /* BulletPhysics.compute_inverse_kinematics (bullet_physics.py:1203-1262), one solve from q_start */

@@ -121,6 +121,24 @@ class OracleWorld(object):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
         self._chk(self.lib.b2o_arm_move_to_joint_positions(self.h, p.ctypes.data_as(C.c_void_p), m))
 
+    def set_motor_targets(self, q, qd=None, mask=None):
+        a = np.ascontiguousarray(q, np.float32)
+        b = None if qd is None else np.ascontiguousarray(qd, np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
+        self._chk(self.lib.b2o_set_motor_targets(self.h, a.ctypes.data_as(C.c_void_p),
+                                                 None if b is None else b.ctypes.data_as(C.c_void_p), m))
+
+    def rebuild_colliders(self):
+        self._chk(self.lib.b2o_rebuild_colliders(self.h))
+
+    def arm_reset_targets(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
+        self._chk(self.lib.b2o_arm_reset_targets(self.h, m))
+
+    # the caller-owned buffers of the CUDA world, under the same attribute names
+    num_movables = property(lambda self: self.array('num_movables'))
+    body_mask = property(lambda self: self.array('body_mask').reshape(self.B, self.N))
+
     def arm_is_ready(self):
         out = np.zeros(self.B, np.uint8)
         self._chk(self.lib.b2o_arm_is_ready(self.h, out.ctypes.data_as(C.c_void_p)))

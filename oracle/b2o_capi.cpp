@@ -169,6 +169,18 @@ int b2o_arm_reset_targets(World* w, const uint8_t* mask) {
   for (int e = 0; e < w->B; ++e) if (!mask || mask[e]) arm_reset_targets(*w, e);
   return 0;
 }
+int b2o_set_motor_targets(World* w, const float* q, const float* qd, const uint8_t* mask) {
+  for (int e = 0; e < w->B; ++e) if (!mask || mask[e]) {
+    float* c = &w->ctrl[(size_t)e * B2S_CTRL_FLOATS];
+    for (int k = 0; k < 7; ++k) { c[18 + k] = q[(size_t)e * 7 + k]; c[25 + k] = qd ? qd[(size_t)e * 7 + k] : 0.0f; }
+    w->ctrl_flags[(size_t)e * 4 + 3] = 1;
+  }
+  return 0;
+}
+int b2o_rebuild_colliders(World* w) {
+  for (int e = 0; e < w->B; ++e) { build_colliders(*w, e); w->num_manifolds[e] = 0; }
+  return 0;
+}
 int b2o_arm_is_ready(World* w, uint8_t* out) { for (int e = 0; e < w->B; ++e) out[e] = (uint8_t)arm_is_ready(*w, e); return 0; }
 int b2o_inverse_kinematics(World* w, const float* pose, const float* q_start, float* q_out) {
   for (int e = 0; e < w->B; ++e) {
@@ -221,6 +233,37 @@ int b2o_render(World* w) {
 }
 int b2o_point_cloud(World* w, uint64_t seed) { for (int e = 0; e < w->B; ++e) point_cloud(*w, e, seed); return 0; }
 int64_t b2o_substeps_executed(World* w) { return w->substeps_executed; }
+
+/* the shared SE(3) leaf math on the CPU (ops as b2s_se3_*: 0 quat_from_euler, 1 euler_from_quat,
+ * 2 matrix_from_quat, 3 quat_multiply, 4 pose_inverse, 5 pose_transform) */
+int b2o_se3(int op, const float* a, const float* b, float* out, int n) {
+  for (int i = 0; i < n; ++i) {
+    if (op == 0) { Q4 q = q_from_euler(a[i * 3], a[i * 3 + 1], a[i * 3 + 2]); out[i * 4] = q.x; out[i * 4 + 1] = q.y; out[i * 4 + 2] = q.z; out[i * 4 + 3] = q.w; }
+    else if (op == 1) { V3 eu = euler_from_q(q4(a[i * 4], a[i * 4 + 1], a[i * 4 + 2], a[i * 4 + 3])); out[i * 3] = eu.x; out[i * 3 + 1] = eu.y; out[i * 3 + 2] = eu.z; }
+    else if (op == 2) {
+      M3 m = q_to_m3(q4(a[i * 4], a[i * 4 + 1], a[i * 4 + 2], a[i * 4 + 3]));
+      float* o = out + i * 9;
+      o[0] = m.r0.x; o[1] = m.r0.y; o[2] = m.r0.z; o[3] = m.r1.x; o[4] = m.r1.y; o[5] = m.r1.z; o[6] = m.r2.x; o[7] = m.r2.y; o[8] = m.r2.z;
+    } else if (op == 3) {
+      Q4 q = qmul(q4(a[i * 4], a[i * 4 + 1], a[i * 4 + 2], a[i * 4 + 3]), q4(b[i * 4], b[i * 4 + 1], b[i * 4 + 2], b[i * 4 + 3]));
+      out[i * 4] = q.x; out[i * 4 + 1] = q.y; out[i * 4 + 2] = q.z; out[i * 4 + 3] = q.w;
+    } else if (op == 4) {
+      Q4 q = q4(a[i * 7 + 3], a[i * 7 + 4], a[i * 7 + 5], a[i * 7 + 6]);
+      V3 pi = mtmul(q_to_m3(q), -v3(a[i * 7], a[i * 7 + 1], a[i * 7 + 2]));
+      Q4 qi = qconj(q);
+      float* o = out + i * 7;
+      o[0] = pi.x; o[1] = pi.y; o[2] = pi.z; o[3] = qi.x; o[4] = qi.y; o[5] = qi.z; o[6] = qi.w;
+    } else {
+      Q4 qa = q4(a[i * 7 + 3], a[i * 7 + 4], a[i * 7 + 5], a[i * 7 + 6]);
+      Q4 qb = q4(b[i * 7 + 3], b[i * 7 + 4], b[i * 7 + 5], b[i * 7 + 6]);
+      V3 p = v3(a[i * 7], a[i * 7 + 1], a[i * 7 + 2]) + qrot(qa, v3(b[i * 7], b[i * 7 + 1], b[i * 7 + 2]));
+      Q4 q = qmul(qa, qb);
+      float* o = out + i * 7;
+      o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = q.x; o[4] = q.y; o[5] = q.z; o[6] = q.w;
+    }
+  }
+  return 0;
+}
 
 /* ids < 100: the B2S_ARR_* arrays; >= 100: the arrays that are caller-owned B2SBuffers on the CUDA side */
 int b2o_array(World* w, int which, void** ptr, int64_t* bytes) {

@@ -129,6 +129,8 @@ SYMBOLS = {
     'b2s_arm_move_to_joint_positions': (C.c_int, [_vp, _vp, _vp, _vp]),
     'b2s_arm_reset_targets': (C.c_int, [_vp, _vp, _vp]),
     'b2s_arm_is_ready': (C.c_int, [_vp, _vp, _vp]),
+    'b2s_set_motor_targets': (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    'b2s_rebuild_colliders': (C.c_int, [_vp, _vp]),
     'b2s_inverse_kinematics': (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     'b2s_forward_kinematics': (C.c_int, [_vp, _vp]),
     'b2s_query_contacts': (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -415,6 +415,17 @@ int b2s_arm_reset_targets(B2SWorld* w, const uint8_t* mask, void* stream) {
   b2s_launch_arm_cmd(w->d, 2, nullptr, mask, nullptr, (cudaStream_t)stream);
   return check_launch(w, "arm_cmd");
 }
+int b2s_set_motor_targets(B2SWorld* w, const float* q, const float* qd, const uint8_t* mask, void* stream) {
+  NEED_READY(w);
+  if (!q) return fail(B2S_E_INVALID, "b2s_set_motor_targets: q is NULL");
+  b2s_launch_arm_cmd(w->d, 4, q, mask, (uint8_t*)qd, (cudaStream_t)stream);
+  return check_launch(w, "arm_cmd");
+}
+int b2s_rebuild_colliders(B2SWorld* w, void* stream) {
+  NEED_READY(w);
+  b2s_launch_rebuild_colliders(w->d, (cudaStream_t)stream);
+  return check_launch(w, "rebuild_colliders");
+}
 int b2s_arm_is_ready(B2SWorld* w, uint8_t* out, void* stream) {
   NEED_READY(w);
   if (!out) return fail(B2S_E_INVALID, "b2s_arm_is_ready: out is NULL");

@@ -306,7 +306,8 @@ __global__ void k_reward(const __grid_constant__ DWorld W, const float* prev_xy,
 }
 
 // ---- robot commands (sawyer_sim.py:186-308) ----
-// cmd 0: move_to_gripper_pose, 1: move_to_joint_positions, 2: reset_targets, 3: is_limb_ready
+// cmd 0: move_to_gripper_pose, 1: move_to_joint_positions, 2: reset_targets, 3: is_limb_ready,
+// 4: latch motor targets (data = q [B][7], out reinterpreted as qd [B][7] or NULL)
 __device__ bool joints_reached_scalar(const DWorld& W, int e) {
   const int32_t* f = W.ctrl_flags + (size_t)e * 4;
   if (!f[1]) return true;
@@ -342,11 +343,41 @@ __global__ void k_arm_cmd(const __grid_constant__ DWorld W, int cmd, const float
     f[1] = 1; f[2] = 0;
   } else if (cmd == 2) {
     f[0] = 0; f[1] = 0;
+  } else if (cmd == 4) {
+    const float* qd = (const float*)out;
+    for (int k = 0; k < 7; ++k) { c[18 + k] = data[(size_t)e * 7 + k]; c[25 + k] = qd ? qd[(size_t)e * 7 + k] : 0.0f; }
+    f[3] = 1;
   } else {
     if (!f[0] || now >= T[1]) f[0] = 0;
     if (!f[1] || now >= T[3] || joints_reached_scalar(W, e)) f[1] = 0;
     out[e] = (!f[0] && !f[1]) ? 1 : 0;
   }
+}
+
+__global__ void k_rebuild_colliders(const __grid_constant__ DWorld W) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= W.B) return;
+  int nc = 0; bool over = false;
+  int32_t* cs = W.col_slot + (size_t)e * W.Hmax;
+  int32_t* ch = W.col_hull + (size_t)e * W.Hmax;
+  for (int s = 0; s < W.Ns; ++s) {
+    if (W.static_flags[s] & B2S_STATIC_NO_COLLIDE) continue;
+    const DAsset& A = W.assets[W.static_asset[s]];
+    for (int h = A.hoff; h < A.hoff + A.hcnt; ++h) { if (nc >= W.Hmax) { over = true; break; } cs[nc] = s; ch[nc] = h; ++nc; }
+  }
+  for (int k = 0; k < W.L; ++k) {
+    const DAsset& A = W.assets[W.arm->link_asset[k]];
+    for (int h = A.hoff; h < A.hoff + A.hcnt; ++h) { if (nc >= W.Hmax) { over = true; break; } cs[nc] = W.Ns + k; ch[nc] = h; ++nc; }
+  }
+  const int n = W.buf.num_movables[e];
+  for (int i = 0; i < n; ++i) {
+    const DAsset& A = W.assets[__float_as_int(MPX(0, e, i))];
+    for (int h = A.hoff; h < A.hoff + A.hcnt; ++h) { if (nc >= W.Hmax) { over = true; break; } cs[nc] = W.Ns + W.L + i; ch[nc] = h; ++nc; }
+  }
+  W.ncol[e] = nc;
+  if (over) W.error_flags[e] |= 32;
+  // the collider numbering changed: cached manifolds are keyed by collider index, drop them
+  W.num_manifolds[e] = 0;
 }
 
 // scalar DLS IK (same arithmetic as arm_ik in b2s_step.cu / oracle arm_ik)
@@ -469,6 +500,7 @@ void b2s_launch_reward(const DWorld& W, const float* p, const float* n, cudaStre
 void b2s_launch_arm_cmd(const DWorld& W, int cmd, const float* data, const uint8_t* mask, uint8_t* out, cudaStream_t s) {
   k_arm_cmd<<<blocks_for(W.B, 128), 128, 0, s>>>(W, cmd, data, mask, out);
 }
+void b2s_launch_rebuild_colliders(const DWorld& W, cudaStream_t s) { k_rebuild_colliders<<<blocks_for(W.B, 64), 64, 0, s>>>(W); }
 void b2s_launch_ik(const DWorld& W, const float* pose, const float* qs, float* qo, cudaStream_t s) { k_ik<<<blocks_for(W.B, 64), 64, 0, s>>>(W, pose, qs, qo); }
 void b2s_launch_fk(const DWorld& W, cudaStream_t s) { k_fk<<<blocks_for(W.B, 64), 64, 0, s>>>(W); }
 void b2s_launch_query_contacts(const DWorld& W, uint8_t* at, uint8_t* am, cudaStream_t s) { k_query_contacts<<<blocks_for(W.B, 128), 128, 0, s>>>(W, at, am); }

@@ -163,6 +163,7 @@ void b2s_launch_set_action(const DWorld& W, cudaStream_t s);
 void b2s_launch_observe(const DWorld& W, cudaStream_t s);
 void b2s_launch_reward(const DWorld& W, const float* prev_xy, const float* next_xy, cudaStream_t s);
 void b2s_launch_arm_cmd(const DWorld& W, int cmd, const float* data, const uint8_t* mask, uint8_t* out, cudaStream_t s);
+void b2s_launch_rebuild_colliders(const DWorld& W, cudaStream_t s);
 void b2s_launch_ik(const DWorld& W, const float* pose, const float* q_start, float* q_out, cudaStream_t s);
 void b2s_launch_fk(const DWorld& W, cudaStream_t s);
 void b2s_launch_query_contacts(const DWorld& W, uint8_t* arm_table, uint8_t* arm_movable, cudaStream_t s);

@@ -157,6 +157,15 @@ class World(object):
         m = self._mask(mask)
         self._chk(self.lib.b2s_arm_reset_targets(self.h, self._ptr(m), self._stream()))
 
+    def set_motor_targets(self, q, qd=None, mask=None):
+        a = torch.as_tensor(q, dtype=torch.float32, device=self.device).reshape(self.B, 7).contiguous()
+        b = None if qd is None else torch.as_tensor(qd, dtype=torch.float32, device=self.device).reshape(self.B, 7).contiguous()
+        m = self._mask(mask)
+        self._chk(self.lib.b2s_set_motor_targets(self.h, self._ptr(a), self._ptr(b), self._ptr(m), self._stream()))
+
+    def rebuild_colliders(self):
+        self._chk(self.lib.b2s_rebuild_colliders(self.h, self._stream()))
+
     def arm_is_ready(self):
         out = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
         self._chk(self.lib.b2s_arm_is_ready(self.h, self._ptr(out), self._stream()))
