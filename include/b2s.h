@@ -60,6 +60,7 @@ enum { B2S_TASK_NONE = 0, B2S_TASK_CLEARING = 1, B2S_TASK_INSERTION = 2, B2S_TAS
 #define B2S_STATIC_ON_TABLE 1u     /* z follows the per-env table height offset */
 #define B2S_STATIC_IS_TABLE 2u     /* counts for check_contact(arm, table) (push_env.py:850) */
 #define B2S_STATIC_NO_COLLIDE 4u   /* visual only (rendered, never collides) */
+#define B2S_STATIC_IS_TILE 8u      /* loaded after the movables (push_env.py:343-357): body uid = index + num_movables */
 
 /* Solver / world parameters.  Every Bullet default named in SURVEY.md 3.4 is a
  * field here so nothing is hard-wired; b2s_default_params() fills them. */

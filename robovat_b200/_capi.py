@@ -28,7 +28,7 @@ TASK_NONE, TASK_CLEARING, TASK_INSERTION, TASK_CROSSING = range(4)
 TASK_IDS = {None: TASK_NONE, 'data_collection': TASK_NONE, 'clearing': TASK_CLEARING,
             'insertion': TASK_INSERTION, 'crossing': TASK_CROSSING}
 
-STATIC_ON_TABLE, STATIC_IS_TABLE, STATIC_NO_COLLIDE = 1, 2, 4
+STATIC_ON_TABLE, STATIC_IS_TABLE, STATIC_NO_COLLIDE, STATIC_IS_TILE = 1, 2, 4, 8
 
 (ARR_MANIFOLD_KEYS, ARR_MANIFOLD_NPTS, ARR_MANIFOLD_PTS, ARR_NUM_MANIFOLDS, ARR_PAIR_KEYS,
  ARR_NUM_PAIRS, ARR_PHASE, ARR_NUM_STEPS, ARR_CTRL, ARR_CTRL_FLAGS, ARR_LINK_POSES,

@@ -175,7 +175,7 @@ def build_scene(config):
         tile_h = float(cfg.SIM.TILE.HEIGHT)
         tile = lib.add_asset('tile', [assets_lib.box_vertices(0.5 * lay.size, 0.5 * lay.size, 0.5 * tile_h)],
                              center_on_com=False)
-        flags = _capi.STATIC_ON_TABLE | (0 if cfg.SIM.TILE.COLLIDE else _capi.STATIC_NO_COLLIDE)
+        flags = _capi.STATIC_ON_TABLE | _capi.STATIC_IS_TILE | (0 if cfg.SIM.TILE.COLLIDE else _capi.STATIC_NO_COLLIDE)
         # PushEnv._load_tiles: region at z_offset 0.001 - 0.025, goal at 0.0015 - 0.025 (push_env.py:343-357)
         for i, c in enumerate(lay.region):
             statics.append({'name': 'tile_%d' % i, 'asset': tile, 'friction': 1.0, 'flags': flags,

@@ -236,6 +236,18 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   if ((rc = upload(w, &d.layout, &lay, 1))) return rc;
 
   d.Ns = s->num_statics; d.L = s->num_links; d.NB = d.Ns + d.L + d.Nmax;
+  {
+    // raster capacities: every static (visual-only ones too), every arm link, Nmax x the largest movable asset
+    auto asset_planes = [&](int a) { int n = 0; for (int h = assets[a].hoff; h < assets[a].hoff + assets[a].hcnt; ++h) n += hulls[h].pcnt; return n; };
+    int cols = 0, pls = 0, mc = 0, mp = 0;
+    for (int i = 0; i < s->num_statics; ++i) { cols += assets[s->static_asset[i]].hcnt; pls += asset_planes(s->static_asset[i]); }
+    for (int k = 0; k < s->num_links; ++k) { cols += assets[s->link_asset[k]].hcnt; pls += asset_planes(s->link_asset[k]); }
+    for (int i = 0; i < s->num_movable_assets; ++i) { mc = std::max(mc, assets[s->movable_assets[i]].hcnt); mp = std::max(mp, asset_planes(s->movable_assets[i])); }
+    for (int i = 0; i < s->num_target_assets; ++i) { mc = std::max(mc, assets[s->target_assets[i]].hcnt); mp = std::max(mp, asset_planes(s->target_assets[i])); }
+    d.max_ray_cols = cols + d.Nmax * mc;
+    d.max_ray_planes = std::max(1, pls + d.Nmax * mp);
+    if (d.max_ray_cols > 256) return fail(B2S_E_CAPACITY, "b2s_load_scene: %d hulls per environment exceed the raster's 256", d.max_ray_cols);
+  }
   const size_t B = d.B, N = d.Nmax, M = P.max_manifolds;
 #define ALLOC(field, count, fill) if ((rc = dalloc(w, &d.field, (count), (fill)))) return rc
   ALLOC(man_keys, 2 * B * M, 0xff); ALLOC(man_npts, 2 * B * M, 0); ALLOC(man_pts, 2 * B * M * 4 * B2S_CP_FLOATS, 0);
@@ -285,7 +297,10 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   // environments per block: with register-resident rows any warp can run any stage of any environment of
   // its block, so a block owns more environments than warps (dynamic hand-out); otherwise one per warp
   {
-    const int wpb = P.warps_per_block;
+    // large scenes (rows in shared memory): fewer warps per block so the block still fits 220 KB
+    while (d.P.warps_per_block > 1 &&
+           ((size_t)d.P.warps_per_block * (sm.words_env + sm.words_warp)) * 4 > 220 * 1024) d.P.warps_per_block -= 1;
+    const int wpb = d.P.warps_per_block;
     int maxE = d.reg_rows ? 2 * wpb : wpb;
     while (maxE > wpb && ((size_t)maxE * sm.words_env + (size_t)wpb * sm.words_warp) * 4 > 220 * 1024) --maxE;
     int E = maxE;
@@ -472,7 +487,7 @@ int b2s_render(B2SWorld* w, void* stream) {
   NEED_READY(w);
   if (!w->d.buf.depth || !w->d.buf.segmask) return fail(B2S_E_STATE, "b2s_render: depth/segmask buffers are not bound");
   b2s_launch_render(w->d, (cudaStream_t)stream);
-  return check_launch(w, "render");
+  return check_launch(w, "render", 2);
 }
 int b2s_point_cloud(B2SWorld* w, uint64_t seed, void* stream) {
   NEED_READY(w);

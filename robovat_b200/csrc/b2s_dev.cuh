@@ -148,6 +148,8 @@ struct DWorld {
   float* stage_body;     // [B][NB][BODY_STRIDE]
   int32_t* stage_meta;   // [B][4 + max_contacts + 65]   nc, ncolours, pad, pad, order[], colstart[]
   SmemLayout sm;
+  int max_ray_planes;    // raster: upper bound of hull face planes / hulls in one environment
+  int max_ray_cols;
   int envs_per_block;    // E: environments a block steps together (E >= warps_per_block)
   int reg_rows;          // 1: contacts fit one per lane (max_contacts <= 32, NB <= 32): rows live in registers
 };

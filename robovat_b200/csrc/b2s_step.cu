@@ -1551,6 +1551,15 @@ __device__ __noinline__ void finish_action(int e, int lane) {
 
 // ----------------------------------------------------------- the kernel -----
 
+// Hand-out of environments inside a stage: dynamic (shared counter) when the solver rows live in registers;
+// with rows in per-warp shared memory an environment must stay with one warp for the whole substep.
+__device__ __forceinline__ int grab_slot(int* counter, int lane, int wib, int E, bool first) {
+  if (!W.reg_rows) return first ? wib : E;
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(counter, 1);
+  return __shfl_sync(FULL, slot, 0);
+}
+
 // Block = Wn warps stepping E environments.  Every substep runs three stages separated by block barriers
 // (scene -> narrow phase -> solve/integrate/phase logic); inside a stage the warps take environments from
 // a shared counter, so a warp stuck on a long solve does not hold the others back, and all warps of the
@@ -1588,10 +1597,10 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     if (!__syncthreads_or(any)) break;
     if (threadIdx.x == 0) s_cnt[2] = 0;
     // ---- stage A: controller + FK, body table, colliders, broad phase
+    bool first0 = true, first1 = true, first2 = true;
     for (;;) {
-      int slot = 0;
-      if (lane == 0) slot = atomicAdd(&s_cnt[0], 1);
-      slot = __shfl_sync(FULL, slot, 0);
+      const int slot = grab_slot(&s_cnt[0], lane, wib, E, first0);
+      first0 = false;
       if (slot >= E) break;
       int* meta = env_meta(slot);
       if (!meta[META_ACTIVE]) continue;
@@ -1602,9 +1611,8 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     if (threadIdx.x == 0) s_cnt[0] = 0;
     // ---- stage B: narrow phase + manifolds
     for (;;) {
-      int slot = 0;
-      if (lane == 0) slot = atomicAdd(&s_cnt[1], 1);
-      slot = __shfl_sync(FULL, slot, 0);
+      const int slot = grab_slot(&s_cnt[1], lane, wib, E, first1);
+      first1 = false;
       if (slot >= E) break;
       int* meta = env_meta(slot);
       if (!meta[META_ACTIVE]) continue;
@@ -1616,9 +1624,8 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     if (threadIdx.x == 0) s_cnt[1] = 0;
     // ---- stage C: solve, integrate, phase machine / settle bookkeeping
     for (;;) {
-      int slot = 0;
-      if (lane == 0) slot = atomicAdd(&s_cnt[2], 1);
-      slot = __shfl_sync(FULL, slot, 0);
+      const int slot = grab_slot(&s_cnt[2], lane, wib, E, first2);
+      first2 = false;
       if (slot >= E) break;
       int* meta = env_meta(slot);
       if (!meta[META_ACTIVE]) continue;

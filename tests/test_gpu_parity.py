@@ -122,3 +122,81 @@ def test_ik_fk_bit_exact():
     helpers.assert_bits_equal(qg, qc, 'ik')
     gpu.joint_state[0].copy_(torch.from_numpy(qc)); cpu.joint_state[0] = qc
     helpers.assert_bits_equal(gpu.forward_kinematics().cpu().numpy(), cpu.forward_kinematics(), 'fk')
+
+
+def test_crossing_task_concave_movables_bit_exact():
+    """BASELINE config #3: TASK_NAME='crossing' LAYOUT_ID=0, 8 concave (multi-hull) movables, tiles as static bodies.
+    More than 32 contact points per env: exercises the shared-memory-row solver path."""
+    cfg, gpu, cpu = helpers.make_pair(12, TASK_NAME='crossing', LAYOUT_ID=0, MOVABLE_NAME='concave',
+                                      MIN_MOVABLE_BODIES=8, MAX_MOVABLE_BODIES=8)
+    assert gpu.params.max_contacts > 32
+    gpu.reset(seed=2); cpu.reset(seed=2)
+    for k in range(6):
+        gpu.step(100); cpu.step(100)
+        _compare_state(gpu, cpu, 'crossing after %d substeps' % (100 * (k + 1)))
+        _compare_contacts(gpu, cpu, 'crossing after %d substeps' % (100 * (k + 1)))
+    assert int(cpu.array(_capi.ARR_SOLVER_STATS).reshape(12, 4)[:, 3].max()) > 32
+    act = np.tile(np.array([0.0, 0.1, 0.8, -0.6], np.float32), (12, 1))
+    gpu.set_action(act); cpu.set_action(act)
+    for _ in range(40):
+        ug, uc = gpu.env_substeps(500), cpu.env_substeps(500)
+        assert ug == uc
+        if uc == 0:
+            break
+    _compare_state(gpu, cpu, 'crossing after action')
+    rg, tg = gpu.reward(); rc, tc = cpu.reward()
+    helpers.assert_bits_equal(rg.cpu().numpy(), rc, 'reward')
+    np.testing.assert_array_equal(tg.cpu().numpy(), tc)
+
+
+def test_render_and_point_cloud_bit_exact():
+    """BASELINE config #4 shape: 128x128 depth + segmentation, then the segmented point cloud."""
+    from robovat_b200 import config as config_lib
+    from robovat_b200.assets import quat_from_euler, quat_to_matrix
+    kin = dict(config_lib.DEFAULT_PUSH_ENV['KINECT2']['DEPTH'], HEIGHT=128, WIDTH=128,
+               INTRINSICS=[120.0, 0.5, 64.0, 0, 118.0, 63.0, 0, 0, 1])
+    cfg, gpu, cpu = helpers.make_pair(6, with_camera=True, KINECT2={'DEPTH': kin}, TASK_NAME='crossing', LAYOUT_ID=1)
+    gpu.reset(seed=8); cpu.reset(seed=8)
+    gpu.step(400); cpu.step(400)
+    rs = np.random.RandomState(0)
+    K = np.tile(np.array([120.0, 0.5, 64.0, 0, 118.0, 63.0, 0, 0, 1.0]), (6, 1)) + rs.uniform(-1, 1, (6, 9)) * [1, 0, 1, 0, 1, 1, 0, 0, 0]
+    R = np.stack([quat_to_matrix(quat_from_euler(np.pi + rs.uniform(-0.1, 0.1), rs.uniform(-0.1, 0.1), rs.uniform(-0.2, 0.2))) for _ in range(6)])
+    t = np.stack([-R[i].dot(np.array([0.6, 0.0, 1.1]) + rs.uniform(-0.05, 0.05, 3)) for i in range(6)])
+    gpu.set_camera(K, R.reshape(6, 9), t, per_env=True); cpu.set_camera(K, R.reshape(6, 9), t, per_env=True)
+    dg, sg = gpu.render(); dc, sc = cpu.render()
+    np.testing.assert_array_equal(sg.cpu().numpy(), sc)
+    helpers.assert_bits_equal(dg.cpu().numpy(), dc, 'depth')
+    assert len(np.unique(sc)) >= 6
+    helpers.assert_bits_equal(gpu.point_cloud(seed=4).cpu().numpy(), cpu.point_cloud(seed=4), 'point cloud')
+
+
+def test_physics_plugin_calls_match():
+    """The BulletPhysics-compatible seam (robovat_b200.physics.CudaPhysics) over the CUDA world and over the oracle:
+    the same scripted sequence of add_body / set_body_dynamics / step / position_control_array / IK / contact queries."""
+    from robovat_b200.physics import CudaPhysics, EE_LINK_INDEX
+    from robovat_b200.assets import quat_from_euler
+    cfg, gpu, cpu = helpers.make_pair(1)
+    outs = []
+    for world in (gpu, cpu):
+        ph = CudaPhysics(world=world, scene=world.scene, time_step=cfg.SIM.TIME_STEP)
+        ph.reset(); ph.set_gravity([0, 0, -9.8]); ph.start()
+        ground = ph.add_body('/assets/scene/ground.urdf', [[0, 0, -0.9], [0, 0, 0]], is_static=True)
+        table = ph.add_body('/assets/scene/table.urdf', [[0.6, 0, 0.0], [0, 0, 0]], is_static=True)
+        box = ph.add_body('/assets/movables/box.urdf', [[0.6, 0.0, 0.1], [0.2, 0.1, 0.3]], scale=1.1)
+        ph.set_body_dynamics(box, mass=0.2, lateral_friction=0.7)
+        arm = ph.add_body('/assets/robots/sawyer_arm.urdf', [[0, 0, 0], [0, 0, 0]], is_static=True)
+        for j, q in enumerate([0.0, -1.18, 0.0, 2.18, 0.0, 0.57, 3.3161]):
+            ph.set_joint_position((arm, j), q)
+        pose = [[0.6, 0.0, 0.3], list(quat_from_euler(np.pi, 0, 0))]
+        trace = []
+        for s in range(1200):
+            if s % 10 == 0:
+                q = ph.compute_inverse_kinematics((arm, EE_LINK_INDEX), pose)[:7]
+            ph.position_control_array(arm, range(7), q, [0.0] * 7)
+            ph.step()
+            trace.append([float(ph.get_joint_position((arm, j))) for j in range(7)] + list(ph.get_body_position(box)))
+        assert ph.num_steps == 1200 and len(ph.get_contact_points(box, table)) >= 1 and not ph.get_contact_points(arm, table)
+        ee = ph.get_link_pose((arm, EE_LINK_INDEX))
+        assert np.abs(np.asarray(ee.position) - [0.6, 0.0, 0.3]).max() < 5e-3
+        outs.append(np.array(trace, np.float32))
+    helpers.assert_bits_equal(outs[0], outs[1], 'plugin trace')
