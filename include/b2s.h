@@ -91,7 +91,7 @@ typedef struct B2SParams {
   int32_t task;                    /* B2S_TASK_* */
   int32_t max_contacts;            /* contact points per env handed to the solver */
   int32_t max_colliders;           /* convex hulls per env (statics + arm links + movable hulls) */
-  int32_t warps_per_block;         /* launch shape of the one-env-per-warp kernels (default 4) */
+  int32_t warps_per_block;         /* warps per block of the substep kernel; 0 = what the library was built for */
   int32_t reserved_i[4];
 
   double time_step;                /* dt; reference default 1e-3 (simulator.py:26) */
@@ -219,7 +219,7 @@ enum {
   B2S_ARR_MOV_PARAMS = 11,     /* float [4][B][Nmax] asset(as int bits), scale, mass, friction */
   B2S_ARR_TABLE_DZ = 12,       /* float [B] */
   B2S_ARR_ERROR_FLAGS = 13,    /* int32 [B] bit0 pair overflow, bit1 manifold overflow, bit2 non-finite state,
-                                  bit3 contact overflow, bit4 colour overflow, bit5 collider overflow */
+                                  bit3 contact overflow, bit4 colour overflow, bit5 collider overflow, bit6 solver invariant */
   B2S_ARR_WAYPOINTS = 14,      /* float [B][2][7] start / end gripper poses */
   B2S_ARR_STATUS = 15,         /* float [B][2][Nmax][4] start/end status: pos3 + yaw (push_env.py:925-937) */
   B2S_ARR_CONTACT_FLAGS = 16,  /* int32 [B] bit0 arm-table, bit1 arm-movable, per last substep */

@@ -242,7 +242,8 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     p.cam_height, p.cam_width = int(cfg.KINECT2.DEPTH.HEIGHT), int(cfg.KINECT2.DEPTH.WIDTH)
     p.num_points = int(cfg.OBS.NUM_POINTS)
     p.task = _capi.TASK_IDS[cfg.TASK_NAME]
-    p.warps_per_block = int(os.environ.get('B2S_WARPS', 16))   # one 512-thread block per SM
+    if os.environ.get('B2S_WARPS'):
+        p.warps_per_block = int(os.environ['B2S_WARPS'])           # default: what the library was built for
     p.time_step = float(cfg.SIM.TIME_STEP)
     p.gravity[:] = phys.GRAVITY
     p.erp2, p.linear_slop, p.warmstart = phys.ERP2, phys.LINEAR_SLOP, phys.WARMSTART

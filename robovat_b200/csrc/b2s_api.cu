@@ -111,7 +111,7 @@ int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
   if (p->max_pairs <= 0 || p->max_manifolds <= 0 || p->max_contacts <= 0 || p->max_colliders <= 0)
     return fail(B2S_E_INVALID, "b2s_create: capacities must be positive");
   if (p->max_colliders > 65535) return fail(B2S_E_INVALID, "b2s_create: max_colliders > 65535");
-  if (p->warps_per_block < 1 || p->warps_per_block * 32 > B2S_BLOCK_THREADS) return fail(B2S_E_INVALID, "b2s_create: warps_per_block must be 1..%d for this build", B2S_BLOCK_THREADS / 32);
+  if (p->warps_per_block < 0 || p->warps_per_block * 32 > B2S_BLOCK_THREADS) return fail(B2S_E_INVALID, "b2s_create: warps_per_block must be 0 (build default) or 1..%d for this build", B2S_BLOCK_THREADS / 32);
   if (p->friction_dirs != 1 && p->friction_dirs != 2) return fail(B2S_E_INVALID, "b2s_create: friction_dirs must be 1 or 2");
   if (!(p->time_step > 0)) return fail(B2S_E_INVALID, "b2s_create: time_step must be > 0");
   int ndev = 0;
@@ -122,6 +122,7 @@ int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
   B2SWorld* w = new B2SWorld();
   memset(&w->d, 0, sizeof(w->d));
   w->d.P = *p;
+  if (w->d.P.warps_per_block == 0) w->d.P.warps_per_block = B2S_BLOCK_THREADS / 32;
   w->d.B = p->num_envs; w->d.Nmax = p->max_movables; w->d.Hmax = p->max_colliders;
   w->device = device; w->scene_loaded = false; w->buffers_bound = false; w->launches = 0;
   w->exp_keys = nullptr; w->exp_npts = nullptr; w->exp_pts = nullptr; w->unfinished_pinned = nullptr;
@@ -273,7 +274,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     CU(cudaMemcpy(d.phase_state, ps.data(), B * 8 * 4, cudaMemcpyHostToDevice));
   }
   CU(cudaMallocHost((void**)&w->unfinished_pinned, sizeof(int)));
-  // shared-memory carve-up per warp
+  // shared-memory carve-up (see SmemLayout)
   SmemLayout& sm = d.sm;
   int o = 0;
   auto take = [&](int words) { int at = o; o += (words + 1) & ~1; return at; };   // keep 8-byte alignment
@@ -282,40 +283,44 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   sm.col = take(d.Hmax * COL_STRIDE);
   sm.pairs = take(P.max_pairs);
   sm.cmk = take(P.max_contacts);
-  sm.used = take(d.NB * 2);
-  sm.meta = take(META_WORDS);
+  sm.used = take(d.reg_rows ? 0 : d.NB * 2);     // colour masks of the generic solve
   sm.words_env = o;
   o = 0;
-  sm.oldkeys = take(P.max_manifolds);
-  sm.con = take(std::max(d.reg_rows ? 0 : P.max_contacts * CON_STRIDE, (int)(EPA_MAXV * 11 + EPA_MAXF * 7)));
   sm.order = take(P.max_contacts);
   sm.colstart = take(66);
+  const int x0 = o;                 // region shared by the narrow-phase scratch and the solver rows
+  sm.oldkeys = take(P.max_manifolds);
   sm.stage = take(4 * B2S_CP_FLOATS);
   sm.fk = take(FK_WORDS);
   sm.simplex = take(48);
+  sm.con = x0;
+  o = std::max(o, x0 + (d.reg_rows ? 512 + 8 * 32 : P.max_contacts * CON_STRIDE));   // reg_rows: colour table + lambda x2 + slots
   sm.words_warp = o;
-  // environments per block: with register-resident rows any warp can run any stage of any environment of
-  // its block, so a block owns more environments than warps (dynamic hand-out); otherwise one per warp
   {
     // large scenes (rows in shared memory): fewer warps per block so the block still fits 220 KB
     while (d.P.warps_per_block > 1 &&
-           ((size_t)d.P.warps_per_block * (sm.words_env + sm.words_warp)) * 4 > 220 * 1024) d.P.warps_per_block -= 1;
+           ((size_t)d.P.warps_per_block * (sm.words_env + META_WORDS + sm.words_warp)) * 4 > 220 * 1024) d.P.warps_per_block -= 1;
     const int wpb = d.P.warps_per_block;
-    int maxE = d.reg_rows ? 2 * wpb : wpb;
-    while (maxE > wpb && ((size_t)maxE * sm.words_env + (size_t)wpb * sm.words_warp) * 4 > 220 * 1024) --maxE;
-    int E = maxE;
+    // environments per block: with register-resident rows any warp can run any stage of any environment of
+    // its block (dynamic hand-out), so a block may own more environments than warps; otherwise one per warp
+    int maxE = d.reg_rows ? 4 * wpb : wpb;
+    while (maxE > 1 && ((size_t)maxE * (sm.words_env + META_WORDS) + (size_t)wpb * sm.words_warp) * 4 > 220 * 1024) --maxE;
+    int E;
     if (P.reserved_i[0] > 0) E = P.reserved_i[0];
     else {
-      // fill whole waves of 148 SMs (one block per SM): B = 4096 -> E = 28 -> 147 blocks
+      // fill whole waves of SMs (one block per SM): B = 4096 -> E = 28 -> 147 blocks
       int dev_sms = 148;
       cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, w->device);
       const int waves = (d.B + dev_sms * maxE - 1) / (dev_sms * maxE);
       E = (d.B + dev_sms * waves - 1) / (dev_sms * waves);
     }
     if (!d.reg_rows) E = wpb;
-    if (E < wpb) E = wpb;
+    if (E < 1) E = 1;
     if (E > maxE) E = maxE;
     d.envs_per_block = E;
+    const size_t blocks = (d.B + E - 1) / E;
+    if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
+    if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)(32 * 64), 0))) return rc;
   }
   size_t smem = b2s_smem_bytes(d);
   if (smem > 227 * 1024) return fail(B2S_E_CAPACITY, "b2s_load_scene: %zu bytes of shared memory per block exceed 227 KB; lower warps_per_block or the capacities", smem);

@@ -70,14 +70,15 @@ struct DLayout {
   int num_movable_assets, num_target_assets;
 };
 
-// per-warp shared-memory carve-up (offsets in 4-byte words from the warp's base)
-// Shared memory of a block = E per-environment regions followed by one scratch region per warp.
+// Shared memory of a block = E per-environment regions, one scratch region per warp, E meta records.
 // A warp may pick up any environment of its block in any stage, so everything that has to survive from
-// one stage to the next (body table, colliders, pair list, contact list) is per environment; GJK/EPA,
-// manifold staging and FK scratch are per warp.
+// one stage to the next (body table, colliders, pair list, contact list) is per environment; GJK, manifold
+// staging, FK scratch and the B-side row data are per warp.  `con` aliases the narrow-phase scratch
+// (oldkeys .. simplex): rows are only alive in the solve stage.  The EPA polytope (rare path, 4 KB per
+// warp) lives in global memory so that the block leaves more of the SM's 256 KB to the L1 cache.
 struct SmemLayout {
-  int body, col, pairs, cmk, used, meta, words_env;                        // per environment
-  int oldkeys, con, order, colstart, stage, fk, simplex, words_warp;       // per warp
+  int body, col, pairs, cmk, used, words_env;                              // per environment
+  int oldkeys, con, order, colstart, stage, fk, simplex, words_warp;       // per warp: scratch
 };
 #define META_ACTIVE 0
 #define META_NP 1
@@ -143,6 +144,8 @@ struct DWorld {
   float* cam;            // [B][21]
   unsigned long long* substeps;   // device counter: total env-substeps executed
   int32_t* unfinished;            // device counter used by env_substeps
+  float* epa_scratch;             // [blocks][warps][EP_WORDS] EPA polytope (rare path: lives in L2, not in shared memory)
+  float* row_scratch;             // [blocks][warps][32][64] solver rows of the environment a warp is solving (L1/L2 resident)
   // staged-mode scratch: contact rows / body velocities dumped between kernels
   float* stage_rows;     // [B][max_contacts][CON_STRIDE]
   float* stage_body;     // [B][NB][BODY_STRIDE]
@@ -150,7 +153,7 @@ struct DWorld {
   SmemLayout sm;
   int max_ray_planes;    // raster: upper bound of hull face planes / hulls in one environment
   int max_ray_cols;
-  int envs_per_block;    // E: environments a block steps together (E >= warps_per_block)
+  int envs_per_block;    // E: environments a block steps together
   int reg_rows;          // 1: contacts fit one per lane (max_contacts <= 32, NB <= 32): rows live in registers
 };
 

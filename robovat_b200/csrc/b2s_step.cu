@@ -82,7 +82,10 @@ struct WarpSmem {
 };
 
 // `sw` packs (environment slot of the block) | (warp in block) << 16
-__device__ __forceinline__ int* env_meta(int slot) { return (int*)(b2s_smem + (size_t)slot * W.sm.words_env + W.sm.meta); }
+__device__ __forceinline__ int* env_meta(int slot) {
+  return (int*)(b2s_smem + (size_t)W.envs_per_block * W.sm.words_env + (size_t)W.P.warps_per_block * W.sm.words_warp +
+                (size_t)slot * META_WORDS);
+}
 __device__ __forceinline__ WarpSmem carve(int sw) {
   // both bases derive from the __shared__ array, so accesses compile to LDS/STS, not generic LD/ST
   float* eb = b2s_smem + (size_t)(sw & 0xffff) * W.sm.words_env;
@@ -112,6 +115,7 @@ __device__ __noinline__ void fk_chain(const DArm* __restrict__ arm, const float*
   float* fk = carve(wib).fk;
   Xf T = xf_from(arm->base);
   __syncwarp();
+#pragma unroll 1
   for (int j = 0; j < B2S_NUM_JOINTS; ++j) {
     Xf Tj = xf_mul(T, xf_from(arm->joint_origin[j]));
     V3 a = v3(arm->joint_axis[j][0], arm->joint_axis[j][1], arm->joint_axis[j][2]);
@@ -340,13 +344,17 @@ __device__ void arm_set_joint_target(int e, int lane, const float* q) {
 
 // -------------------------------------------------------------- support ----
 
-struct ColRef { V3 pos; M3 R; float scale, margin; int voff, vcnt; V3 cen; };
+// pose of the collider's body is read from the shared body table through `b` (broadcast LDS): keeping pos/R
+// in the struct made it 20 words, which the compiler parked in local memory around the noinline EPA calls
+struct ColRef { const float* b; float scale, margin; int voff, vcnt; V3 cen; };
+__device__ __forceinline__ V3 cr_pos(const ColRef& c) { return LD3(c.b + BO_POS); }
+__device__ __forceinline__ M3 cr_R(const ColRef& c) { return ldm3(c.b + BO_R); }
 
 __device__ __forceinline__ ColRef col_ref(const float* col, const float* body, int c) {
   const float* cr = col + c * COL_STRIDE;
   const float* b = body + __float_as_int(cr[CO_SLOT]) * BODY_STRIDE;
   ColRef r;
-  r.pos = LD3(b + BO_POS); r.R = ldm3(b + BO_R);
+  r.b = b;
   r.scale = cr[CO_SCALE]; r.margin = cr[CO_MARGIN];
   const DHull* H = W.hulls + __float_as_int(cr[CO_HULL]);
   r.voff = H->voff; r.vcnt = H->vcnt;
@@ -356,7 +364,8 @@ __device__ __forceinline__ ColRef col_ref(const float* col, const float* body, i
 
 // argmax_i v_i . d over the hull's vertices (first maximum), one or two vertices per lane
 __device__ __forceinline__ int support(const ColRef& c, V3 d, V3* p, int lane) {
-  V3 dl = mtmul(c.R, d);
+  const M3 R = cr_R(c);
+  V3 dl = mtmul(R, d);
   float best = 0.0f;
   int bi = 0x7fffffff;
   bool has = false;
@@ -374,7 +383,7 @@ __device__ __forceinline__ int support(const ColRef& c, V3 d, V3* p, int lane) {
   unsigned cand = (has && key == m) ? (unsigned)bi : 0x7fffffffu;
   int idx = (int)__reduce_min_sync(FULL, cand);
   float4 v = __ldg(W.verts + c.voff + idx);
-  *p = c.pos + mmul(c.R, v3(v.x, v.y, v.z) * c.scale);
+  *p = cr_pos(c) + mmul(R, v3(v.x, v.y, v.z) * c.scale);
   return idx;
 }
 
@@ -387,12 +396,65 @@ __device__ __forceinline__ int support(const ColRef& c, V3 d, V3* p, int lane) {
 #define SX_IB 40
 #define SX_N 44
 
-__device__ __noinline__ void closest_simplex_dev(const V3* w, int n, b2s_simplex_result* r) { b2s_closest_simplex(w, n, r); }
+// Device form of b2s_closest_simplex (include/b2s_geom.h): the same arithmetic and the same decisions, but the
+// triangle routine exists ONCE (noinline, canonical vertex roles 0,1,2) and the callers remap its weights.  The
+// header version inlines it five times with different index triples: 1570 SASS instructions (25 KB, most of the
+// 32 KB instruction cache) against ~600 here, and the GJK loop is the hottest loop of the narrow phase.
+struct TriRes { V3 v; float t0, t1, t2; int used; };
+__device__ __noinline__ void closest_tri_dev(V3 a, V3 b, V3 c, TriRes* o) {
+  b2s_simplex_result t;
+  b2s_closest_triangle(a, b, c, 0, 1, 2, &t);
+  o->v = t.v; o->t0 = t.bary[0]; o->t1 = t.bary[1]; o->t2 = t.bary[2]; o->used = t.used;
+}
+// writes the weights of the triangle (i0, i1, i2 are compile-time constants at every call site)
+#define TRI_TO_RESULT(T, i0, i1, i2, R)                                                        \
+  {                                                                                            \
+    (R)->v = (T).v;                                                                            \
+    (R)->bary[0] = (R)->bary[1] = (R)->bary[2] = (R)->bary[3] = 0.0f;                          \
+    if ((T).used & 1) (R)->bary[i0] = (T).t0;                                                  \
+    if ((T).used & 2) (R)->bary[i1] = (T).t1;                                                  \
+    if ((T).used & 4) (R)->bary[i2] = (T).t2;                                                  \
+    (R)->used = (((T).used & 1) << (i0)) | ((((T).used >> 1) & 1) << (i1)) | ((((T).used >> 2) & 1) << (i2)); \
+  }
+__device__ __noinline__ void closest_simplex_dev(const V3* w, int n, b2s_simplex_result* r) {
+  r->inside = 0;
+  r->degenerate = 0;
+  if (n == 1) {
+    r->v = w[0];
+    r->bary[0] = 1.0f; r->bary[1] = r->bary[2] = r->bary[3] = 0.0f;
+    r->used = 1;
+    return;
+  }
+  if (n == 2) { b2s_closest_segment(w[0], w[1], 0, 1, r); return; }
+  TriRes t;
+  if (n == 3) { closest_tri_dev(w[0], w[1], w[2], &t); TRI_TO_RESULT(t, 0, 1, 2, r); return; }
+  const int o0 = b2s_origin_outside_plane(w[0], w[1], w[2], w[3]);
+  const int o1 = b2s_origin_outside_plane(w[0], w[2], w[3], w[1]);
+  const int o2 = b2s_origin_outside_plane(w[0], w[3], w[1], w[2]);
+  const int o3 = b2s_origin_outside_plane(w[1], w[3], w[2], w[0]);
+  if (o0 < 0 || o1 < 0 || o2 < 0 || o3 < 0) {
+    r->degenerate = 1;
+    closest_tri_dev(w[1], w[2], w[3], &t); TRI_TO_RESULT(t, 1, 2, 3, r);
+    return;
+  }
+  if (!o0 && !o1 && !o2 && !o3) {
+    r->inside = 1;
+    r->v = v3(0.0f, 0.0f, 0.0f);
+    r->bary[0] = r->bary[1] = r->bary[2] = r->bary[3] = 0.25f;
+    r->used = 15;
+    return;
+  }
+  float best = 3.0e38f;
+  if (o0) { closest_tri_dev(w[0], w[1], w[2], &t); float d = len2(t.v); if (d < best) { best = d; TRI_TO_RESULT(t, 0, 1, 2, r); } }
+  if (o1) { closest_tri_dev(w[0], w[2], w[3], &t); float d = len2(t.v); if (d < best) { best = d; TRI_TO_RESULT(t, 0, 2, 3, r); } }
+  if (o2) { closest_tri_dev(w[0], w[3], w[1], &t); float d = len2(t.v); if (d < best) { best = d; TRI_TO_RESULT(t, 0, 3, 1, r); } }
+  if (o3) { closest_tri_dev(w[1], w[3], w[2], &t); float d = len2(t.v); if (d < best) { best = d; TRI_TO_RESULT(t, 1, 3, 2, r); } }
+}
 
 // The simplex lives in shared memory in PHYSICAL slots that never move; `perm` (2 bits per entry) maps
 // the logical order (= the oracle's compacted order) to physical slots and `ids` packs (ia | ib << 8)
 // of the logical entries, so the duplicate test and the compaction are register-only integer work.
-__device__ int gjk(const ColRef& A, const ColRef& B, float limit, float* sx, V3* v_out, V3* pa,
+__device__ __noinline__ int gjk(const ColRef& A, const ColRef& B, float limit, float* sx, V3* v_out, V3* pa,
                    V3* pb, int lane) {
   V3 v = A.cen - B.cen;
   if (len2(v) < 1e-12f) v = v3(1.0f, 0.0f, 0.0f);
@@ -911,6 +973,7 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
   int newn = 0, ncon = 0, cflags = 0;
   bool man_over = false, con_over = false;
   float* stg = S.stage;   // [4][16]
+  float* epa_scr = W.epa_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * EP_WORDS;
   for (int p = 0; p < np; ++p) {
     const int key = S.pairs[p];
     const int a = key >> 16, b = key & 0xffff;
@@ -938,8 +1001,8 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
       if (lane < n) {
 #pragma unroll
         for (int t = 0; t < B2S_CP_FLOATS; ++t) pt[t] = stg[lane * B2S_CP_FLOATS + t];
-        V3 wA = A.pos + mmul(A.R, v3(pt[0], pt[1], pt[2]));
-        V3 wB = Bc.pos + mmul(Bc.R, v3(pt[3], pt[4], pt[5]));
+        V3 wA = cr_pos(A) + mmul(cr_R(A), v3(pt[0], pt[1], pt[2]));
+        V3 wB = cr_pos(Bc) + mmul(cr_R(Bc), v3(pt[3], pt[4], pt[5]));
         V3 nn = v3(pt[6], pt[7], pt[8]);
         float dist = dot(wA - wB, nn);
         if (!(dist > threshold)) {
@@ -960,9 +1023,9 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
     }
     V3 pA, pB, nrm;
     float dist;
-    if (collide_pair(A, Bc, threshold, S.sx, S.con, &pA, &pB, &nrm, &dist, lane)) {
-      V3 lA = mtmul(A.R, pA - A.pos);
-      V3 lB = mtmul(Bc.R, pB - Bc.pos);
+    if (collide_pair(A, Bc, threshold, S.sx, epa_scr, &pA, &pB, &nrm, &dist, lane)) {
+      V3 lA = mtmul(cr_R(A), pA - cr_pos(A));
+      V3 lB = mtmul(cr_R(Bc), pB - cr_pos(Bc));
       // manifold_add (uniform decisions, lane 0 writes)
       int nearest = -1;
       float shortest = threshold * threshold;
@@ -1245,19 +1308,25 @@ __device__ __noinline__ void substep_post(int e, int lane, int wib, int C, int n
   (void)newn;
 }
 
-// ---- register-resident solve (max_contacts <= 32 and NB <= 32): one contact per lane ----------
-// Each lane builds the three Jacobian rows of its contact in registers, colours are assigned with
-// per-body 64-bit masks distributed over the lanes (lane s holds the mask of body slot s), and the
-// Gauss-Seidel sweep runs colour by colour with only the body velocities in shared memory.
-struct RowR { V3 dir, angA, angB, iangA, iangB; float inv_d, d, bias, lam; };
-
-__device__ __forceinline__ float rowr_jv(const RowR& r, const float* bA, const float* bB) {
-  return ((dot(r.dir, LD3(bA + BO_VEL)) + dot(r.angA, LD3(bA + BO_ANG))) - dot(r.dir, LD3(bB + BO_VEL))) - dot(r.angB, LD3(bB + BO_ANG));
-}
-__device__ __forceinline__ void rowr_apply(const RowR& r, float* bA, float* bB, float imA, float imB, bool dA, bool dB, float dl) {
-  if (dA) { ST3(bA + BO_VEL, vmad(LD3(bA + BO_VEL), r.dir, imA * dl)); ST3(bA + BO_ANG, vmad(LD3(bA + BO_ANG), r.iangA, dl)); }
-  if (dB) { ST3(bB + BO_VEL, vmad(LD3(bB + BO_VEL), r.dir, -(imB * dl))); ST3(bB + BO_ANG, vmad(LD3(bB + BO_ANG), r.iangB, -dl)); }
-}
+// ---- body-centric solve (max_contacts <= 32 and NB <= 32) ------------------------------------------------
+// Row build and colouring run one CONTACT per lane; the Gauss-Seidel sweeps run one BODY per lane.
+// The sweep of one environment is a chain of dependent row updates (12 per body and iteration for a body
+// resting on four points) and 5% of the env-substeps run all 50 iterations, so its latency -- not its
+// throughput -- sets the length of the block's solve stage.  With the velocity of a body in the registers of
+// "its" lane (lane = body slot) a row update is two dot products, a clamp and two fused multiply-adds on
+// registers: no shared-memory round trip of the velocities, no warp barrier between colours.  The rows are
+// immutable during the sweeps; the contact lanes park them in a per-warp record array in global memory
+// (256 B per contact, read back as 128-bit loads that hit L1 after the warm start), lambda lives in shared
+// memory.  Order of operations per body = colour order = the oracle's order, and every row update performs
+// the oracle's IEEE operations, so results stay bit-identical.
+// A contact between two dynamic bodies is processed by both lanes in the same colour step: they exchange
+// their velocities with shuffles, compute the same impulse and each applies its own side.
+#define RR_ROW 20                       // dir3 angA3 iangA3 angB3 iangB3 inv_d d k1 k2 pad
+#define RR_HEAD 60                      // bias0 mu imA imB
+#define RR_WORDS 64                     // per contact
+#define SOLVE_T_WORDS 512               // byte table [64 colours][32 slots] in the warp's `con` scratch
+#define SOLVE_LAM (SOLVE_T_WORDS)       // float lambda [3][32], the B lane's copy of it [3][32], slotA [32], slotB [32]
+#define SOLVE_WORDS (SOLVE_T_WORDS + 8 * 32)
 
 __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, int newn) {
   const WarpSmem S = carve(wib);
@@ -1269,18 +1338,20 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   const size_t nbase = ((size_t)par * W.B + e) * P.max_manifolds;
   const int nrows = 1 + P.friction_dirs;
   const bool act = lane < C;
-  RowR R[3];
+  float* rr = W.row_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * (32 * RR_WORDS);
+  unsigned char* T = (unsigned char*)S.con;
+  float* lam = S.con + SOLVE_LAM;
   int sA = 0, sB = 0, mk = 0;
-  float mu = 0.0f, imA = 0.0f, imB = 0.0f;
   bool dA = false, dB = false;
-  float* bA = S.body; float* bB = S.body;
+  __syncwarp();
   if (act) {
     mk = S.cmk[lane];
     const int m = mk >> 2, k = mk & 3;
     const int key = W.man_keys[nbase + m];
     const int a = key >> 16, b = key & 0xffff;
     sA = __float_as_int(S.col[a * COL_STRIDE + CO_SLOT]); sB = __float_as_int(S.col[b * COL_STRIDE + CO_SLOT]);
-    bA = S.body + sA * BODY_STRIDE; bB = S.body + sB * BODY_STRIDE;
+    const float* bA = S.body + sA * BODY_STRIDE;
+    const float* bB = S.body + sB * BODY_STRIDE;
     const float* p = W.man_pts + ((nbase + m) * 4 + k) * B2S_CP_FLOATS;
     V3 posA = LD3(bA + BO_POS), posB = LD3(bB + BO_POS);
     V3 wA = posA + mmul(ldm3(bA + BO_R), v3(p[0], p[1], p[2]));
@@ -1289,32 +1360,36 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
     V3 rA = wA - posA, rB = wB - posB;
     V3 t1, t2;
     plane_space(n, &t1, &t2);
+    const V3 velB = LD3(bB + BO_VEL), angvB = LD3(bB + BO_ANG);
     if (P.friction_dirs == 1) {
-      V3 rel = (LD3(bA + BO_VEL) + cross(LD3(bA + BO_ANG), rA)) - (LD3(bB + BO_VEL) + cross(LD3(bB + BO_ANG), rB));
+      V3 rel = (LD3(bA + BO_VEL) + cross(LD3(bA + BO_ANG), rA)) - (velB + cross(angvB, rB));
       V3 lat = rel - n * dot(rel, n);
       float l2 = len2(lat);
       if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
     }
-    imA = bA[BO_INVM]; imB = bB[BO_INVM];
+    const float imA = bA[BO_INVM], imB = bB[BO_INVM];
+    dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC; dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
     const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
+    float4* rec = (float4*)(rr + lane * RR_WORDS);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
-      R[r].dir = dir;
-      R[r].angA = cross(rA, dir); R[r].angB = cross(rB, dir);
-      R[r].iangA = mmul(iA, R[r].angA); R[r].iangB = mmul(iB, R[r].angB);
-      float d = ((imA + imB) + dot(R[r].iangA, R[r].angA)) + dot(R[r].iangB, R[r].angB);
-      R[r].inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
-      R[r].d = d;
-      R[r].bias = 0.0f;
-      float lam = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
-      if (r >= nrows) lam = 0.0f;
-      R[r].lam = lam;
+      const V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
+      const V3 angA = cross(rA, dir), angB = cross(rB, dir);
+      const V3 iangA = mmul(iA, angA), iangB = mmul(iB, angB);
+      const float d = ((imA + imB) + dot(iangA, angA)) + dot(iangB, angB);
+      const float inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
+      float l0 = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
+      if (r >= nrows) l0 = 0.0f;
+      lam[r * 32 + lane] = l0;
+      rec[r * 5 + 0] = make_float4(dir.x, dir.y, dir.z, angA.x);
+      rec[r * 5 + 1] = make_float4(angA.y, angA.z, iangA.x, iangA.y);
+      rec[r * 5 + 2] = make_float4(iangA.z, angB.x, angB.y, angB.z);
+      rec[r * 5 + 3] = make_float4(iangB.x, iangB.y, iangB.z, inv_d);
+      rec[r * 5 + 4] = make_float4(d, dot(dir, velB), dot(angB, angvB), 0.0f);
     }
-    float pen = p[9] + P.linear_slop;
-    R[0].bias = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
-    mu = bA[BO_FRIC] * bB[BO_FRIC];
-    dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC; dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
+    const float pen = p[9] + P.linear_slop;
+    const float bias0 = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
+    rec[15] = make_float4(bias0, bA[BO_FRIC] * bB[BO_FRIC], imA, imB);
   }
   // greedy colouring in contact order; lane s keeps the colour mask of body slot s
   unsigned long long used = 0ull;
@@ -1332,55 +1407,104 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
     if ((idA && lane == isA) || (idB && lane == isB)) used |= 1ull << k;
   }
   if (col_over && lane == 0) W.error_flags[e] |= 16;
-  const bool on = act && mycol >= 0;
-  // warm start
-  for (int k = 0; k < ncolours; ++k) {
-    if (on && mycol == k) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) if (r < nrows) rowr_apply(R[r], bA, bB, imA, imB, dA, dB, R[r].lam);
-    }
-    __syncwarp();
+  // T[k][slot] = contact of colour k touching dynamic body `slot`: index | side << 5 | coupled << 6, 0xff = none
+  for (int i = lane; i < ncolours * 8; i += 32) ((unsigned*)T)[i] = 0xffffffffu;
+  __syncwarp();
+  if (act && mycol >= 0) {
+    const unsigned cpl = (dA && dB) ? 64u : 0u;
+    if (dA) T[mycol * 32 + sA] = (unsigned char)(lane | cpl);
+    if (dB) T[mycol * 32 + sB] = (unsigned char)(lane | 32u | cpl);
   }
+  // colours that hold a contact between two dynamic bodies need the velocity exchange (warp uniform)
+  unsigned long long coupled = 0ull;
+  for (int k = 0; k < ncolours; ++k)
+    if (__any_sync(FULL, act && mycol == k && dA && dB)) coupled |= 1ull << k;
+  __syncwarp();
+  // ---- sweeps: lane = body slot
+  const float* myb = S.body + (lane < W.NB ? lane : 0) * BODY_STRIDE;
+  const bool dyn = lane < W.NB && __float_as_int(myb[BO_TYPE]) == B2S_TYPE_DYNAMIC;
+  V3 vel = LD3(myb + BO_VEL), ang = LD3(myb + BO_ANG);
+  // one row update of the contact this lane meets in colour k; pass 0: warm start, 1: normal row, 2: friction rows
+#define SOLVE_STEP(PASS)                                                                                          \
+  {                                                                                                               \
+    const unsigned t = dyn ? (unsigned)T[k * 32 + lane] : 0xffu;                                                  \
+    const bool has = t != 0xffu;                                                                                  \
+    const int c = t & 31;                                                                                         \
+    const bool sideB = (t & 32u) != 0u, cpl = (t & 64u) != 0u;                                                    \
+    V3 ov = v3(0, 0, 0), ow = v3(0, 0, 0);                                                                        \
+    if ((coupled >> k) & 1ull) {                                                                                  \
+      int src = lane;                                                                                             \
+      if (has && cpl) src = __float_as_int(sideB ? lam[192 + c] : lam[224 + c]);                                  \
+      ov = v3(__shfl_sync(FULL, vel.x, src), __shfl_sync(FULL, vel.y, src), __shfl_sync(FULL, vel.z, src));       \
+      ow = v3(__shfl_sync(FULL, ang.x, src), __shfl_sync(FULL, ang.y, src), __shfl_sync(FULL, ang.z, src));       \
+    }                                                                                                             \
+    if (has) {                                                                                                    \
+      const float4* rec = (const float4*)(rr + c * RR_WORDS);                                                     \
+      const float4 hd = rec[15];                                                                                  \
+      const float im = sideB ? hd.w : hd.z;                                                                       \
+      const int r0 = (PASS == 2) ? 1 : 0, r1 = (PASS == 1) ? 1 : nrows;                                           \
+      float* ml = sideB ? lam + 96 : lam;            /* both lanes of a coupled contact keep their own lambda */  \
+      const float lim = hd.y * ml[c];                                                                             \
+      for (int r = r0; r < r1; ++r) {                                                                             \
+        const float4 q0 = rec[r * 5], q1 = rec[r * 5 + 1], q2 = rec[r * 5 + 2], q3 = rec[r * 5 + 3], q4v = rec[r * 5 + 4]; \
+        const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
+        const V3 angB = v3(q2.y, q2.z, q2.w), iangB = v3(q3.x, q3.y, q3.z);                                       \
+        float dl;                                                                                                 \
+        const float l = ml[r * 32 + c];                                                                           \
+        if (PASS == 0) dl = l;                                                                                    \
+        else {                                                                                                    \
+          const V3 vA = sideB ? ov : vel, wA = sideB ? ow : ang;                                                  \
+          const float a = dot(dir, vA) + dot(angA, wA);                                                           \
+          float k1 = q4v.y, k2 = q4v.z;                                                                           \
+          if (cpl) { k1 = dot(dir, sideB ? vel : ov); k2 = dot(angB, sideB ? ang : ow); }                         \
+          const float jv = (a - k1) - k2;                                                                         \
+          dl = (((PASS == 1) ? hd.x : 0.0f) - jv) * q3.w;                                                         \
+          float nl = l + dl;                                                                                      \
+          nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
+          dl = nl - l;                                                                                            \
+          ml[r * 32 + c] = nl;                                                                                    \
+          const float res = dl * q4v.x;                                                                           \
+          maxres = fmaxf(maxres, res * res);                                                                      \
+        }                                                                                                         \
+        if (!sideB) {                                                                                             \
+          vel = vmad(vel, dir, im * dl); ang = vmad(ang, iangA, dl);                                              \
+          if (cpl) { ov = vmad(ov, dir, -(hd.w * dl)); ow = vmad(ow, iangB, -dl); }   /* what the partner does */ \
+        } else {                                                                                                  \
+          vel = vmad(vel, dir, -(im * dl)); ang = vmad(ang, iangB, -dl);                                          \
+          if (cpl) { ov = vmad(ov, dir, hd.z * dl); ow = vmad(ow, iangA, dl); }                                   \
+        }                                                                                                         \
+      }                                                                                                           \
+    }                                                                                                             \
+  }
+  // slots of the two bodies of every contact, for the partner lookup of coupled contacts
+  if (act) {
+    lam[192 + lane] = __int_as_float(sA); lam[224 + lane] = __int_as_float(sB);
+    lam[96 + lane] = lam[lane]; lam[128 + lane] = lam[32 + lane]; lam[160 + lane] = lam[64 + lane];
+    if (dB && !dA && lane >= 0) W.error_flags[e] |= 64;   // cannot happen: movable colliders are numbered last
+  }
+  __syncwarp();
+  float maxres = 0.0f;
+  for (int k = 0; k < ncolours; ++k) SOLVE_STEP(0)
   int iters = 0;
   for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
-    float maxres = 0.0f;
-    for (int k = 0; k < ncolours; ++k) {
-      if (on && mycol == k) {
-        float dl = (R[0].bias - rowr_jv(R[0], bA, bB)) * R[0].inv_d;
-        float nl = fmaxf(0.0f, R[0].lam + dl);
-        dl = nl - R[0].lam;
-        R[0].lam = nl;
-        rowr_apply(R[0], bA, bB, imA, imB, dA, dB, dl);
-        float res = dl * R[0].d;
-        maxres = fmaxf(maxres, res * res);
-      }
-      __syncwarp();
-    }
-    for (int k = 0; k < ncolours; ++k) {
-      if (on && mycol == k) {
-        const float lim = mu * R[0].lam;
-#pragma unroll
-        for (int r = 1; r < 3; ++r) {
-          if (r < nrows) {
-            float dl = (0.0f - rowr_jv(R[r], bA, bB)) * R[r].inv_d;
-            float nl = fminf(lim, fmaxf(-lim, R[r].lam + dl));
-            dl = nl - R[r].lam;
-            R[r].lam = nl;
-            rowr_apply(R[r], bA, bB, imA, imB, dA, dB, dl);
-            float res = dl * R[r].d;
-            maxres = fmaxf(maxres, res * res);
-          }
-        }
-      }
-      __syncwarp();
-    }
+    maxres = 0.0f;
+    for (int k = 0; k < ncolours; ++k) SOLVE_STEP(1)
+    __syncwarp();
+    for (int k = 0; k < ncolours; ++k) SOLVE_STEP(2)
+    __syncwarp();
     iters = it + 1;
     unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
     if (__uint_as_float(mx) <= P.residual_threshold) break;
   }
+#undef SOLVE_STEP
+  if (dyn) {
+    float* wb = S.body + lane * BODY_STRIDE;
+    ST3(wb + BO_VEL, vel); ST3(wb + BO_ANG, ang);
+  }
+  __syncwarp();
   if (act) {
     float* p = W.man_pts + ((nbase + (mk >> 2)) * 4 + (mk & 3)) * B2S_CP_FLOATS;
-    p[10] = R[0].lam; p[11] = R[1].lam; p[12] = R[2].lam;
+    p[10] = lam[lane]; p[11] = lam[32 + lane]; p[12] = lam[64 + lane];
   }
   if (lane == 0) {
     int32_t* st = W.solver_stats + (size_t)e * 4;
@@ -1563,8 +1687,11 @@ __device__ __forceinline__ int grab_slot(int* counter, int lane, int wib, int E,
 // Block = Wn warps stepping E environments.  Every substep runs three stages separated by block barriers
 // (scene -> narrow phase -> solve/integrate/phase logic); inside a stage the warps take environments from
 // a shared counter, so a warp stuck on a long solve does not hold the others back, and all warps of the
-// block execute the same code region at the same time (the kernel is far larger than the instruction
-// cache; walking it together is what keeps instruction fetch from dominating).
+// block execute the same code region at the same time (the kernel is ~10x the 32 KB instruction cache;
+// walking it together is what keeps instruction fetch from dominating).  Measured alternatives, all slower
+// on 4096 envs x 100 substeps mid-push: no barriers + a ready ring of environments
+// (2.0x slower: 16 warps in 16 code regions), warps leaving the barrier protocol during long solves
+// (1.15-1.25x slower: persistent stragglers become the tail of the launch), two 8-warp blocks per SM (1.2x).
 __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps) {
   __shared__ int s_cnt[3];
   const int lane = threadIdx.x & 31;
@@ -1697,4 +1824,6 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
   k_substeps<<<blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps);
 }
 
-size_t b2s_smem_bytes(const DWorld& W) { return ((size_t)W.envs_per_block * W.sm.words_env + (size_t)W.P.warps_per_block * W.sm.words_warp) * 4; }
+size_t b2s_smem_bytes(const DWorld& W) {
+  return ((size_t)W.envs_per_block * (W.sm.words_env + META_WORDS) + (size_t)W.P.warps_per_block * W.sm.words_warp) * 4;
+}
