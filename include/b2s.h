@@ -230,7 +230,8 @@ enum {
   B2S_ARR_NUM_COLLIDERS = 21,  /* int32 [B] */
   B2S_ARR_COL_SLOT = 22,       /* int32 [B][max_colliders] body slot of each collider */
   B2S_ARR_COL_HULL = 23,       /* int32 [B][max_colliders] hull id of each collider */
-  B2S_ARR_COUNT = 24
+  B2S_ARR_PROF = 24,           /* uint64 [8] stage timing of the substep kernel (ns; tuning builds only) */
+  B2S_ARR_COUNT = 25
 };
 #define B2S_CP_FLOATS 16   /* localA3 localB3 normalB3 dist lambda_n lambda_t1 lambda_t2 t1x t1y t1z */
 #define B2S_CTRL_FLOATS 40

@@ -262,7 +262,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   ALLOC(contact_flags, B, 0); ALLOC(phase_state, B * 8, 0); ALLOC(solver_stats, B * 4, 0);
   ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
   ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
-  ALLOC(substeps, 1, 0); ALLOC(unfinished, 1, 0);
+  ALLOC(substeps, 1, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024, 0);
   if ((rc = dalloc(w, &w->exp_keys, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_npts, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_pts, B * M * 4 * B2S_CP_FLOATS, 0))) return rc;
@@ -320,7 +320,8 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     d.envs_per_block = E;
     const size_t blocks = (d.B + E - 1) / E;
     if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
-    if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)(32 * 64), 0))) return rc;
+    if ((rc = dalloc(w, &d.env_map, blocks * (size_t)E, 0xff))) return rc;
+    if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)(32 * 68), 0))) return rc;
   }
   size_t smem = b2s_smem_bytes(d);
   if (smem > 227 * 1024) return fail(B2S_E_CAPACITY, "b2s_load_scene: %zu bytes of shared memory per block exceed 227 KB; lower warps_per_block or the capacities", smem);
@@ -338,6 +339,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   reg(B2S_ARR_SOLVER_STATS, d.solver_stats, B * 16); reg(B2S_ARR_CTRL_TIME, d.ctrl_time, B * 40);
   reg(B2S_ARR_LINK_VEL, d.link_vel, B * d.L * 24); reg(B2S_ARR_NUM_COLLIDERS, d.ncol, B * 4);
   reg(B2S_ARR_COL_SLOT, d.col_slot, B * d.Hmax * 4); reg(B2S_ARR_COL_HULL, d.col_hull, B * d.Hmax * 4);
+  reg(B2S_ARR_PROF, d.prof, (8 + 4 * 1024) * 8);
   w->scene_loaded = true;
   return 0;
 }
@@ -363,7 +365,7 @@ int b2s_settle(B2SWorld* w, float lin, float ang, int max_steps, void* stream) {
   NEED_READY(w);
   if (max_steps < 1) return fail(B2S_E_INVALID, "b2s_settle: max_steps < 1");
   b2s_launch_substeps(w->d, 0, MODE_SETTLE, lin, ang, max_steps, (cudaStream_t)stream);
-  return check_launch(w, "settle");
+  return check_launch(w, "settle", 2);      // deal of the environments + substep kernel
 }
 
 int b2s_step(B2SWorld* w, int n, void* stream) {
@@ -371,7 +373,7 @@ int b2s_step(B2SWorld* w, int n, void* stream) {
   if (n < 0) return fail(B2S_E_INVALID, "b2s_step: n < 0");
   if (n == 0) return 0;
   b2s_launch_substeps(w->d, n, MODE_RAW, 0, 0, 0, (cudaStream_t)stream);
-  return check_launch(w, "step");
+  return check_launch(w, "step", 2);
 }
 
 int b2s_step_staged(B2SWorld* w, int n, void* stream) {
@@ -379,7 +381,7 @@ int b2s_step_staged(B2SWorld* w, int n, void* stream) {
   if (n < 0) return fail(B2S_E_INVALID, "b2s_step_staged: n < 0");
   int64_t launches = 0;
   b2s_launch_staged(w->d, n, (cudaStream_t)stream, &launches);
-  return check_launch(w, "step_staged", (int)launches);
+  return check_launch(w, "step_staged", 2 * (int)launches);
 }
 
 int b2s_set_action(B2SWorld* w, void* stream) {
@@ -394,7 +396,7 @@ int b2s_env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaMemsetAsync(w->d.unfinished, 0, sizeof(int), s));
   b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, s);
-  int rc = check_launch(w, "env_substeps");
+  int rc = check_launch(w, "env_substeps", 2);
   if (rc) return rc;
   if (unfinished_host) {
     CU(cudaMemcpyAsync(w->unfinished_pinned, w->d.unfinished, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -87,6 +87,7 @@ struct SmemLayout {
 #define META_SETTLE_STEPS 4
 #define META_SETTLE_STABLE 5
 #define META_FINISHED 6
+#define META_ENV 7            // environment index of the slot in this launch
 #define META_WORDS 8
 
 #define BODY_STRIDE 35   // pos3 R9 vel3 ang3 invm1 invI9 fric1 type1 quat4 = 34 (+1 pad, odd stride)
@@ -145,7 +146,9 @@ struct DWorld {
   unsigned long long* substeps;   // device counter: total env-substeps executed
   int32_t* unfinished;            // device counter used by env_substeps
   float* epa_scratch;             // [blocks][warps][EP_WORDS] EPA polytope (rare path: lives in L2, not in shared memory)
-  float* row_scratch;             // [blocks][warps][32][64] solver rows of the environment a warp is solving (L1/L2 resident)
+  int32_t* env_map;               // [blocks][E] environment stepped in a block slot (-1 none), re-dealt before every launch
+  unsigned long long* prof;       // [8] stage timing counters (only written by -DB2S_PROF builds)
+  float* row_scratch;             // [blocks][warps][32][68] solver rows of the environment a warp is solving (L1/L2 resident)
   // staged-mode scratch: contact rows / body velocities dumped between kernels
   float* stage_rows;     // [B][max_contacts][CON_STRIDE]
   float* stage_body;     // [B][NB][BODY_STRIDE]
@@ -162,6 +165,7 @@ enum { SPLIT_NONE = 0, SPLIT_PRE = 1, SPLIT_POST = 2 };   // staged mode: stop b
 
 // host launchers (defined next to their kernels)
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, cudaStream_t s);
+void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s);
 void b2s_launch_staged(const DWorld& W, int n, cudaStream_t s, int64_t* launches);
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s);
 void b2s_launch_set_action(const DWorld& W, cudaStream_t s);

@@ -454,8 +454,9 @@ __device__ __noinline__ void closest_simplex_dev(const V3* w, int n, b2s_simplex
 // The simplex lives in shared memory in PHYSICAL slots that never move; `perm` (2 bits per entry) maps
 // the logical order (= the oracle's compacted order) to physical slots and `ids` packs (ia | ib << 8)
 // of the logical entries, so the duplicate test and the compaction are register-only integer work.
-__device__ __noinline__ int gjk(const ColRef& A, const ColRef& B, float limit, float* sx, V3* v_out, V3* pa,
+__device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float limit, float* sx, V3* v_out, V3* pa,
                    V3* pb, int lane) {
+  const ColRef A = A_in, B = B_in;      // register copies: the references point into the caller's local memory
   V3 v = A.cen - B.cen;
   if (len2(v) < 1e-12f) v = v3(1.0f, 0.0f, 0.0f);
   int n = 0;
@@ -1321,12 +1322,13 @@ __device__ __noinline__ void substep_post(int e, int lane, int wib, int C, int n
 // the oracle's IEEE operations, so results stay bit-identical.
 // A contact between two dynamic bodies is processed by both lanes in the same colour step: they exchange
 // their velocities with shuffles, compute the same impulse and each applies its own side.
-#define RR_ROW 20                       // dir3 angA3 iangA3 angB3 iangB3 inv_d d k1 k2 pad
-#define RR_HEAD 60                      // bias0 mu imA imB
-#define RR_WORDS 64                     // per contact
+// record of one contact, in float4 units: row r at [4r .. 4r+3] =
+//   (dir.xyz, angA.x) (angA.yz, iangA.xy) (iangA.z, 1/d, d, k1) (k2, imA, bias0 | mu, imB)
+// then, as scalars from word 48, angB.xyz iangB.xyz of every row (only read for a dynamic body B)
+#define RR_B 48
+#define RR_WORDS 68                     // per contact (272 B, 16-byte aligned)
 #define SOLVE_T_WORDS 512               // byte table [64 colours][32 slots] in the warp's `con` scratch
 #define SOLVE_LAM (SOLVE_T_WORDS)       // float lambda [3][32], the B lane's copy of it [3][32], slotA [32], slotB [32]
-#define SOLVE_WORDS (SOLVE_T_WORDS + 8 * 32)
 
 __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, int newn) {
   const WarpSmem S = carve(wib);
@@ -1371,6 +1373,10 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
     dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC; dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
     const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
     float4* rec = (float4*)(rr + lane * RR_WORDS);
+    float* recb = rr + lane * RR_WORDS + RR_B;
+    const float pen = p[9] + P.linear_slop;
+    const float bias0 = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
+    const float mu = bA[BO_FRIC] * bB[BO_FRIC];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
@@ -1381,15 +1387,15 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       float l0 = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
       if (r >= nrows) l0 = 0.0f;
       lam[r * 32 + lane] = l0;
-      rec[r * 5 + 0] = make_float4(dir.x, dir.y, dir.z, angA.x);
-      rec[r * 5 + 1] = make_float4(angA.y, angA.z, iangA.x, iangA.y);
-      rec[r * 5 + 2] = make_float4(iangA.z, angB.x, angB.y, angB.z);
-      rec[r * 5 + 3] = make_float4(iangB.x, iangB.y, iangB.z, inv_d);
-      rec[r * 5 + 4] = make_float4(d, dot(dir, velB), dot(angB, angvB), 0.0f);
+      rec[r * 4 + 0] = make_float4(dir.x, dir.y, dir.z, angA.x);
+      rec[r * 4 + 1] = make_float4(angA.y, angA.z, iangA.x, iangA.y);
+      rec[r * 4 + 2] = make_float4(iangA.z, inv_d, d, dot(dir, velB));
+      rec[r * 4 + 3] = make_float4(dot(angB, angvB), imA, (r == 0) ? bias0 : mu, imB);
+      if (dB) {
+        recb[r * 6 + 0] = angB.x; recb[r * 6 + 1] = angB.y; recb[r * 6 + 2] = angB.z;
+        recb[r * 6 + 3] = iangB.x; recb[r * 6 + 4] = iangB.y; recb[r * 6 + 5] = iangB.z;
+      }
     }
-    const float pen = p[9] + P.linear_slop;
-    const float bias0 = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
-    rec[15] = make_float4(bias0, bA[BO_FRIC] * bB[BO_FRIC], imA, imB);
   }
   // greedy colouring in contact order; lane s keeps the colour mask of body slot s
   unsigned long long used = 0ull;
@@ -1424,79 +1430,119 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   const float* myb = S.body + (lane < W.NB ? lane : 0) * BODY_STRIDE;
   const bool dyn = lane < W.NB && __float_as_int(myb[BO_TYPE]) == B2S_TYPE_DYNAMIC;
   V3 vel = LD3(myb + BO_VEL), ang = LD3(myb + BO_ANG);
-  // one row update of the contact this lane meets in colour k; pass 0: warm start, 1: normal row, 2: friction rows
-#define SOLVE_STEP(PASS)                                                                                          \
+  // one row update of the contact this lane meets in colour k; pass 0: warm start, 1: normal row, 2: friction rows.
+  // STEP_FAST: no contact of the colour joins two dynamic bodies (warp uniform) -- every lane is the A side.
+#define STEP_FAST(PASS)                                                                                           \
+  {                                                                                                               \
+    const unsigned t = dyn ? (unsigned)T[k * 32 + lane] : 0xffu;                                                  \
+    if (t != 0xffu) {                                                                                             \
+      const int c = t & 31;                                                                                       \
+      const float4* rec = (const float4*)(rr + c * RR_WORDS);                                                     \
+      float lim = 0.0f;                                                                                           \
+      if (PASS == 2) lim = rec[7].z * lam[c];                                                                     \
+      _Pragma("unroll")                                                                                           \
+      for (int r = (PASS == 2) ? 1 : 0; r < ((PASS == 1) ? 1 : 3); ++r) {                                         \
+        if (r >= nrows) break;                                                                                    \
+        const float4 q0 = rec[r * 4], q1 = rec[r * 4 + 1], q2 = rec[r * 4 + 2], q3 = rec[r * 4 + 3];              \
+        const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
+        const float l = lam[r * 32 + c];                                                                          \
+        float dl = l;                                                                                             \
+        if (PASS != 0) {                                                                                          \
+          const float jv = ((dot(dir, vel) + dot(angA, ang)) - q2.w) - q3.x;                                      \
+          dl = (((PASS == 1) ? q3.z : 0.0f) - jv) * q2.y;                                                         \
+          float nl = l + dl;                                                                                      \
+          nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
+          dl = nl - l;                                                                                            \
+          lam[r * 32 + c] = nl;                                                                                   \
+          const float res = dl * q2.z;                                                                            \
+          maxres = fmaxf(maxres, res * res);                                                                      \
+        }                                                                                                         \
+        vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                              \
+      }                                                                                                           \
+    }                                                                                                             \
+  }
+  // slots of the two bodies of every contact (partner lookup of coupled contacts) and the B lane's copy of lambda
+  if (act) {
+    lam[192 + lane] = __int_as_float(sA); lam[224 + lane] = __int_as_float(sB);
+    lam[96 + lane] = lam[lane]; lam[128 + lane] = lam[32 + lane]; lam[160 + lane] = lam[64 + lane];
+    if (dB && !dA) W.error_flags[e] |= 64;   // cannot happen: movable colliders are numbered last
+  }
+  __syncwarp();
+  // STEP_SLOW: the colour holds a contact between two dynamic bodies (rare: movables touching each other).  Its
+  // two lanes exchange velocities with shuffles, compute the same impulse (each on its own copy of lambda) and
+  // apply their own side.  (Measured: moving this step out of line costs 20% -- taking the address of the
+  // velocities parks them in local memory for the whole sweep.)
+#define STEP_SLOW(PASS)                                                                                           \
   {                                                                                                               \
     const unsigned t = dyn ? (unsigned)T[k * 32 + lane] : 0xffu;                                                  \
     const bool has = t != 0xffu;                                                                                  \
     const int c = t & 31;                                                                                         \
     const bool sideB = (t & 32u) != 0u, cpl = (t & 64u) != 0u;                                                    \
-    V3 ov = v3(0, 0, 0), ow = v3(0, 0, 0);                                                                        \
-    if ((coupled >> k) & 1ull) {                                                                                  \
-      int src = lane;                                                                                             \
-      if (has && cpl) src = __float_as_int(sideB ? lam[192 + c] : lam[224 + c]);                                  \
-      ov = v3(__shfl_sync(FULL, vel.x, src), __shfl_sync(FULL, vel.y, src), __shfl_sync(FULL, vel.z, src));       \
-      ow = v3(__shfl_sync(FULL, ang.x, src), __shfl_sync(FULL, ang.y, src), __shfl_sync(FULL, ang.z, src));       \
-    }                                                                                                             \
+    int src = lane;                                                                                               \
+    if (has && cpl) src = __float_as_int(sideB ? lam[192 + c] : lam[224 + c]);                                    \
+    V3 ov = v3(__shfl_sync(FULL, vel.x, src), __shfl_sync(FULL, vel.y, src), __shfl_sync(FULL, vel.z, src));      \
+    V3 ow = v3(__shfl_sync(FULL, ang.x, src), __shfl_sync(FULL, ang.y, src), __shfl_sync(FULL, ang.z, src));      \
     if (has) {                                                                                                    \
       const float4* rec = (const float4*)(rr + c * RR_WORDS);                                                     \
-      const float4 hd = rec[15];                                                                                  \
-      const float im = sideB ? hd.w : hd.z;                                                                       \
+      const float* recb = rr + c * RR_WORDS + RR_B;                                                               \
       const int r0 = (PASS == 2) ? 1 : 0, r1 = (PASS == 1) ? 1 : nrows;                                           \
-      float* ml = sideB ? lam + 96 : lam;            /* both lanes of a coupled contact keep their own lambda */  \
-      const float lim = hd.y * ml[c];                                                                             \
+      float* ml = sideB ? lam + 96 : lam;                                                                         \
+      float lim = 0.0f;                                                                                           \
+      if (PASS == 2) lim = rec[7].z * ml[c];                                                                      \
       for (int r = r0; r < r1; ++r) {                                                                             \
-        const float4 q0 = rec[r * 5], q1 = rec[r * 5 + 1], q2 = rec[r * 5 + 2], q3 = rec[r * 5 + 3], q4v = rec[r * 5 + 4]; \
+        const float4 q0 = rec[r * 4], q1 = rec[r * 4 + 1], q2 = rec[r * 4 + 2], q3 = rec[r * 4 + 3];              \
         const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
-        const V3 angB = v3(q2.y, q2.z, q2.w), iangB = v3(q3.x, q3.y, q3.z);                                       \
-        float dl;                                                                                                 \
+        V3 angB = v3(0, 0, 0), iangB = v3(0, 0, 0);                                                               \
+        if (cpl) { angB = LD3(recb + r * 6); iangB = LD3(recb + r * 6 + 3); }                                     \
         const float l = ml[r * 32 + c];                                                                           \
-        if (PASS == 0) dl = l;                                                                                    \
-        else {                                                                                                    \
+        float dl = l;                                                                                             \
+        if (PASS != 0) {                                                                                          \
           const V3 vA = sideB ? ov : vel, wA = sideB ? ow : ang;                                                  \
           const float a = dot(dir, vA) + dot(angA, wA);                                                           \
-          float k1 = q4v.y, k2 = q4v.z;                                                                           \
+          float k1 = q2.w, k2 = q3.x;                                                                             \
           if (cpl) { k1 = dot(dir, sideB ? vel : ov); k2 = dot(angB, sideB ? ang : ow); }                         \
           const float jv = (a - k1) - k2;                                                                         \
-          dl = (((PASS == 1) ? hd.x : 0.0f) - jv) * q3.w;                                                         \
+          dl = (((PASS == 1) ? q3.z : 0.0f) - jv) * q2.y;                                                         \
           float nl = l + dl;                                                                                      \
           nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
           dl = nl - l;                                                                                            \
           ml[r * 32 + c] = nl;                                                                                    \
-          const float res = dl * q4v.x;                                                                           \
+          const float res = dl * q2.z;                                                                            \
           maxres = fmaxf(maxres, res * res);                                                                      \
         }                                                                                                         \
         if (!sideB) {                                                                                             \
-          vel = vmad(vel, dir, im * dl); ang = vmad(ang, iangA, dl);                                              \
-          if (cpl) { ov = vmad(ov, dir, -(hd.w * dl)); ow = vmad(ow, iangB, -dl); }   /* what the partner does */ \
+          vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                            \
+          if (cpl) { ov = vmad(ov, dir, -(q3.w * dl)); ow = vmad(ow, iangB, -dl); }   /* what the partner does */ \
         } else {                                                                                                  \
-          vel = vmad(vel, dir, -(im * dl)); ang = vmad(ang, iangB, -dl);                                          \
-          if (cpl) { ov = vmad(ov, dir, hd.z * dl); ow = vmad(ow, iangA, dl); }                                   \
+          vel = vmad(vel, dir, -(q3.w * dl)); ang = vmad(ang, iangB, -dl);                                        \
+          ov = vmad(ov, dir, q3.y * dl); ow = vmad(ow, iangA, dl);                                                \
         }                                                                                                         \
       }                                                                                                           \
     }                                                                                                             \
   }
-  // slots of the two bodies of every contact, for the partner lookup of coupled contacts
-  if (act) {
-    lam[192 + lane] = __int_as_float(sA); lam[224 + lane] = __int_as_float(sB);
-    lam[96 + lane] = lam[lane]; lam[128 + lane] = lam[32 + lane]; lam[160 + lane] = lam[64 + lane];
-    if (dB && !dA && lane >= 0) W.error_flags[e] |= 64;   // cannot happen: movable colliders are numbered last
-  }
-  __syncwarp();
+  // warm start (pass 0), then per iteration the normal rows (pass 1) of all colours and the friction rows
+  // (pass 2).  The fast step is specialised per pass; the coupled step takes the pass at run time.
+  // (Measured alternatives, all slower: one flattened row-step loop with run-time row selects, 1.5x; software
+  // pipelining of the operand loads across colour steps, 1.3x -- the compiler keeps this loop tight as it is.)
   float maxres = 0.0f;
-  for (int k = 0; k < ncolours; ++k) SOLVE_STEP(0)
   int iters = 0;
+#pragma unroll 1
+  for (int k = 0; k < ncolours; ++k) { if ((coupled >> k) & 1ull) { const int pass = 0; STEP_SLOW(pass) } else STEP_FAST(0) }
+  __syncwarp();
   for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
     maxres = 0.0f;
-    for (int k = 0; k < ncolours; ++k) SOLVE_STEP(1)
+#pragma unroll 1
+    for (int k = 0; k < ncolours; ++k) { if ((coupled >> k) & 1ull) { const int pass = 1; STEP_SLOW(pass) } else STEP_FAST(1) }
     __syncwarp();
-    for (int k = 0; k < ncolours; ++k) SOLVE_STEP(2)
+#pragma unroll 1
+    for (int k = 0; k < ncolours; ++k) { if ((coupled >> k) & 1ull) { const int pass = 2; STEP_SLOW(pass) } else STEP_FAST(2) }
     __syncwarp();
     iters = it + 1;
     unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
     if (__uint_as_float(mx) <= P.residual_threshold) break;
   }
-#undef SOLVE_STEP
+#undef STEP_FAST
+#undef STEP_SLOW
   if (dyn) {
     float* wb = S.body + lane * BODY_STRIDE;
     ST3(wb + BO_VEL, vel); ST3(wb + BO_ANG, ang);
@@ -1675,6 +1721,18 @@ __device__ __noinline__ void finish_action(int e, int lane) {
 
 // ----------------------------------------------------------- the kernel -----
 
+// Stage timing for tuning (compiled only with -DB2S_PROF; see tools/profile_step.py): W.prof[0..2] = duration of
+// stage A/B/C summed over blocks and rounds (thread 0, barrier to barrier), [3..5] = busy time of the warps inside
+// the stage summed over warps, [6] = rounds, [7] = longest single environment of stage C summed over rounds.
+#ifdef B2S_PROF
+__device__ __forceinline__ long long prof_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; }
+#define PROF_STAGE(i) { const long long now_ = prof_now(); if (lane == 0) atomicAdd(W.prof + 3 + (i), (unsigned long long)(now_ - pstart_)); }
+#define PROF_MARK(i) { const long long now_ = prof_now(); if (threadIdx.x == 0) { atomicAdd(W.prof + (i), (unsigned long long)(now_ - pstart_)); W.prof[8 + blockIdx.x * 4 + (i)] += (unsigned long long)(now_ - pstart_); } pstart_ = now_; }
+#else
+#define PROF_STAGE(i)
+#define PROF_MARK(i)
+#endif
+
 // Hand-out of environments inside a stage: dynamic (shared counter) when the solver rows live in registers;
 // with rows in per-warp shared memory an environment must stay with one warp for the whole substep.
 __device__ __forceinline__ int grab_slot(int* counter, int lane, int wib, int E, bool first) {
@@ -1694,6 +1752,10 @@ __device__ __forceinline__ int grab_slot(int* counter, int lane, int wib, int E,
 // (1.15-1.25x slower: persistent stragglers become the tail of the launch), two 8-warp blocks per SM (1.2x).
 __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps) {
   __shared__ int s_cnt[3];
+#ifdef B2S_PROF
+  __shared__ int s_maxc;
+  if (threadIdx.x == 0) s_maxc = 0;
+#endif
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int Wn = blockDim.x >> 5;
@@ -1710,8 +1772,9 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     int any = any_next;
     if (s == 0) {
       for (int slot = wib; slot < E; slot += Wn) {
-        const int e = e0 + slot;
-        const bool valid = e < W.B;
+        const int e = W.env_map[e0 + slot];
+        const bool valid = e >= 0;
+        if (lane == 0) env_meta(slot)[META_ENV] = e;
         bool active;
         if (mode == MODE_RAW) active = valid && n > 0;
         else if (mode == MODE_ENV) active = valid && n > 0 && W.phase[valid ? e : 0] != B2S_PHASE_IDLE;
@@ -1723,6 +1786,10 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     any_next = 0;
     if (!__syncthreads_or(any)) break;
     if (threadIdx.x == 0) s_cnt[2] = 0;
+#ifdef B2S_PROF
+    long long pstart_ = prof_now();
+    if (threadIdx.x == 0) { atomicAdd(W.prof + 6, 1ull); W.prof[8 + blockIdx.x * 4 + 3] += 1ull; }
+#endif
     // ---- stage A: controller + FK, body table, colliders, broad phase
     bool first0 = true, first1 = true, first2 = true;
     for (;;) {
@@ -1731,10 +1798,12 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       if (slot >= E) break;
       int* meta = env_meta(slot);
       if (!meta[META_ACTIVE]) continue;
-      const int np = stage_scene(e0 + slot, lane, slot | (wib << 16));
+      const int np = stage_scene(meta[META_ENV], lane, slot | (wib << 16));
       if (lane == 0) meta[META_NP] = np;
     }
+    PROF_STAGE(0)
     __syncthreads();
+    PROF_MARK(0)
     if (threadIdx.x == 0) s_cnt[0] = 0;
     // ---- stage B: narrow phase + manifolds
     for (;;) {
@@ -1744,10 +1813,12 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       int* meta = env_meta(slot);
       if (!meta[META_ACTIVE]) continue;
       int C = 0, newn = 0;
-      stage_narrow(e0 + slot, lane, slot | (wib << 16), meta[META_NP], &C, &newn, !W.reg_rows);
+      stage_narrow(meta[META_ENV], lane, slot | (wib << 16), meta[META_NP], &C, &newn, !W.reg_rows);
       if (lane == 0) { meta[META_C] = C; meta[META_NEWN] = newn; }
     }
+    PROF_STAGE(1)
     __syncthreads();
+    PROF_MARK(1)
     if (threadIdx.x == 0) s_cnt[1] = 0;
     // ---- stage C: solve, integrate, phase machine / settle bookkeeping
     for (;;) {
@@ -1756,7 +1827,10 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       if (slot >= E) break;
       int* meta = env_meta(slot);
       if (!meta[META_ACTIVE]) continue;
-      const int e = e0 + slot;
+#ifdef B2S_PROF
+      const long long penv_ = prof_now();
+#endif
+      const int e = meta[META_ENV];
       const int sw = slot | (wib << 16);
       const int ph = (mode == MODE_ENV) ? W.phase[e] : B2S_PHASE_IDLE;
       if (W.reg_rows) substep_post_reg(e, lane, sw, meta[META_C], meta[META_NEWN]);
@@ -1802,11 +1876,22 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       // activity of this environment in the next substep, published by the warp that just stepped it
       if (lane == 0) meta[META_ACTIVE] = nxt ? 1 : 0;
       any_next |= nxt ? 1 : 0;
+#ifdef B2S_PROF
+      if (lane == 0) atomicMax(&s_maxc, (int)(prof_now() - penv_));
+#endif
     }
+#ifdef B2S_PROF
+    PROF_STAGE(2)
+    __syncthreads();
+    PROF_MARK(2)
+    if (threadIdx.x == 0) { atomicAdd(W.prof + 7, (unsigned long long)s_maxc); s_maxc = 0; }
+#endif
   }
   if (mode == MODE_ENV)
-    for (int slot = wib; slot < E; slot += Wn)
-      if (e0 + slot < W.B && lane == 0 && W.phase[e0 + slot] != B2S_PHASE_IDLE) atomicAdd(W.unfinished, 1);
+    for (int slot = wib; slot < E; slot += Wn) {
+      const int e = W.env_map[e0 + slot];
+      if (e >= 0 && lane == 0 && W.phase[e] != B2S_PHASE_IDLE) atomicAdd(W.unfinished, 1);
+    }
   if (lane == 0 && done_steps) atomicAdd(W.substeps, (unsigned long long)done_steps);
 }
 
@@ -1820,6 +1905,7 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
     cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
+  b2s_launch_assign_envs(W, mode, s);
   cudaMemcpyToSymbolAsync(g_W, &W, sizeof(DWorld), 0, cudaMemcpyHostToDevice, s);
   k_substeps<<<blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps);
 }

@@ -108,6 +108,38 @@ def test_push_action_phase_machine_bit_exact():
     assert (moved > 0.02).sum() >= 8, moved
 
 
+def test_stacked_movables_couple_dynamic_bodies_bit_exact():
+    """Movables piled on each other: contacts between two DYNAMIC bodies (both lanes of the body-centric
+    solve exchange velocities), checked every 25 substeps while the pile collapses and settles."""
+    _, gpu, cpu = helpers.make_pair(32)
+    gpu.reset(seed=7); cpu.reset(seed=7)
+    gpu.settle(0.1, 0.1, 500); cpu.settle(0.1, 0.1, 500)
+    st = np.array(cpu.body_state)                      # [13][B][Nmax]
+    nm = cpu.array('num_movables')
+    rs = np.random.RandomState(3)
+    for e in range(32):
+        for i in range(1, int(nm[e])):                 # body i goes 6 cm above body i-1, slightly off centre
+            st[0:2, e, i] = st[0:2, e, 0] + rs.uniform(-0.015, 0.015, size=2)
+            st[2, e, i] = st[2, e, 0] + 0.06 * i
+            st[7:13, e, i] = 0.0
+    cpu.body_state[...] = st
+    gpu.body_state.copy_(torch.from_numpy(st))
+    coupled = 0
+    for k in range(16):
+        gpu.step(25); cpu.step(25)
+        _compare_state(gpu, cpu, 'pile after %d substeps' % (25 * (k + 1)))
+        _compare_contacts(gpu, cpu, 'pile after %d substeps' % (25 * (k + 1)))
+        keys = cpu.array(_capi.ARR_MANIFOLD_KEYS).reshape(32, -1)
+        slots = cpu.array(_capi.ARR_COL_SLOT).reshape(32, -1)
+        first_movable = gpu.params.max_colliders - gpu.params.max_movables     # one hull per movable in this config
+        for e in range(32):
+            for key in keys[e][keys[e] >= 0]:
+                if (key >> 16) >= first_movable and (key & 0xffff) >= first_movable:
+                    coupled += 1
+        del slots
+    assert coupled > 100, coupled
+
+
 def test_ik_fk_bit_exact():
     cfg, gpu, cpu = helpers.make_pair(16)
     gpu.reset(seed=0); cpu.reset(seed=0)

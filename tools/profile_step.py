@@ -24,6 +24,8 @@ w.set_action()
 if skip:
     w.env_substeps(skip)          # get every arm into the pre/start/motion phases
 torch.cuda.synchronize()
+w.array(24).zero_()
+torch.cuda.synchronize()
 t = []
 for i in range(launches):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -40,3 +42,16 @@ print('ms per launch', [round(a.elapsed_time(b), 3) for a, b in t])
 st = w.array(18).view(envs, 4).cpu().numpy()
 print('mean rows %.1f colours %.2f iters %.1f contacts %.1f' % tuple(st.mean(axis=0)))
 print('pairs mean %.2f manifolds mean %.2f' % (w.array(5).float().mean().item(), w.array(3).float().mean().item()))
+prof = w.array(24).cpu().numpy().astype(float)
+if prof[6] > 0:
+    blocks = (envs + w.params.reserved_i[0] - 1) // w.params.reserved_i[0] if w.params.reserved_i[0] else 147
+    r = prof[6]
+    print('stage ns per round (block mean): A %.0f B %.0f C %.0f | warp-busy fraction A %.2f B %.2f C %.2f | longest env in C %.0f' % (
+        prof[0] / r, prof[1] / r, prof[2] / r, prof[3] / (16 * prof[0]), prof[4] / (16 * prof[1]), prof[5] / (16 * prof[2]), prof[7] / r))
+    pb = prof[8:8 + 4 * 1024].reshape(1024, 4)
+    pb = pb[pb[:, 3] > 0]
+    tot = pb[:, :3].sum(axis=1) / 1e6
+    order = np.argsort(tot)
+    print('blocks %d: total ms min %.1f median %.1f max %.1f' % (len(pb), tot.min(), np.median(tot), tot.max()))
+    for i in list(order[:2]) + list(order[-4:]):
+        print('  block %4d  A %.1f B %.1f C %.1f ms  rounds %d' % (i, pb[i, 0] / 1e6, pb[i, 1] / 1e6, pb[i, 2] / 1e6, pb[i, 3]))
