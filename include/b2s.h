@@ -233,7 +233,8 @@ enum {
   B2S_ARR_PROF = 24,           /* uint64 [8] stage timing of the substep kernel (ns; tuning builds only) */
   B2S_ARR_COUNT = 25
 };
-#define B2S_CP_FLOATS 16   /* localA3 localB3 normalB3 dist lambda_n lambda_t1 lambda_t2 t1x t1y t1z */
+#define B2S_CP_FLOATS 16   /* localA3 localB3 normalB3 dist lambda_n lambda_t1 lambda_t2, then 3 spare words: in point 0 of a
+                              manifold they hold the GJK simplex of the pair's last call (int n, (ia | ib << 8) x 4) */
 #define B2S_CTRL_FLOATS 40
 
 typedef struct B2SWorld B2SWorld;

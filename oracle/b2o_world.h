@@ -130,7 +130,7 @@ void substep(World& w, int e);
 int support(const World& w, const ColX& c, V3 d, V3* p);
 /* narrow phase of one pair; returns 1 and fills the contact when distance < threshold */
 int collide_pair(const World& w, const ColX& A, const ColX& B, float threshold,
-                 V3* pA, V3* pB, V3* normal, float* distance);
+                 V3* pA, V3* pB, V3* normal, float* distance, int32_t* cache);
 
 /* ---- arm (b2o_arm.cpp) ---- */
 void arm_fk(const World& w, const float* q, const float* qd, float* link_poses /*[L+1][7]*/,

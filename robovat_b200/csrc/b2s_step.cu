@@ -71,6 +71,22 @@ extern __shared__ float b2s_smem[];
 __constant__ DWorld g_W;
 #define W g_W
 
+// Stage timing for tuning (compiled only with -DB2S_PROF; see tools/profile_step.py): W.prof[0..2] = duration of
+// stage A/B/C summed over blocks and rounds (thread 0, barrier to barrier), [3..5] = busy time of the warps inside
+// the stage summed over warps, [6] = rounds, [7] = longest single environment of stage C summed over rounds.
+#ifdef B2S_PROF
+__device__ __forceinline__ long long prof_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; }
+#define PROF_STAGE(i) { const long long now_ = prof_now(); if (lane == 0) atomicAdd(W.prof + 3 + (i), (unsigned long long)(now_ - pstart_)); }
+#define PROF_MARK(i) { const long long now_ = prof_now(); if (threadIdx.x == 0) { atomicAdd(W.prof + (i), (unsigned long long)(now_ - pstart_)); W.prof[8 + blockIdx.x * 4 + (i)] += (unsigned long long)(now_ - pstart_); } pstart_ = now_; }
+#define PROF_SEC(i) { const long long now_ = prof_now(); if (lane == 0) atomicAdd(W.prof + 8 + 4096 + (i), (unsigned long long)(now_ - psec_)); psec_ = now_; }
+#define PROF_SEC0() long long psec_ = prof_now();
+#else
+#define PROF_STAGE(i)
+#define PROF_MARK(i)
+#define PROF_SEC(i)
+#define PROF_SEC0()
+#endif
+
 struct Xf { V3 p; Q4 q; };
 __device__ __forceinline__ Xf xf_from(const float* a) { Xf t; t.p = v3(a[0], a[1], a[2]); t.q = q4(a[3], a[4], a[5], a[6]); return t; }
 __device__ __forceinline__ Xf xf_mul(Xf a, Xf b) { Xf t; t.p = a.p + qrot(a.q, b.p); t.q = qmul(a.q, b.q); return t; }
@@ -454,6 +470,17 @@ __device__ __noinline__ void closest_simplex_dev(const V3* w, int n, b2s_simplex
 // The simplex lives in shared memory in PHYSICAL slots that never move; `perm` (2 bits per entry) maps
 // the logical order (= the oracle's compacted order) to physical slots and `ids` packs (ia | ib << 8)
 // of the logical entries, so the duplicate test and the compaction are register-only integer work.
+// world position of hull vertex i (the point `support` returns for that index)
+__device__ __forceinline__ V3 vertex_world(const ColRef& c, int i) {
+  const float4 v = __ldg(W.verts + c.voff + i);
+  return cr_pos(c) + mmul(cr_R(c), v3(v.x, v.y, v.z) * c.scale);
+}
+
+// sx[SX_CACHE..+2] (in/out): the simplex of the pair's previous call as vertex indices -- n, then (ia | ib << 8) of
+// the entries 0,1 and 2,3 packed 16 bits each.  Like Bullet's cached separating axis it warm-starts the descent: a
+// resting pair confirms its closest features with one support query instead of rebuilding them (4.9 -> ~1.5
+// iterations per pair on the bench scene).  n = 0: cold start.  (oracle/b2o_physics.cpp gjk)
+#define SX_CACHE 45
 __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float limit, float* sx, V3* v_out, V3* pa,
                    V3* pb, int lane) {
   const ColRef A = A_in, B = B_in;      // register copies: the references point into the caller's local memory
@@ -465,33 +492,56 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
   bool have = false;
   float bary0 = 0, bary1 = 0, bary2 = 0, bary3 = 0;
   int status = 1;
-  for (int it = 0; it < W.P.gjk_max_iters; ++it) {
-    V3 a, b;
-    int ia = support(A, -v, &a, lane);
-    int ib = support(B, v, &b, lane);
-    V3 ww = a - b;
-    float vv = dot(v, v), vw = dot(v, ww);
-    if (vw > 0.0f && vw * vw > (limit * limit) * vv) return 0;
-    const unsigned id = (unsigned)ia | ((unsigned)ib << 8);
-    bool dup = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) if (k < n && (unsigned)((ids >> (16 * k)) & 0xffffu) == id) dup = true;
-    if (dup) break;
-    if (have && (vv - vw) <= vv * 1e-6f) break;
-    // lowest free physical slot
-    unsigned usedp = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) if (k < n) usedp |= 1u << ((perm >> (2 * k)) & 3u);
-    const int ps = __ffs(~usedp) - 1;
+  __syncwarp();
+  const int cn = __float_as_int(sx[SX_CACHE]);
+  bool warm = cn > 0;
+  if (warm) {
+    ids = (unsigned long long)(unsigned)__float_as_int(sx[SX_CACHE + 1]) | ((unsigned long long)(unsigned)__float_as_int(sx[SX_CACHE + 2]) << 32);
     __syncwarp();
-    if (lane == 0) {
-      ST3(sx + SX_W + ps * 3, ww); ST3(sx + SX_A + ps * 3, a); ST3(sx + SX_B + ps * 3, b);
-      sx[SX_IA + ps] = __int_as_float(ia); sx[SX_IB + ps] = __int_as_float(ib);
+    if (lane < cn) {
+      const unsigned id = (unsigned)((ids >> (16 * lane)) & 0xffffull);
+      const int ia = (int)(id & 255u), ib = (int)(id >> 8);
+      const V3 a = vertex_world(A, ia), b = vertex_world(B, ib);
+      ST3(sx + SX_W + lane * 3, a - b); ST3(sx + SX_A + lane * 3, a); ST3(sx + SX_B + lane * 3, b);
+      sx[SX_IA + lane] = __int_as_float(ia); sx[SX_IB + lane] = __int_as_float(ib);
     }
-    __syncwarp();
-    perm = (perm & ~(3u << (2 * n))) | ((unsigned)ps << (2 * n));
-    ids = (ids & ~(0xffffull << (16 * n))) | ((unsigned long long)id << (16 * n));
-    n = n + 1;
+    n = cn;
+    perm = 0xE4u;                        // logical entry k in physical slot k
+  }
+  __syncwarp();
+  if (lane == 0) { sx[SX_CACHE] = __int_as_float(0); sx[SX_CACHE + 1] = __int_as_float(0); sx[SX_CACHE + 2] = __int_as_float(0); }
+  __syncwarp();
+  for (int it = 0; it < W.P.gjk_max_iters; ++it) {
+    float vv = 0.0f;
+    if (!warm) {
+      V3 a, b;
+      int ia = support(A, -v, &a, lane);
+      int ib = support(B, v, &b, lane);
+      V3 ww = a - b;
+      vv = dot(v, v);
+      const float vw = dot(v, ww);
+      if (vw > 0.0f && vw * vw > (limit * limit) * vv) return 0;
+      const unsigned id = (unsigned)ia | ((unsigned)ib << 8);
+      bool dup = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (k < n && (unsigned)((ids >> (16 * k)) & 0xffffu) == id) dup = true;
+      if (dup) break;
+      if (have && (vv - vw) <= vv * 1e-6f) break;
+      // lowest free physical slot
+      unsigned usedp = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (k < n) usedp |= 1u << ((perm >> (2 * k)) & 3u);
+      const int ps = __ffs(~usedp) - 1;
+      __syncwarp();
+      if (lane == 0) {
+        ST3(sx + SX_W + ps * 3, ww); ST3(sx + SX_A + ps * 3, a); ST3(sx + SX_B + ps * 3, b);
+        sx[SX_IA + ps] = __int_as_float(ia); sx[SX_IB + ps] = __int_as_float(ib);
+      }
+      __syncwarp();
+      perm = (perm & ~(3u << (2 * n))) | ((unsigned)ps << (2 * n));
+      ids = (ids & ~(0xffffull << (16 * n))) | ((unsigned long long)id << (16 * n));
+      n = n + 1;
+    }
     V3 wl[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) wl[k] = LD3(sx + SX_W + ((perm >> (2 * k)) & 3u) * 3);
@@ -516,9 +566,10 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
     bary0 = nb0; bary1 = nb1; bary2 = nb2; bary3 = nb3;
     float nv = len2(r.v);
     if (nv < 1e-14f) { status = 2; break; }
-    if (have && nv >= vv) { v = r.v; break; }
+    if (!warm && have && nv >= vv) { v = r.v; break; }
     v = r.v;
     have = true;
+    if (warm) { warm = false; --it; }    // the warm start is not one of the gjk_max_iters iterations
   }
   if (status == 2) {
     // EPA wants the simplex in logical order at slots 0..n-1
@@ -552,6 +603,13 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
     }
   }
   *pa = xa; *pb = xb; *v_out = v;
+  __syncwarp();
+  if (lane == 0) {
+    sx[SX_CACHE] = __int_as_float(n);
+    sx[SX_CACHE + 1] = __int_as_float((int)(unsigned)(ids & 0xffffffffull));
+    sx[SX_CACHE + 2] = __int_as_float((int)(unsigned)(ids >> 32));
+  }
+  __syncwarp();
   return 1;
 }
 
@@ -808,6 +866,7 @@ __device__ __noinline__ int stage_scene(int e, int lane, int wib) {
   const float dt = (float)P.time_step;
   const int Ns = W.Ns, L = W.L, NB = W.NB, Nmax = W.Nmax;
   const int nm = W.buf.num_movables[e];
+  PROF_SEC0()
 
   stage_arm(e, lane, wib);
   {
@@ -816,6 +875,7 @@ __device__ __noinline__ int stage_scene(int e, int lane, int wib) {
     for (int j = 0; j < 7; ++j) { q[j] = W.buf.joint_state[(0 * 7 + j) * W.B + e]; qd[j] = W.buf.joint_state[(1 * 7 + j) * W.B + e]; }
     arm_fk_links(e, lane, q, qd, wib);
   }
+  PROF_SEC(8)
   // body table: statics + movables (links were written by arm_fk_links)
   const V3 g = v3(P.gravity[0], P.gravity[1], P.gravity[2]);
   const float ld = fmaxf(0.0f, 1.0f - P.linear_damping * dt), ad = fmaxf(0.0f, 1.0f - P.angular_damping * dt);
@@ -872,6 +932,7 @@ __device__ __noinline__ int stage_scene(int e, int lane, int wib) {
   }
   __syncwarp();
 
+  PROF_SEC(9)
   // colliders + AABBs (one collider per lane)
   const int nc = W.ncol[e];
   int first_dyn = nc, arm0 = nc, arm1 = 0;
@@ -908,6 +969,7 @@ __device__ __noinline__ int stage_scene(int e, int lane, int wib) {
   }
   __syncwarp();
 
+  PROF_SEC(10)
   // broad phase: sorted pair keys, ballot compaction keeps the sequential order
   int np = 0;
   bool pair_over = false;
@@ -955,6 +1017,7 @@ __device__ __noinline__ int stage_scene(int e, int lane, int wib) {
   for (int p = lane; p < np; p += 32) W.pair_keys[(size_t)e * P.max_pairs + p] = S.pairs[p];
   if (lane == 0) { W.num_pairs[e] = np; if (pair_over) W.error_flags[e] |= 1; }
   __syncwarp();
+  PROF_SEC(11)
   (void)Nmax;
   return np;
 }
@@ -974,6 +1037,7 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
   int newn = 0, ncon = 0, cflags = 0;
   bool man_over = false, con_over = false;
   float* stg = S.stage;   // [4][16]
+  PROF_SEC0()
   float* epa_scr = W.epa_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * EP_WORDS;
   for (int p = 0; p < np; ++p) {
     const int key = S.pairs[p];
@@ -992,8 +1056,10 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
     if (found != 0x7fffffff) {
       n = W.man_npts[obase + found];
       const float* src = W.man_pts + (obase + found) * 4 * B2S_CP_FLOATS;
-      stg[lane] = src[lane]; stg[lane + 32] = src[lane + 32];
-    }
+      const float s0 = src[lane];
+      stg[lane] = s0; stg[lane + 32] = src[lane + 32];
+      if (lane >= 13 && lane < 16) S.sx[SX_CACHE + lane - 13] = s0;      // GJK simplex of the previous substep
+    } else if (lane < 3) S.sx[SX_CACHE + lane] = __int_as_float(0);
     __syncwarp();
     // refresh (one point per lane), compaction keeps the order
     {
@@ -1022,9 +1088,12 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
       n = __popc(km);
       __syncwarp();
     }
+    PROF_SEC(4)
     V3 pA, pB, nrm;
     float dist;
-    if (collide_pair(A, Bc, threshold, S.sx, epa_scr, &pA, &pB, &nrm, &dist, lane)) {
+    const int hit_ = collide_pair(A, Bc, threshold, S.sx, epa_scr, &pA, &pB, &nrm, &dist, lane);
+    PROF_SEC(5)
+    if (hit_) {
       V3 lA = mtmul(cr_R(A), pA - cr_pos(A));
       V3 lB = mtmul(cr_R(Bc), pB - cr_pos(Bc));
       // manifold_add (uniform decisions, lane 0 writes)
@@ -1057,7 +1126,7 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
     if (n > 0) {
       if (newn < M) {
         float* dst = W.man_pts + (nbase + newn) * 4 * B2S_CP_FLOATS;
-        dst[lane] = (lane < n * B2S_CP_FLOATS) ? stg[lane] : 0.0f;
+        dst[lane] = (lane >= 13 && lane < 16) ? S.sx[SX_CACHE + lane - 13] : ((lane < n * B2S_CP_FLOATS) ? stg[lane] : 0.0f);
         dst[lane + 32] = (lane + 32 < n * B2S_CP_FLOATS) ? stg[lane + 32] : 0.0f;
         if (lane == 0) { W.man_keys[nbase + newn] = key; W.man_npts[nbase + newn] = n; }
         const int tA = __float_as_int(ca[CO_TYPE]) & 255, tfB = __float_as_int(cb[CO_TYPE]);
@@ -1072,6 +1141,7 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
       } else man_over = true;
     }
     (void)sA; (void)sB;
+    PROF_SEC(6)
   }
   __syncwarp();
   for (int k = newn + lane; k < M; k += 32) { W.man_keys[nbase + k] = -1; W.man_npts[nbase + k] = 0; }
@@ -1137,6 +1207,7 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
     cn[CN_INVMB] = (__float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC) ? imB : 0.0f;
   }
   __syncwarp();
+  PROF_SEC(7)
   *nc_out = ncon;
   *newn_out = newn;
 }
@@ -1341,6 +1412,7 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   const int nrows = 1 + P.friction_dirs;
   const bool act = lane < C;
   float* rr = W.row_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * (32 * RR_WORDS);
+  PROF_SEC0()
   unsigned char* T = (unsigned char*)S.con;
   float* lam = S.con + SOLVE_LAM;
   int sA = 0, sB = 0, mk = 0;
@@ -1397,6 +1469,7 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       }
     }
   }
+  PROF_SEC(0)
   // greedy colouring in contact order; lane s keeps the colour mask of body slot s
   unsigned long long used = 0ull;
   int mycol = -1, ncolours = 0;
@@ -1524,23 +1597,33 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   // (pass 2).  The fast step is specialised per pass; the coupled step takes the pass at run time.
   // (Measured alternatives, all slower: one flattened row-step loop with run-time row selects, 1.5x; software
   // pipelining of the operand loads across colour steps, 1.3x -- the compiler keeps this loop tight as it is.)
+  // Two instances of the sweep: environments without a coupled colour (the rule) run loops that contain the
+  // fast step only -- ~200 instructions that stay in the L0 instruction cache for up to 50 iterations -- the
+  // others run the general loops.
+  PROF_SEC(1)
   float maxres = 0.0f;
   int iters = 0;
-#pragma unroll 1
-  for (int k = 0; k < ncolours; ++k) { if ((coupled >> k) & 1ull) { const int pass = 0; STEP_SLOW(pass) } else STEP_FAST(0) }
-  __syncwarp();
-  for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
-    maxres = 0.0f;
-#pragma unroll 1
-    for (int k = 0; k < ncolours; ++k) { if ((coupled >> k) & 1ull) { const int pass = 1; STEP_SLOW(pass) } else STEP_FAST(1) }
-    __syncwarp();
-#pragma unroll 1
-    for (int k = 0; k < ncolours; ++k) { if ((coupled >> k) & 1ull) { const int pass = 2; STEP_SLOW(pass) } else STEP_FAST(2) }
-    __syncwarp();
-    iters = it + 1;
-    unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
-    if (__uint_as_float(mx) <= P.residual_threshold) break;
+#define SWEEP(GENERAL)                                                                                            \
+  {                                                                                                               \
+    _Pragma("unroll 1")                                                                                           \
+    for (int k = 0; k < ncolours; ++k) { if (GENERAL && ((coupled >> k) & 1ull)) { const int pass = 0; STEP_SLOW(pass) } else STEP_FAST(0) } \
+    __syncwarp();                                                                                                 \
+    for (int it = 0; it < P.solver_iterations && C > 0; ++it) {                                                   \
+      maxres = 0.0f;                                                                                              \
+      _Pragma("unroll 1")                                                                                         \
+      for (int k = 0; k < ncolours; ++k) { if (GENERAL && ((coupled >> k) & 1ull)) { const int pass = 1; STEP_SLOW(pass) } else STEP_FAST(1) } \
+      __syncwarp();                                                                                               \
+      _Pragma("unroll 1")                                                                                         \
+      for (int k = 0; k < ncolours; ++k) { if (GENERAL && ((coupled >> k) & 1ull)) { const int pass = 2; STEP_SLOW(pass) } else STEP_FAST(2) } \
+      __syncwarp();                                                                                               \
+      iters = it + 1;                                                                                             \
+      unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));                                             \
+      if (__uint_as_float(mx) <= P.residual_threshold) break;                                                     \
+    }                                                                                                             \
   }
+  if (coupled == 0ull) SWEEP(false) else SWEEP(true)
+  PROF_SEC(2)
+#undef SWEEP
 #undef STEP_FAST
 #undef STEP_SLOW
   if (dyn) {
@@ -1580,6 +1663,7 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   __syncwarp();
   if (lane == 0) W.num_steps[e] += 1;
   __syncwarp();
+  PROF_SEC(3)
   (void)newn;
 }
 
@@ -1720,18 +1804,6 @@ __device__ __noinline__ void finish_action(int e, int lane) {
 }
 
 // ----------------------------------------------------------- the kernel -----
-
-// Stage timing for tuning (compiled only with -DB2S_PROF; see tools/profile_step.py): W.prof[0..2] = duration of
-// stage A/B/C summed over blocks and rounds (thread 0, barrier to barrier), [3..5] = busy time of the warps inside
-// the stage summed over warps, [6] = rounds, [7] = longest single environment of stage C summed over rounds.
-#ifdef B2S_PROF
-__device__ __forceinline__ long long prof_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; }
-#define PROF_STAGE(i) { const long long now_ = prof_now(); if (lane == 0) atomicAdd(W.prof + 3 + (i), (unsigned long long)(now_ - pstart_)); }
-#define PROF_MARK(i) { const long long now_ = prof_now(); if (threadIdx.x == 0) { atomicAdd(W.prof + (i), (unsigned long long)(now_ - pstart_)); W.prof[8 + blockIdx.x * 4 + (i)] += (unsigned long long)(now_ - pstart_); } pstart_ = now_; }
-#else
-#define PROF_STAGE(i)
-#define PROF_MARK(i)
-#endif
 
 // Hand-out of environments inside a stage: dynamic (shared counter) when the solver rows live in registers;
 // with rows in per-warp shared memory an environment must stay with one warp for the whole substep.

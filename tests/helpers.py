@@ -28,14 +28,16 @@ def make_pair(num_envs, with_camera=False, **bindings):
 
 
 def manifold_view(keys, npts, pts, B, M):
-    """Canonical comparable form: (keys, npts, points masked to the live entries)."""
+    """Canonical comparable form: (keys, npts, points masked to the live entries, GJK simplex cache words)."""
     keys = np.asarray(keys).reshape(B, M).copy()
     npts = np.asarray(npts).reshape(B, M).copy()
     pts = np.asarray(pts).reshape(B, M, 4, _capi.CP_FLOATS).copy()
     live = np.arange(4)[None, None, :] < npts[:, :, None]
     pts[~live] = 0
+    cache = np.ascontiguousarray(pts[:, :, 0, 13:16]).view(np.uint32).copy()     # n, (ia | ib << 8) x 4 (include/b2s.h)
+    cache[npts == 0] = 0
     pts[..., 13:] = 0
-    return keys, npts, pts
+    return keys, npts, pts, cache
 
 
 def bits(a):

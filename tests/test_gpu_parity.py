@@ -35,6 +35,7 @@ def _compare_contacts(gpu, cpu, what):
     np.testing.assert_array_equal(gk[0], ck[0], err_msg=what + ': manifold keys')
     np.testing.assert_array_equal(gk[1], ck[1], err_msg=what + ': manifold npts')
     helpers.assert_bits_equal(gk[2], ck[2], what + ': manifold points')
+    np.testing.assert_array_equal(gk[3], ck[3], err_msg=what + ': GJK simplex cache')
     np.testing.assert_array_equal(gpu.array(_capi.ARR_CONTACT_FLAGS).cpu().numpy(), cpu.array(_capi.ARR_CONTACT_FLAGS))
     np.testing.assert_array_equal(gpu.array(_capi.ARR_SOLVER_STATS).cpu().numpy(), cpu.array(_capi.ARR_SOLVER_STATS))
     np.testing.assert_array_equal(gpu.array(_capi.ARR_ERROR_FLAGS).cpu().numpy(), cpu.array(_capi.ARR_ERROR_FLAGS))

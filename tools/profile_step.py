@@ -55,3 +55,6 @@ if prof[6] > 0:
     print('blocks %d: total ms min %.1f median %.1f max %.1f' % (len(pb), tot.min(), np.median(tot), tot.max()))
     for i in list(order[:2]) + list(order[-4:]):
         print('  block %4d  A %.1f B %.1f C %.1f ms  rounds %d' % (i, pb[i, 0] / 1e6, pb[i, 1] / 1e6, pb[i, 2] / 1e6, pb[i, 3]))
+    sec = prof[8 + 4096:8 + 4096 + 12] / 1e6
+    names = ['C rows', 'C colour', 'C sweeps', 'C integrate', 'B lookup/refresh', 'B collide', 'B manifold', 'B tail', 'A arm+fk', 'A bodies', 'A colliders', 'A broad']
+    print('warp-ms by section: ' + ', '.join('%s %.0f' % (n, v) for n, v in zip(names, sec)))

@@ -1,1 +1,1 @@
-B2S_LIB=$PWD/robovat_b200/csrc/variants/libb2s_prof.so timeout -s KILL 200 python tools/profile_step.py 4096 100 4 600 2>&1 | tail -14
+B2S_LIB=$PWD/robovat_b200/csrc/variants/libb2s_prof.so timeout -s KILL 200 python tools/profile_step.py 4096 100 4 600 2>&1 | tail -16
