@@ -11,6 +11,8 @@ Everything written here is an OUTPUT OF THE REFERENCE'S OWN CODE:
   reward.json           robovat.reward_fns.push_reward.get_reward_fn(task, layout)(state, next_state)
   sampler.json          robovat.envs.push.heuristic_push_sampler.HeuristicPushSampler.sample
   camera.json           robovat.perception.camera.camera.Camera + bullet_camera.intrinsic_to_projection_matrix
+  mesh.json             robovat.utils.mesh_utils (OBJ reader, volume / area / centroid), the URDF text written from
+                        tools/templates/*.xml and tools/convert_obj_to_urdf.split_wrl_file
   waypoints.json        robovat.envs.push.push_env.PushEnv._compute_waypoints
   push_step_trace.npz   the reference PushEnv.step() (its own _execute_action, SawyerSim, ControllableBody,
                         Simulator.wait_until_stable) driving OUR physics backend substep by substep
@@ -205,6 +207,93 @@ def push_body0(dx, dy):
     return fn
 
 
+OBJ_SAMPLE = '''# comment line
+v 0 0 0
+v 1 0 0
+v 0 1 0
+
+v 0 0 1
+vt 0.5 0.5
+vn 0 0 1
+f 1/1/1 3/1/1 2/1/1
+f 1//1 2//1 4//1
+f 2 3 4
+f 1 4 3
+bogus line
+'''
+
+WRL_SAMPLE = '''#VRML V2.0 utf8
+Group {
+ children [
+  Shape { geometry IndexedFaceSet { coord Coordinate { point [
+   0 0 0,
+   1 0 0,
+   0 1 0,
+   0 0 1,
+  ] } coordIndex [ 0, 2, 1, -1, 0, 1, 3, -1, 1, 2, 3, -1, 0, 3, 2, -1, ] } }
+ ]
+}
+#VRML V2.0 utf8
+Group {
+ children [
+  Shape { geometry IndexedFaceSet { coord Coordinate { point [
+   2 0 0,
+   3 0 0,
+   2 1 0,
+   2 0 1,
+  ] } coordIndex [ 0, 2, 1, -1, 0, 1, 3, -1, 1, 2, 3, -1, 0, 3, 2, -1, ] } }
+ ]
+}
+'''
+
+
+def gen_mesh():
+    """Reference mesh_utils on the committed OBJ sources + a hand-written OBJ with v/vt/vn faces; URDF template text."""
+    import importlib.util
+    import tempfile
+    from robovat.utils import mesh_utils
+    out = {'objs': {}}
+    data = os.path.join(ROOT, 'robovat_b200', 'data', 'urdf')
+    paths = {name: os.path.join(data, name, name + '.obj') for name in sorted(os.listdir(data))}
+    tmp = tempfile.mkdtemp()
+    sample = os.path.join(tmp, 'sample.obj')
+    with open(sample, 'w') as f:
+        f.write(OBJ_SAMPLE)
+    paths['sample'] = sample
+    for name, path in paths.items():
+        v, t = mesh_utils.read_from_obj(path)
+        out['objs'][name] = {'text': open(path).read(), 'vertices': _tolist(v), 'triangles': np.asarray(t).tolist(),
+                             'volume': float(mesh_utils.compute_volume(v, t)),
+                             'surface_area': float(mesh_utils.compute_surface_area(v, t)),
+                             'centroid': _tolist(mesh_utils.compute_centroid(v, t))}
+    tdir = os.path.join('/root/reference', 'tools', 'templates')
+    visual = open(os.path.join(tdir, 'visual_template.xml')).read()
+    collision = open(os.path.join(tdir, 'collision_template.xml')).read()
+    urdf = open(os.path.join(tdir, 'urdf_template.xml')).read()
+    cases = []
+    for body_name, files, mass, c, scale, rgba in (
+            ('L', ['L_vhacd_0_of_2.obj', 'L_vhacd_1_of_2.obj'], 0.1, [-0.0165432, -0.00654321, 1.2e-9], 1.0, '0.50 0.50 0.50 1.00'),
+            ('thing', ['thing_vhacd_0_of_1.obj'], 0.25, [0.0, 1e-7, -123.456], 0.75, '0.12 0.34 0.56 1.00')):
+        vt = ''.join(visual.format(filename=fn, scale=scale) for fn in files)
+        ct = ''.join(collision.format(filename=fn, scale=scale) for fn in files)
+        text = urdf.format(body_name=body_name, mass=mass, ixx=1, iyy=1, izz=1, ixy=0, ixz=0, iyz=0, cx=c[0], cy=c[1], cz=c[2],
+                           visual=vt, collision=ct, rgba=rgba)
+        cases.append({'body_name': body_name, 'files': files, 'mass': mass, 'centroid': c, 'scale': scale, 'rgba': rgba, 'text': text})
+    out['urdf'] = cases
+    # split_wrl_file of the reference tool (its module imports only os/argparse/numpy + robovat.utils)
+    import types
+    sys.modules.setdefault('_init_paths', types.ModuleType('_init_paths'))    # tools/_init_paths.py only edits sys.path
+    spec = importlib.util.spec_from_file_location('ref_convert', '/root/reference/tools/convert_obj_to_urdf.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    wrl = os.path.join(tmp, 'output.wrl')
+    with open(wrl, 'w') as f:
+        f.write(WRL_SAMPLE)
+    pieces = [open(p).read() for p in mod.split_wrl_file(wrl, tmp_dir=tmp)]
+    out['wrl'] = {'text': WRL_SAMPLE, 'pieces': pieces, 'groups': mod.count_output_groups(wrl)}
+    return out
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_cosim, ref_shim
@@ -216,6 +305,9 @@ def main():
         with open(os.path.join(OUT, name), 'w') as f:
             json.dump(obj, f)
         print('wrote', name)
+    dump('mesh.json', gen_mesh())
+    if '--only-mesh' in sys.argv:
+        return
     dump('transformations.json', gen_transformations(rs))
     dump('pose.json', gen_pose(rs))
     # robovat.envs.__init__ imports gym-based envs: stub the package objects

@@ -16,6 +16,7 @@ import numpy as np
 from robovat_b200 import _capi
 from robovat_b200 import assets as assets_lib
 from robovat_b200 import layouts as push_layouts
+from robovat_b200 import mesh_io
 
 
 class AttrDict(dict):
@@ -55,6 +56,14 @@ DEFAULT_PUSH_ENV = {
             'PATHS': ['box', 'hex', 'wedge'], 'TARGET_PATHS': ['box'],
             'SCALE': [0.8, 1.2], 'MASS': [0.05, 0.3], 'FRICTION': [0.4, 1.0], 'MARGIN': 0.12,
             # uniform over the obstacle grid of crossing/0 (layouts.py:182-186)
+            'POSE': {'X': [0.37, 0.82], 'Y': [-0.41, 0.49], 'Z': 0.2,
+                     'ROLL': [-math.pi, math.pi], 'PITCH': [-math.pi / 2, math.pi / 2],
+                     'YAW': [-math.pi, math.pi]},
+        },
+        'VHACD': {                     # V-HACD decompositions written by tools/make_vhacd_assets.py (reference bin/vhacd)
+            'PATHS': ['urdf/L/L.urdf', 'urdf/T/T.urdf', 'urdf/U/U.urdf', 'urdf/plus/plus.urdf'],
+            'TARGET_PATHS': ['urdf/L/L.urdf'],
+            'SCALE': [0.8, 1.0], 'MASS': [0.05, 0.3], 'FRICTION': [0.4, 1.0], 'MARGIN': 0.12,
             'POSE': {'X': [0.37, 0.82], 'Y': [-0.41, 0.49], 'Z': 0.2,
                      'ROLL': [-math.pi, math.pi], 'PITCH': [-math.pi / 2, math.pi / 2],
                      'YAW': [-math.pi, math.pi]},
@@ -196,7 +205,14 @@ def build_scene(config):
         shapes.update({'vhacd_' + k: v for k, v in vh.items()})
     ids = {}
     for name in list(mcfg.PATHS) + list(mcfg.TARGET_PATHS):
-        if name not in ids:
+        if name in ids:
+            continue
+        if name.endswith('.urdf'):
+            # a URDF from the reference asset pipeline (tools/convert_obj_to_urdf.py): hulls in the inertial frame
+            path = name if os.path.isabs(name) else os.path.join(assets_lib.DATA_DIR, name)
+            hulls, _ = mesh_io.urdf_asset(path)
+            ids[name] = lib.add_asset(name, hulls, center_on_com=False)
+        else:
             ids[name] = lib.add_asset(name, shapes[name])
     movable_assets = [ids[n] for n in mcfg.PATHS]
     target_assets = [ids[n] for n in mcfg.TARGET_PATHS]

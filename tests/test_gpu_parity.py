@@ -182,6 +182,26 @@ def test_crossing_task_concave_movables_bit_exact():
     np.testing.assert_array_equal(tg.cpu().numpy(), tc)
 
 
+def test_vhacd_urdf_movables_bit_exact():
+    """Movables loaded from the URDF files of the reference asset pipeline (V-HACD hulls, inertial frame = the
+    reference's area-weighted centroid): drop, settle and one push, CUDA == oracle."""
+    cfg, gpu, cpu = helpers.make_pair(16, MOVABLE_NAME='vhacd', MIN_MOVABLE_BODIES=3, MAX_MOVABLE_BODIES=3)
+    gpu.reset(seed=6); cpu.reset(seed=6)
+    for k in range(5):
+        gpu.step(100); cpu.step(100)
+        _compare_state(gpu, cpu, 'vhacd after %d substeps' % (100 * (k + 1)))
+        _compare_contacts(gpu, cpu, 'vhacd after %d substeps' % (100 * (k + 1)))
+    gpu.settle(); cpu.settle()
+    act = np.tile(np.array([0.0, -0.1, 0.7, 0.7], np.float32), (16, 1))
+    gpu.set_action(act); cpu.set_action(act)
+    for _ in range(40):
+        ug, uc = gpu.env_substeps(500), cpu.env_substeps(500)
+        assert ug == uc
+        if uc == 0:
+            break
+    _compare_state(gpu, cpu, 'vhacd after action')
+
+
 def test_render_and_point_cloud_bit_exact():
     """BASELINE config #4 shape: 128x128 depth + segmentation, then the segmented point cloud."""
     from robovat_b200 import config as config_lib
