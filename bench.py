@@ -115,6 +115,15 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic():
+    """DRAM bytes per env-substep of k_substeps from the committed ncu --set full capture (None when absent)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_k_substeps_dram_traffic.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['dram_bytes_per_env_substep'])
+    return None
+
+
 def run_cpu_sample(cfg, threads, target_seconds, seed):
     """Oracle port on the host cores over a bounded sample of the same workload."""
     from oracle import b2o
@@ -305,6 +314,8 @@ def main():
     value = total_substeps / (ms * 1e-3)
     peak, peak_src = measured_peak()
     achieved = (substeps * ALGO_BYTES_PER_SUBSTEP) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    per_launch = substeps / float(max(1, n_kernel_launches))          # env-substeps one launch processes on this rank
+    traffic = measured_traffic()
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world_size, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -315,7 +326,9 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'kernel': 'k_substeps', 'launches': n_kernel_launches,
+                     'traffic': traffic * per_launch if traffic else None, 'traffic_unit': 'bytes per launch (ncu dram read+write)',
+                     'algorithmic_bytes_per_launch': ALGO_BYTES_PER_SUBSTEP * per_launch, 'env_substeps_per_launch': per_launch,
+                     'kernel': 'k_substeps', 'launches': n_kernel_launches,
                      'avg_launch_ms': kernel_ms / max(1, n_kernel_launches), 'kernel_share_of_step': kernel_ms / ms if ms > 0 else None,
                      'algorithmic_bytes_per_substep': ALGO_BYTES_PER_SUBSTEP, 'peak_source': peak_src,
                      'note': 'state is shared-memory/L2 resident by design: the kernel is latency/issue bound, not HBM bound (DESIGN.md)'},

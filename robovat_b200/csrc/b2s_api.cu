@@ -308,7 +308,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     int E;
     if (P.reserved_i[0] > 0) E = P.reserved_i[0];
     else {
-      // fill whole waves of SMs (one block per SM): B = 4096 -> E = 28 -> 147 blocks
+      // fill whole waves of SMs (one block per SM): B = 4096 -> 28 per block -> 147 blocks
       int dev_sms = 148;
       cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, w->device);
       const int waves = (d.B + dev_sms * maxE - 1) / (dev_sms * maxE);
@@ -317,8 +317,12 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     if (!d.reg_rows) E = wpb;
     if (E < 1) E = 1;
     if (E > maxE) E = maxE;
+    d.num_blocks = (d.B + E - 1) / E;
+    // spare slots: the deal (k_assign_envs) gives the blocks that hold the expensive environments at most one
+    // environment per warp and lets the cheap blocks take the rest
+    if (d.reg_rows && P.reserved_i[0] <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7));
     d.envs_per_block = E;
-    const size_t blocks = (d.B + E - 1) / E;
+    const size_t blocks = d.num_blocks;
     if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
     if ((rc = dalloc(w, &d.env_map, blocks * (size_t)E, 0xff))) return rc;
     if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)(32 * 68), 0))) return rc;

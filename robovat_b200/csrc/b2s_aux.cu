@@ -382,14 +382,20 @@ __global__ void k_rebuild_colliders(const __grid_constant__ DWorld W) {
 
 // Deals the environments to the blocks of the substep kernel before every launch.  The cost of an environment is
 // persistent over hundreds of substeps (a pushed body needs 20-50 solver iterations per substep, a resting one
-// 3-6; an idle environment none), and a launch lasts as long as its slowest block, so the environments are ranked
-// by the solver work of their last substep (iterations x colours, counting sort) and dealt round-robin: every
-// block gets the same share of expensive environments.  Results do not depend on the deal (environments never
-// interact); with contiguous blocks the slowest block of a mid-push launch took 1.3x the median.
+// 3-6; an idle environment none), the solve of one environment is a sequential chain, and a block advances in
+// lock-step rounds, so a round lasts as long as the block's slowest solve.  The environments are ranked by the
+// solver work of their last substep (iterations x colours, counting sort); the expensive ones are concentrated
+// in a few blocks that get at most one environment per warp (one wave per stage, and all of its solves are
+// equally long, so nobody waits), the cheap ones are dealt round-robin over the remaining blocks, which take
+// two waves per stage but never wait for a 50-iteration solve.  Results do not depend on the deal
+// (environments never interact).  Measured on the mid-push workload: contiguous blocks 1.0, cost-ranked
+// round-robin over all blocks 1.0, this two-class deal see DESIGN.md section 5.
+#define HEAVY_KEY 60       // iterations x colours of the last substep from which an environment counts as expensive
 __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DWorld W, int mode, int nblocks) {
   __shared__ int hist[256];
   __shared__ int base[256];
-  const int E = W.envs_per_block;
+  __shared__ int s_heavy;
+  const int E = W.envs_per_block, Wn = W.P.warps_per_block;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
   for (int i = threadIdx.x; i < nblocks * E; i += blockDim.x) W.env_map[i] = -1;
   __syncthreads();
@@ -400,14 +406,29 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
     atomicAdd(&hist[255 - key], 1);                 // bin 0 = most expensive
   }
   __syncthreads();
-  if (threadIdx.x == 0) { int acc = 0; for (int i = 0; i < 256; ++i) { base[i] = acc; acc += hist[i]; } }
+  if (threadIdx.x == 0) {
+    int acc = 0, heavy = 0;
+    for (int i = 0; i < 256; ++i) { base[i] = acc; acc += hist[i]; if (255 - i >= HEAVY_KEY) heavy = acc; }
+    s_heavy = heavy;
+  }
   __syncthreads();
+  // blocks of the expensive class: one environment per warp; bounded by what the other blocks can still take
+  int Hb = 0;
+  if (E > Wn && nblocks > 1) {
+    const int hb_max = (nblocks * E - W.B) / (E - Wn);
+    Hb = min(min((s_heavy + Wn - 1) / Wn, hb_max), nblocks - 1);
+    if (Hb < 0) Hb = 0;
+  }
+  const int hcap = Hb * Wn, Lb = nblocks - Hb;
   for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
     const int32_t* st = W.solver_stats + (size_t)e * 4;
     int key = 1 + min(254, st[1] * st[2]);
     if (mode == MODE_ENV && W.phase[e] == B2S_PHASE_IDLE) key = 0;
     const int p = atomicAdd(&base[255 - key], 1);
-    W.env_map[(size_t)(p % nblocks) * E + p / nblocks] = e;
+    int block, slot;
+    if (p < hcap) { block = p % Hb; slot = p / Hb; }
+    else { const int q = p - hcap; block = Hb + q % Lb; slot = q / Lb; }
+    W.env_map[(size_t)block * E + slot] = e;
   }
 }
 
@@ -525,8 +546,7 @@ __global__ void k_se3(int op, const float* a, const float* b, float* out, int n)
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
 void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s) {
-  const int nblocks = (W.B + W.envs_per_block - 1) / W.envs_per_block;
-  k_assign_envs<<<1, 1024, 0, s>>>(W, mode, nblocks);
+  k_assign_envs<<<1, 1024, 0, s>>>(W, mode, W.num_blocks);
 }
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s) { k_reset<<<blocks_for(W.B, 64), 64, 0, s>>>(W, mask, seed); }
 void b2s_launch_set_action(const DWorld& W, cudaStream_t s) { k_set_action<<<blocks_for(W.B, 128), 128, 0, s>>>(W); }

@@ -156,7 +156,8 @@ struct DWorld {
   SmemLayout sm;
   int max_ray_planes;    // raster: upper bound of hull face planes / hulls in one environment
   int max_ray_cols;
-  int envs_per_block;    // E: environments a block steps together
+  int envs_per_block;    // E: environment SLOTS of a block (capacity; the deal may leave some empty)
+  int num_blocks;        // blocks of the substep kernel
   int reg_rows;          // 1: contacts fit one per lane (max_contacts <= 32, NB <= 32): rows live in registers
 };
 

@@ -1970,7 +1970,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
 #undef W
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, cudaStream_t s) {
   const int wpb = W.P.warps_per_block;
-  const int blocks = (W.B + W.envs_per_block - 1) / W.envs_per_block;
+  const int blocks = W.num_blocks;
   size_t smem = b2s_smem_bytes(W);
   static size_t configured = 0;
   if (smem > configured) {
