@@ -11,6 +11,7 @@ Everything written here is an OUTPUT OF THE REFERENCE'S OWN CODE:
   reward.json           robovat.reward_fns.push_reward.get_reward_fn(task, layout)(state, next_state)
   sampler.json          robovat.envs.push.heuristic_push_sampler.HeuristicPushSampler.sample
   camera.json           robovat.perception.camera.camera.Camera + bullet_camera.intrinsic_to_projection_matrix
+  episodes.json         robovat.io.episode_generation.generate_episode(s) on a scripted stand-in env
   mesh.json             robovat.utils.mesh_utils (OBJ reader, volume / area / centroid), the URDF text written from
                         tools/templates/*.xml and tools/convert_obj_to_urdf.split_wrl_file
   waypoints.json        robovat.envs.push.push_env.PushEnv._compute_waypoints
@@ -294,6 +295,46 @@ def gen_mesh():
     return out
 
 
+class ScriptedEnv(object):
+    """Deterministic stand-in env for the episode driver: reward / done follow a script."""
+
+    def __init__(self, script):
+        self.script, self.t, self.resets = script, 0, 0
+
+    def reset(self):
+        self.t = 0
+        self.resets += 1
+        return {'position': [float(self.resets), 0.0]}
+
+    def step(self, action):
+        reward, done = self.script[self.t]
+        self.t += 1
+        return {'position': [float(self.resets), float(self.t)]}, reward + float(action[0]), done, None
+
+
+class ScriptedPolicy(object):
+    def action(self, observation):
+        return [observation['position'][1] * 0.5, 1.0]
+
+
+def gen_episodes():
+    """robovat.io.episode_generation.generate_episode(s) on the scripted env: transitions per episode."""
+    from robovat.io import episode_generation
+    out = []
+    for script, num_steps in (([(1.0, False), (2.0, False), (3.0, True), (4.0, False)], None),
+                              ([(1.0, False), (2.0, False), (3.0, False), (4.0, True)], 2),
+                              ([(5.0, True)], None)):
+        env = ScriptedEnv(script)
+        ep = episode_generation.generate_episode(env, ScriptedPolicy(), num_steps=num_steps)
+        gen = episode_generation.generate_episodes(ScriptedEnv(script), ScriptedPolicy(), num_steps=num_steps, debug=True)
+        two = [next(gen), next(gen)]
+        out.append({'script': script, 'num_steps': num_steps, 'keys': sorted(ep.keys()),
+                    'transitions': [{'state': t['state'], 'action': t['action'], 'reward': t['reward'], 'info': t['info']}
+                                    for t in ep['transitions']],
+                    'indices': [i for i, _ in two], 'lengths': [len(e['transitions']) for _, e in two]})
+    return out
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_cosim, ref_shim
@@ -306,6 +347,7 @@ def main():
             json.dump(obj, f)
         print('wrote', name)
     dump('mesh.json', gen_mesh())
+    dump('episodes.json', gen_episodes())
     if '--only-mesh' in sys.argv:
         return
     dump('transformations.json', gen_transformations(rs))

@@ -387,10 +387,12 @@ __global__ void k_rebuild_colliders(const __grid_constant__ DWorld W) {
 // solver work of their last substep (iterations x colours, counting sort); the expensive ones are concentrated
 // in a few blocks that get at most one environment per warp (one wave per stage, and all of its solves are
 // equally long, so nobody waits), the cheap ones are dealt round-robin over the remaining blocks, which take
-// two waves per stage but never wait for a 50-iteration solve.  Results do not depend on the deal
-// (environments never interact).  Measured on the mid-push workload: contiguous blocks 1.0, cost-ranked
-// round-robin over all blocks 1.0, this two-class deal see DESIGN.md section 5.
-#define HEAVY_KEY 60       // iterations x colours of the last substep from which an environment counts as expensive
+// two waves per stage and mostly short solves.  Results do not depend on the deal (environments never interact).
+// Measured on the mid-push workload (4096 envs x 100 substeps): contiguous blocks 40.5 ms with the slowest block
+// at 1.41x the median; cost-ranked round-robin over all blocks the same; this two-class deal 36.7 ms, slowest
+// block 1.13x the median.  What remains are sporadic 50-iteration solves (a replaced contact point loses its
+// warm start), which no deal can predict.
+#define HEAVY_KEY 1        // every stepping environment is a candidate: the class is as large as the spare slots allow (hb_max)
 __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DWorld W, int mode, int nblocks) {
   __shared__ int hist[256];
   __shared__ int base[256];

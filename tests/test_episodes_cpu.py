@@ -1,0 +1,121 @@
+"""Episode driver and episode files against the reference's own driver run on a scripted
+stand-in env (tests/golden/episodes.json, written by oracle/gen_golden.py)."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from robovat_b200 import episodes
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'episodes.json')
+
+
+class ScriptedEnv(object):
+    def __init__(self, script):
+        self.script, self.t, self.resets = script, 0, 0
+
+    def reset(self):
+        self.t = 0
+        self.resets += 1
+        return {'position': [float(self.resets), 0.0]}
+
+    def step(self, action):
+        reward, done = self.script[self.t]
+        self.t += 1
+        return {'position': [float(self.resets), float(self.t)]}, reward + float(action[0]), done, None
+
+
+class ScriptedPolicy(object):
+    def action(self, observation):
+        return [observation['position'][1] * 0.5, 1.0]
+
+
+def test_generate_episode_matches_reference_driver():
+    with open(GOLDEN) as f:
+        cases = json.load(f)
+    assert len(cases) == 3
+    for case in cases:
+        script = [tuple(x) for x in case['script']]
+        ep = episodes.generate_episode(ScriptedEnv(script), ScriptedPolicy(), num_steps=case['num_steps'])
+        assert sorted(ep.keys()) == case['keys']
+        got = [{'state': t['state'], 'action': t['action'], 'reward': t['reward'], 'info': t['info']} for t in ep['transitions']]
+        assert got == case['transitions']
+        gen = episodes.generate_episodes(ScriptedEnv(script), ScriptedPolicy(), num_steps=case['num_steps'], debug=True)
+        two = [next(gen), next(gen)]
+        assert [i for i, _ in two] == case['indices']
+        assert [len(e['transitions']) for _, e in two] == case['lengths']
+
+
+def test_generate_episodes_discards_failed_episodes_and_can_stop():
+    class Flaky(ScriptedEnv):
+        def step(self, action):
+            if self.resets == 2:
+                raise RuntimeError('boom')
+            return ScriptedEnv.step(self, action)
+    gen = episodes.generate_episodes(Flaky([(1.0, True)]), ScriptedPolicy(), num_episodes=3, timeout=0, strict=True)
+    out = list(gen)
+    assert [i for i, _ in out] == [0, 1, 2]          # the failed second attempt is discarded, indices stay dense
+
+
+def test_batched_driver_slices_per_environment():
+    class BatchEnv(object):
+        num_envs = 3
+
+        def reset(self):
+            self.t = 0
+            return {'position': np.zeros((3, 2, 3)), 'body_mask': np.ones((3, 2))}
+
+        def step(self, action):
+            self.t += 1
+            done = np.array([self.t >= 1, self.t >= 2, self.t >= 3])
+            return {'position': np.full((3, 2, 3), float(self.t)), 'body_mask': np.ones((3, 2))}, np.arange(3.0) + self.t, done, None
+
+    class BatchPolicy(object):
+        def action(self, observation):
+            return np.tile(np.arange(4, dtype=np.float32), (3, 1)) + observation['position'][:, 0, :1]
+    eps = episodes.generate_batched_episodes(BatchEnv(), BatchPolicy())
+    assert [len(e['transitions']) for e in eps] == [1, 2, 3]
+    assert eps[2]['transitions'][1]['state']['position'].shape == (2, 3)
+    assert eps[1]['transitions'][1]['reward'] == 3.0 and eps[1]['transitions'][1]['action'].shape == (4,)
+
+
+def test_pickle_writer_file_format(tmp_path):
+    writer = episodes.PickleWriter(str(tmp_path), num_entries_per_file=2, use_random_name=False)
+    for i in range(5):
+        writer({'timestamp': str(i), 'transitions': [{'reward': float(i)}]})
+    writer.close()
+    files = sorted(os.listdir(str(tmp_path)))
+    assert files == ['data_000000.pickle', 'data_000001.pickle', 'data_000002.pickle']
+    assert [len(episodes.read_all(str(tmp_path / f))) for f in files] == [2, 2, 1]
+    with open(str(tmp_path / files[0]), 'rb') as f:          # a plain stream of pickles, as the reference reads it
+        assert pickle.load(f)['timestamp'] == '0' and pickle.load(f)['timestamp'] == '1'
+        with pytest.raises(EOFError):
+            pickle.load(f)
+
+
+def test_batched_sampler_is_distribution_equivalent_to_the_scalar_one():
+    """BatchedHeuristicPolicy (vectorised rejection sampling) vs HeuristicPushSampler (bit-identical to the reference,
+    tests/test_golden_cpu.py): every accepted action satisfies the reference's acceptance rule and the accepted
+    actions have the same distribution (first two moments, 240 samples each)."""
+    from robovat_b200 import config, policies
+    pc = config.default_policy_config()
+    position = np.array([[0.55, 0.10, 0.03], [0.70, -0.15, 0.03], [0.45, -0.20, 0.03]])
+    mask = np.ones(3)
+    n = 240
+    s = policies.HeuristicPushSampler(pc.ACTION.CSPACE.LOW, pc.ACTION.CSPACE.HIGH, pc.ACTION.MOTION.TRANSLATION_X,
+                                      pc.ACTION.MOTION.TRANSLATION_Y, max_attemps=20000)
+    np.random.seed(5)
+    scalar = np.stack([s.sample(position, mask, 1, 0)[0] for _ in range(n)])
+    obs = {'position': np.tile(position, (n, 1, 1)), 'body_mask': np.ones((n, 3)), 'num_episodes': np.ones(n, np.int64),
+           'num_steps': np.zeros(n, np.int64)}
+    batched = policies.BatchedHeuristicPolicy(pc, seed=7, rounds=20000).action(obs)
+    for a in (scalar, batched):
+        for row in a[:200]:
+            wp = s.get_waypoints(row[:2], row[2:])
+            assert s.is_waypoint_clear(wp[0], None, position, s.start_margin)
+            assert not s.is_waypoint_clear(wp[0], wp[1], position[1:2], s.motion_margin)     # target = num_episodes % 3 = 1
+    se = np.sqrt(scalar.var(axis=0) / n + batched.var(axis=0) / n)
+    assert (np.abs(scalar.mean(axis=0) - batched.mean(axis=0)) < 5 * se + 1e-3).all(), (scalar.mean(axis=0), batched.mean(axis=0))
+    assert (np.abs(scalar.std(axis=0) - batched.std(axis=0)) < 0.25 * scalar.std(axis=0) + 1e-3).all()
