@@ -432,7 +432,7 @@ __device__ __noinline__ void closest_tri_dev(V3 a, V3 b, V3 c, TriRes* o) {
     if ((T).used & 4) (R)->bary[i2] = (T).t2;                                                  \
     (R)->used = (((T).used & 1) << (i0)) | ((((T).used >> 1) & 1) << (i1)) | ((((T).used >> 2) & 1) << (i2)); \
   }
-__device__ __noinline__ void closest_simplex_dev(const V3* w, int n, b2s_simplex_result* r) {
+__device__ __forceinline__ void closest_simplex_dev(const V3* w, int n, b2s_simplex_result* r) {
   r->inside = 0;
   r->degenerate = 0;
   if (n == 1) {
