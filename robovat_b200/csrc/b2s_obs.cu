@@ -4,8 +4,8 @@
 // = Bullet's CPU TinyRenderer, 180 degree flip, depth linearisation) and SegmentedPointCloudObs.get_observation
 // (robovat/observations/camera_obs.py:182-212: numpy deprojection + per-body grouping + random down-sampling).
 //
-// Raster: direct pinhole ray casting, no OpenGL round trip.  One block renders a 32x8 pixel tile of one
-// environment: the block first transforms every hull face plane of the scene into the CAMERA frame in shared
+// Raster: direct pinhole ray casting, no OpenGL round trip.  A block renders 32x8 pixel tiles of one
+// environment (its share of the image): the block first transforms every hull face plane of the scene into the CAMERA frame in shared
 // memory (so a pixel's ray/plane test is one 3-term dot product and one divide), then every thread clips its
 // ray against the convex hulls, with a conservative bounding-sphere reject per hull.  Outputs are written
 // coalesced: 4 B depth + 1 B segmentation per pixel is the only HBM traffic that scales with the image
@@ -26,10 +26,8 @@ __device__ __forceinline__ int body_uid(const DWorld& W, int n, int first_tile, 
 
 extern __shared__ float4 ray_smem[];
 
-__global__ void __launch_bounds__(TILE_W* TILE_H) k_render(const __grid_constant__ DWorld W, int tiles_x, int max_cols) {
+__global__ void __launch_bounds__(TILE_W* TILE_H) k_render(const __grid_constant__ DWorld W, int tiles_x, int num_tiles, int max_cols) {
   const int e = blockIdx.y;
-  const int tile = blockIdx.x;
-  const int tx = tile % tiles_x, ty = tile / tiles_x;
   const int tid = threadIdx.x;
   const B2SParams& P = W.P;
   const int H = P.cam_height, Wd = P.cam_width;
@@ -96,10 +94,16 @@ __global__ void __launch_bounds__(TILE_W* TILE_H) k_render(const __grid_constant
     cols[c].uid = body_uid(W, n, first_tile, slot) & 255;
   }
   __syncthreads();
-  // 3. one ray per thread
-  const int u = tx * TILE_W + (tid % TILE_W), v = ty * TILE_H + (tid / TILE_W);
-  if (u >= Wd || v >= H) return;
+  // 3. one ray per thread and tile; the block walks its share of the image's tiles, so the scene set-up above
+  //    (one block per 256 pixels before: 64 x per 128x128 frame) is paid once per block: 1.85 -> 1.03 ms for 2048
+  //    envs at 128x128.  What is left is ALU work -- every ray is clipped against the hulls whose bounding sphere it
+  //    crosses (always ground and table, plus the arm links in view), six planes and up to six IEEE divisions
+  //    each; a per-tile cull by the spheres' pixel rectangles changed nothing (1.06 ms) and was dropped again.
   const float fx = cam[0], sk = cam[1], cx = cam[2], fy = cam[4], cy = cam[5];
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  const int tx = tile % tiles_x, ty = tile / tiles_x;
+  const int u = tx * TILE_W + (tid % TILE_W), v = ty * TILE_H + (tid / TILE_W);
+  if (u >= Wd || v >= H) continue;
   const float dy = ((float)v - cy) / fy;
   const float dx = (((float)u - cx) - sk * dy) / fx;
   const V3 dir = v3(dx, dy, 1.0f);
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(TILE_W* TILE_H) k_render(const __grid_constant
   }
   W.buf.depth[((size_t)e * H + v) * Wd + u] = best;
   W.buf.segmask[((size_t)e * H + v) * Wd + u] = (uint8_t)uid;
+  }
 }
 
 // ---- segmented point cloud: one warp per (env, movable) ------------------------------------------------
@@ -201,7 +206,14 @@ void b2s_launch_render(const DWorld& W, cudaStream_t s) {
   static size_t configured = 0;
   if (smem > configured) { cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
   b2s_launch_fk(W, s);                      // link poses of the current joint state
-  k_render<<<dim3(tiles_x * tiles_y, W.B), TILE_W * TILE_H, smem, s>>>(W, tiles_x, max_cols);
+  // blocks per environment: enough blocks to fill the GPU a few times over, at most one per tile
+  const int num_tiles = tiles_x * tiles_y;
+  int per_env = (8 * 148 + W.B - 1) / W.B;
+  per_env = per_env < 1 ? 1 : (per_env > num_tiles ? num_tiles : per_env);
+#ifdef B2S_RENDER_PER_TILE
+  per_env = num_tiles;                      // tuning: the previous mapping, one block per tile
+#endif
+  k_render<<<dim3(per_env, W.B), TILE_W * TILE_H, smem, s>>>(W, tiles_x, num_tiles, max_cols);
 }
 
 void b2s_launch_point_cloud(const DWorld& W, uint64_t seed, cudaStream_t s) {

@@ -15,6 +15,11 @@ per = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 skip = int(sys.argv[4]) if len(sys.argv) > 4 else 600
 cfg = bench.bench_config(envs)
+if os.environ.get('B2S_CFG') == 'crossing':          # BASELINE configs[2]: crossing layout 0, 8 concave (multi-hull) movables
+    from robovat_b200 import config as config_lib
+    cfg = config_lib.default_push_env_config(TASK_NAME='crossing', LAYOUT_ID=0, MOVABLE_NAME=os.environ.get('B2S_MOVABLE', 'concave'),
+                                             MIN_MOVABLE_BODIES=8, MAX_MOVABLE_BODIES=8)
+    cfg.SIM.TIME_STEP = 1.0 / 240.0
 env = PushEnv(config=cfg, num_envs=envs, seed=0)
 env.reset()
 w = env.world
