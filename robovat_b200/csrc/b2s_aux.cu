@@ -392,7 +392,8 @@ __global__ void k_rebuild_colliders(const __grid_constant__ DWorld W) {
 // at 1.41x the median; cost-ranked round-robin over all blocks the same; this two-class deal 36.7 ms, slowest
 // block 1.13x the median.  What remains are sporadic 50-iteration solves (a replaced contact point loses its
 // warm start), which no deal can predict.
-#define HEAVY_KEY 1        // every stepping environment is a candidate: the class is as large as the spare slots allow (hb_max)
+#define HEAVY_KEY 60       // iterations x colours of the last substep from which an environment counts as expensive (a resting
+                           // scene has none: then the deal is a plain round-robin, which is the best for uniform work)
 __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DWorld W, int mode, int nblocks) {
   __shared__ int hist[256];
   __shared__ int base[256];

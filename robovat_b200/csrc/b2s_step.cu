@@ -432,7 +432,12 @@ __device__ __noinline__ void closest_tri_dev(V3 a, V3 b, V3 c, TriRes* o) {
     if ((T).used & 4) (R)->bary[i2] = (T).t2;                                                  \
     (R)->used = (((T).used & 1) << (i0)) | ((((T).used >> 1) & 1) << (i1)) | ((((T).used >> 2) & 1) << (i2)); \
   }
-__device__ __forceinline__ void closest_simplex_dev(const V3* w, int n, b2s_simplex_result* r) {
+#ifdef B2S_SIMPLEX_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void closest_simplex_dev(const V3* w, int n, b2s_simplex_result* r) {
   r->inside = 0;
   r->degenerate = 0;
   if (n == 1) {

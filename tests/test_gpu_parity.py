@@ -274,3 +274,47 @@ def test_episode_drivers_on_the_cuda_env():
     assert all(np.isfinite(t['reward']) for e in eps for t in e['transitions'])
     assert eps[0]['transitions'][0]['state']['position'].shape == (int(cfg.MAX_MOVABLE_BODIES), 3)
     env.close()
+
+
+def test_ragged_movable_counts_and_partial_reset_bit_exact():
+    """Edge cases of the batch: environments with 1..5 movables (zero padded slots), a masked reset of some
+    environments mid-run, and environments whose action never started (idle) next to running ones."""
+    cfg, gpu, cpu = helpers.make_pair(24, MIN_MOVABLE_BODIES=1, MAX_MOVABLE_BODIES=5)
+    gpu.reset(seed=9); cpu.reset(seed=9)
+    nm = cpu.array('num_movables')
+    assert nm.min() < nm.max() and nm.min() >= 1 and nm.max() <= 5
+    np.testing.assert_array_equal(gpu.num_movables.cpu().numpy(), nm)
+    gpu.settle(0.1, 0.1, 500); cpu.settle(0.1, 0.1, 500)
+    _compare_state(gpu, cpu, 'ragged settle')
+    mask = (np.arange(24) % 3 == 0)
+    gpu.reset(seed=10, mask=mask); cpu.reset(seed=10, mask=mask)
+    gpu.step(300); cpu.step(300)
+    _compare_state(gpu, cpu, 'ragged after masked reset')
+    _compare_contacts(gpu, cpu, 'ragged after masked reset')
+    act = np.tile(np.array([0.1, 0.0, -0.8, 0.5], np.float32), (24, 1))
+    gpu.set_action(act); cpu.set_action(act)
+    idle = np.arange(24) % 4 == 0                      # these environments do not execute the action
+    ph_g = gpu.array(_capi.ARR_PHASE); ph_c = cpu.array(_capi.ARR_PHASE)
+    ph_g[torch.from_numpy(idle).to(ph_g.device)] = _capi.PHASE_IDLE
+    ph_c[idle] = _capi.PHASE_IDLE
+    before = np.array(cpu.array(_capi.ARR_NUM_STEPS))
+    for _ in range(4):
+        ug, uc = gpu.env_substeps(300), cpu.env_substeps(300)
+        assert ug == uc
+    _compare_state(gpu, cpu, 'ragged mid action')
+    after = cpu.array(_capi.ARR_NUM_STEPS)
+    assert (after[idle] == before[idle]).all() and (after[~idle] > before[~idle]).all()
+    np.testing.assert_array_equal(gpu.array(_capi.ARR_NUM_STEPS).cpu().numpy(), after)
+
+
+def test_capacity_overflow_is_flagged_identically():
+    """Maximum sizes: a pair / manifold capacity that is too small raises the same error flags on both sides and the
+    surviving contacts still agree."""
+    cfg, gpu, cpu = helpers.make_pair(8, TASK_NAME='crossing', LAYOUT_ID=0, MOVABLE_NAME='concave',
+                                      MIN_MOVABLE_BODIES=8, MAX_MOVABLE_BODIES=8, params={'max_pairs': 12, 'max_manifolds': 8})
+    gpu.reset(seed=2); cpu.reset(seed=2)
+    for k in range(3):
+        gpu.step(100); cpu.step(100)
+        np.testing.assert_array_equal(gpu.array(_capi.ARR_ERROR_FLAGS).cpu().numpy(), cpu.array(_capi.ARR_ERROR_FLAGS))
+        _compare_contacts(gpu, cpu, 'overflow after %d substeps' % (100 * (k + 1)))
+    assert int(cpu.array(_capi.ARR_ERROR_FLAGS).max()) & 3
