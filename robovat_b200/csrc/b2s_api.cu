@@ -107,7 +107,7 @@ int b2s_default_params(B2SParams* p) {
 
 int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
   if (!p || !out) return fail(B2S_E_INVALID, "b2s_create: NULL argument");
-  if (p->num_envs <= 0 || p->max_movables <= 0 || p->max_movables > 64) return fail(B2S_E_INVALID, "b2s_create: num_envs/max_movables out of range");
+  if (p->num_envs <= 0 || p->max_movables <= 0 || p->max_movables > 32) return fail(B2S_E_INVALID, "b2s_create: num_envs must be > 0 and max_movables 1..32 (one movable per lane in the solve)");
   if (p->max_pairs <= 0 || p->max_manifolds <= 0 || p->max_contacts <= 0 || p->max_colliders <= 0)
     return fail(B2S_E_INVALID, "b2s_create: capacities must be positive");
   if (p->max_colliders > 65535) return fail(B2S_E_INVALID, "b2s_create: max_colliders > 65535");
@@ -283,18 +283,17 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   sm.col = take(d.Hmax * COL_STRIDE);
   sm.pairs = take(P.max_pairs);
   sm.cmk = take(P.max_contacts);
-  sm.used = take(d.reg_rows ? 0 : d.NB * 2);     // colour masks of the generic solve
   sm.words_env = o;
   o = 0;
-  sm.order = take(P.max_contacts);
-  sm.colstart = take(66);
   const int x0 = o;                 // region shared by the narrow-phase scratch and the solver rows
   sm.oldkeys = take(P.max_manifolds);
   sm.stage = take(4 * B2S_CP_FLOATS);
   sm.fk = take(FK_WORDS);
   sm.simplex = take(48);
   sm.con = x0;
-  o = std::max(o, x0 + (d.reg_rows ? 512 + 8 * 32 : P.max_contacts * CON_STRIDE));   // reg_rows: colour table + lambda x2 + slots
+  // solve-stage scratch: small path = colour table (bytes) + lambda x2 + slots; big path = colour table (16 bit) +
+  // bodies and colour of every contact
+  o = std::max(o, x0 + (d.reg_rows ? 512 + 8 * 32 : 1024 + (P.max_contacts + 1) / 2 + (P.max_contacts + 3) / 4 + 2));
   sm.words_warp = o;
   {
     // large scenes (rows in shared memory): fewer warps per block so the block still fits 220 KB
@@ -303,7 +302,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     const int wpb = d.P.warps_per_block;
     // environments per block: with register-resident rows any warp can run any stage of any environment of
     // its block (dynamic hand-out), so a block may own more environments than warps; otherwise one per warp
-    int maxE = d.reg_rows ? 4 * wpb : wpb;
+    int maxE = 4 * wpb;
     while (maxE > 1 && ((size_t)maxE * (sm.words_env + META_WORDS) + (size_t)wpb * sm.words_warp) * 4 > 220 * 1024) --maxE;
     int E;
     if (P.reserved_i[0] > 0) E = P.reserved_i[0];
@@ -314,18 +313,17 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
       const int waves = (d.B + dev_sms * maxE - 1) / (dev_sms * maxE);
       E = (d.B + dev_sms * waves - 1) / (dev_sms * waves);
     }
-    if (!d.reg_rows) E = wpb;
     if (E < 1) E = 1;
     if (E > maxE) E = maxE;
     d.num_blocks = (d.B + E - 1) / E;
     // spare slots: the deal (k_assign_envs) gives the blocks that hold the expensive environments at most one
     // environment per warp and lets the cheap blocks take the rest
-    if (d.reg_rows && P.reserved_i[0] <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7));
+    if (P.reserved_i[0] <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7));
     d.envs_per_block = E;
     const size_t blocks = d.num_blocks;
     if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
     if ((rc = dalloc(w, &d.env_map, blocks * (size_t)E, 0xff))) return rc;
-    if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)(32 * 68), 0))) return rc;
+    if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)std::max(32 * 68, P.max_contacts * 76), 0))) return rc;
   }
   size_t smem = b2s_smem_bytes(d);
   if (smem > 227 * 1024) return fail(B2S_E_CAPACITY, "b2s_load_scene: %zu bytes of shared memory per block exceed 227 KB; lower warps_per_block or the capacities", smem);

@@ -77,8 +77,8 @@ struct DLayout {
 // (oldkeys .. simplex): rows are only alive in the solve stage.  The EPA polytope (rare path, 4 KB per
 // warp) lives in global memory so that the block leaves more of the SM's 256 KB to the L1 cache.
 struct SmemLayout {
-  int body, col, pairs, cmk, used, words_env;                              // per environment
-  int oldkeys, con, order, colstart, stage, fk, simplex, words_warp;       // per warp: scratch
+  int body, col, pairs, cmk, words_env;                        // per environment
+  int oldkeys, con, stage, fk, simplex, words_warp;            // per warp: scratch
 };
 #define META_ACTIVE 0
 #define META_NP 1
@@ -92,8 +92,6 @@ struct SmemLayout {
 
 #define BODY_STRIDE 35   // pos3 R9 vel3 ang3 invm1 invI9 fric1 type1 quat4 = 34 (+1 pad, odd stride)
 #define COL_STRIDE 13    // hull slot type|flags scale margin rad amin3 amax3 = 12 (+1)
-#define CON_STRIDE 65    // see k_contacts: 3 rows x 19 + slotA slotB mu m|k colour = 62 (+pad, odd)
-#define ROW_WORDS 19     // dir3 angA3 angB3 iangA3 iangB3 inv_d d bias lambda
 #define FK_WORDS 96      // frames 7x7, axes 7x3, origins 7x3 = 91
 
 struct DWorld {
@@ -149,20 +147,15 @@ struct DWorld {
   int32_t* env_map;               // [blocks][E] environment stepped in a block slot (-1 none), re-dealt before every launch
   unsigned long long* prof;       // [8] stage timing counters (only written by -DB2S_PROF builds)
   float* row_scratch;             // [blocks][warps][32][68] solver rows of the environment a warp is solving (L1/L2 resident)
-  // staged-mode scratch: contact rows / body velocities dumped between kernels
-  float* stage_rows;     // [B][max_contacts][CON_STRIDE]
-  float* stage_body;     // [B][NB][BODY_STRIDE]
-  int32_t* stage_meta;   // [B][4 + max_contacts + 65]   nc, ncolours, pad, pad, order[], colstart[]
   SmemLayout sm;
   int max_ray_planes;    // raster: upper bound of hull face planes / hulls in one environment
   int max_ray_cols;
   int envs_per_block;    // E: environment SLOTS of a block (capacity; the deal may leave some empty)
   int num_blocks;        // blocks of the substep kernel
-  int reg_rows;          // 1: contacts fit one per lane (max_contacts <= 32, NB <= 32): rows live in registers
+  int reg_rows;          // 1: contacts fit one per lane and body slots one per lane (max_contacts <= 32, NB <= 32): small solve path
 };
 
 enum { MODE_RAW = 0, MODE_ENV = 1, MODE_SETTLE = 2 };
-enum { SPLIT_NONE = 0, SPLIT_PRE = 1, SPLIT_POST = 2 };   // staged mode: stop before / resume after PGS
 
 // host launchers (defined next to their kernels)
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, cudaStream_t s);

@@ -45,24 +45,6 @@ __device__ __forceinline__ void stm3(float* p, M3 m) { ST3(p, m.r0); ST3(p + 3, 
 #define CO_RAD 5
 #define CO_AMIN 6
 #define CO_AMAX 9
-// contact record offsets
-#define CN_SLOTA 57
-#define CN_SLOTB 58
-#define CN_MU 59
-#define CN_MK 60
-#define CN_COLOUR 61
-#define CN_INVMA 62
-#define CN_INVMB 63
-// row offsets
-#define RW_DIR 0
-#define RW_ANGA 3
-#define RW_ANGB 6
-#define RW_IANGA 9
-#define RW_IANGB 12
-#define RW_INVD 15
-#define RW_D 16
-#define RW_BIAS 17
-#define RW_LAMBDA 18
 
 extern __shared__ float b2s_smem[];
 
@@ -93,8 +75,7 @@ __device__ __forceinline__ Xf xf_mul(Xf a, Xf b) { Xf t; t.p = a.p + qrot(a.q, b
 __device__ __forceinline__ void xf_store(Xf t, float* o) { o[0] = t.p.x; o[1] = t.p.y; o[2] = t.p.z; o[3] = t.q.x; o[4] = t.q.y; o[5] = t.q.z; o[6] = t.q.w; }
 
 struct WarpSmem {
-  float* body; float* col; int* pairs; int* oldkeys; int* cmk; float* con; int* order; int* colstart;
-  unsigned long long* used; float* stage; float* fk; float* sx;
+  float* body; float* col; int* pairs; int* oldkeys; int* cmk; float* con; float* stage; float* fk; float* sx;
 };
 
 // `sw` packs (environment slot of the block) | (warp in block) << 16
@@ -108,9 +89,8 @@ __device__ __forceinline__ WarpSmem carve(int sw) {
   float* wb = b2s_smem + (size_t)W.envs_per_block * W.sm.words_env + (size_t)(sw >> 16) * W.sm.words_warp;
   WarpSmem s;
   s.body = eb + W.sm.body; s.col = eb + W.sm.col; s.pairs = (int*)(eb + W.sm.pairs); s.cmk = (int*)(eb + W.sm.cmk);
-  s.used = (unsigned long long*)(eb + W.sm.used);
-  s.oldkeys = (int*)(wb + W.sm.oldkeys); s.con = wb + W.sm.con; s.order = (int*)(wb + W.sm.order);
-  s.colstart = (int*)(wb + W.sm.colstart); s.stage = wb + W.sm.stage; s.fk = wb + W.sm.fk; s.sx = wb + W.sm.simplex;
+  s.oldkeys = (int*)(wb + W.sm.oldkeys); s.con = wb + W.sm.con;
+  s.stage = wb + W.sm.stage; s.fk = wb + W.sm.fk; s.sx = wb + W.sm.simplex;
   return s;
 }
 
@@ -1159,186 +1139,29 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
   }
   __syncwarp();
 
-  // contact rows, one contact per lane (generic path: rows in shared memory)
-  const int nrows = 1 + P.friction_dirs;
-  for (int c = lane; build_rows && c < ncon; c += 32) {
-    const int mk = S.cmk[c];
-    const int m = mk >> 2, k = mk & 3;
-    const int key = W.man_keys[nbase + m];
-    const int a = key >> 16, b = key & 0xffff;
-    const int sA = __float_as_int(S.col[a * COL_STRIDE + CO_SLOT]), sB = __float_as_int(S.col[b * COL_STRIDE + CO_SLOT]);
-    const float* bA = S.body + sA * BODY_STRIDE;
-    const float* bB = S.body + sB * BODY_STRIDE;
-    const float* p = W.man_pts + ((nbase + m) * 4 + k) * B2S_CP_FLOATS;
-    float* cn = S.con + c * CON_STRIDE;
-    V3 posA = LD3(bA + BO_POS), posB = LD3(bB + BO_POS);
-    V3 wA = posA + mmul(ldm3(bA + BO_R), v3(p[0], p[1], p[2]));
-    V3 wB = posB + mmul(ldm3(bB + BO_R), v3(p[3], p[4], p[5]));
-    V3 n = v3(p[6], p[7], p[8]);
-    V3 rA = wA - posA, rB = wB - posB;
-    V3 t1, t2;
-    plane_space(n, &t1, &t2);
-    if (P.friction_dirs == 1) {
-      V3 rel = (LD3(bA + BO_VEL) + cross(LD3(bA + BO_ANG), rA)) - (LD3(bB + BO_VEL) + cross(LD3(bB + BO_ANG), rB));
-      V3 lat = rel - n * dot(rel, n);
-      float l2 = len2(lat);
-      if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
-    }
-    const float imA = bA[BO_INVM], imB = bB[BO_INVM];
-    const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      float* row = cn + r * ROW_WORDS;
-      V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
-      V3 angA = cross(rA, dir), angB = cross(rB, dir);
-      V3 iangA = mmul(iA, angA), iangB = mmul(iB, angB);
-      float d = ((imA + imB) + dot(iangA, angA)) + dot(iangB, angB);
-      ST3(row + RW_DIR, dir); ST3(row + RW_ANGA, angA); ST3(row + RW_ANGB, angB);
-      ST3(row + RW_IANGA, iangA); ST3(row + RW_IANGB, iangB);
-      row[RW_INVD] = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
-      row[RW_D] = d;
-      row[RW_BIAS] = 0.0f;
-      float lam = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
-      if (r >= nrows) lam = 0.0f;
-      row[RW_LAMBDA] = lam;
-    }
-    float pen = p[9] + P.linear_slop;
-    cn[RW_BIAS] = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
-    cn[CN_SLOTA] = __int_as_float(sA); cn[CN_SLOTB] = __int_as_float(sB);
-    cn[CN_MU] = bA[BO_FRIC] * bB[BO_FRIC];
-    cn[CN_MK] = __int_as_float(mk);
-    cn[CN_COLOUR] = __int_as_float(-1);
-    cn[CN_INVMA] = (__float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC) ? imA : 0.0f;
-    cn[CN_INVMB] = (__float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC) ? imB : 0.0f;
-  }
-  __syncwarp();
+  (void)build_rows; (void)dt;
   PROF_SEC(7)
   *nc_out = ncon;
   *newn_out = newn;
 }
 
-// greedy colouring in contact order + stable sort by colour (oracle step 7)
-__device__ __noinline__ int colour_contacts(int e, int lane, int wib, int C) {
-  const WarpSmem S = carve(wib);
-  for (int s = lane; s < W.NB; s += 32) S.used[s] = 0ull;
-  __syncwarp();
-  int ncolours = 0;
-  if (lane == 0) {
-    bool over = false;
-    for (int i = 0; i < C; ++i) {
-      float* cn = S.con + i * CON_STRIDE;
-      int sA = __float_as_int(cn[CN_SLOTA]), sB = __float_as_int(cn[CN_SLOTB]);
-      bool dA = __float_as_int(S.body[sA * BODY_STRIDE + BO_TYPE]) == B2S_TYPE_DYNAMIC;
-      bool dB = __float_as_int(S.body[sB * BODY_STRIDE + BO_TYPE]) == B2S_TYPE_DYNAMIC;
-      unsigned long long mask = (dA ? S.used[sA] : 0ull) | (dB ? S.used[sB] : 0ull);
-      if (mask == ~0ull) { over = true; cn[CN_COLOUR] = __int_as_float(-1); continue; }
-      int k = __ffsll((long long)~mask) - 1;
-      cn[CN_COLOUR] = __int_as_float(k);
-      if (k + 1 > ncolours) ncolours = k + 1;
-      if (dA) S.used[sA] |= 1ull << k;
-      if (dB) S.used[sB] |= 1ull << k;
-    }
-    if (over) W.error_flags[e] |= 16;
-  }
-  ncolours = __shfl_sync(FULL, ncolours, 0);
-  __syncwarp();
-  for (int c = lane; c < C; c += 32) {
-    int my = __float_as_int(S.con[c * CON_STRIDE + CN_COLOUR]);
-    if (my < 0) continue;
-    int pos = 0;
-    for (int o = 0; o < C; ++o) {
-      int oc = __float_as_int(S.con[o * CON_STRIDE + CN_COLOUR]);
-      pos += (oc >= 0 && (oc < my || (oc == my && o < c))) ? 1 : 0;
-    }
-    S.order[pos] = c;
-  }
-  for (int k = lane; k <= ncolours; k += 32) {
-    int cnt = 0;
-    for (int o = 0; o < C; ++o) {
-      int oc = __float_as_int(S.con[o * CON_STRIDE + CN_COLOUR]);
-      cnt += (oc >= 0 && oc < k) ? 1 : 0;
-    }
-    S.colstart[k] = cnt;
-  }
-  __syncwarp();
-  return ncolours;
-}
+// ---- body-centric solve, any number of contacts (max_movables <= 32) ---------------------------------------
+// Same scheme as substep_post_reg below (read its header first) for scenes that do not fit one contact per lane
+// and one body slot per lane: config #3 has 8 multi-hull movables on 18 tile bodies, ~120 contact points and ~30
+// colours per environment.  Differences: rows are built 32 contacts at a time; lane i of the sweeps is MOVABLE i
+// (the only dynamic bodies), not body slot i; lambda and the body indices of a contact live in its record
+// (76 words in the warp's global scratch) instead of shared memory; the sequential greedy colouring reads the
+// contact's bodies from a small shared array instead of shuffling them out of the contact lanes.  The row
+// arithmetic, the colouring rule and the sweep order are the oracle's, so results are bit-identical.
+// (This path replaced a contact-per-lane solver with all rows in shared memory: 50 KB per warp, i.e. 4 warps
+// per SM on config #3, whose solve stage took 76 % of the substep.)
+#define RR_B 48                          // word offset of angB/iangB in a contact record (both body-centric paths)
+#define RB_WORDS 76                      // record: rows [0,48) as in substep_post_reg, angB/iangB [48,66), lambda [66,69),
+#define RB_LAM 66                        //   the B lane's lambda [69,72), movable index of A | B << 8 | flags at 72
+#define RB_LAMB 69
+#define RB_INFO 72
 
-__device__ __forceinline__ float row_jv(const float* row, const float* bA, const float* bB) {
-  return ((dot(LD3(row + RW_DIR), LD3(bA + BO_VEL)) + dot(LD3(row + RW_ANGA), LD3(bA + BO_ANG))) -
-          dot(LD3(row + RW_DIR), LD3(bB + BO_VEL))) - dot(LD3(row + RW_ANGB), LD3(bB + BO_ANG));
-}
-__device__ __forceinline__ void row_apply(const float* row, float* bA, float* bB, float imA, float imB, bool dA, bool dB, float dl) {
-  V3 dir = LD3(row + RW_DIR);
-  if (dA) { ST3(bA + BO_VEL, vmad(LD3(bA + BO_VEL), dir, imA * dl)); ST3(bA + BO_ANG, vmad(LD3(bA + BO_ANG), LD3(row + RW_IANGA), dl)); }
-  if (dB) { ST3(bB + BO_VEL, vmad(LD3(bB + BO_VEL), dir, -(imB * dl))); ST3(bB + BO_ANG, vmad(LD3(bB + BO_ANG), LD3(row + RW_IANGB), -dl)); }
-}
-
-// projected Gauss-Seidel over the colour-ordered rows held in shared memory (oracle step 8)
-__device__ __noinline__ int pgs_solve(int lane, float* body, float* con, const int* order, const int* colstart,
-                         int C, int ncolours) {
-  const B2SParams& P = W.P;
-  const int nrows = 1 + P.friction_dirs;
-  // warm start
-  for (int k = 0; k < ncolours; ++k) {
-    for (int idx = colstart[k] + lane; idx < colstart[k + 1]; idx += 32) {
-      float* cn = con + order[idx] * CON_STRIDE;
-      int sA = __float_as_int(cn[CN_SLOTA]), sB = __float_as_int(cn[CN_SLOTB]);
-      float* bA = body + sA * BODY_STRIDE; float* bB = body + sB * BODY_STRIDE;
-      bool dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC, dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
-      for (int r = 0; r < nrows; ++r) row_apply(cn + r * ROW_WORDS, bA, bB, bA[BO_INVM], bB[BO_INVM], dA, dB, cn[r * ROW_WORDS + RW_LAMBDA]);
-    }
-    __syncwarp();
-  }
-  int iters_used = 0;
-  for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
-    float maxres = 0.0f;
-    for (int k = 0; k < ncolours; ++k) {
-      for (int idx = colstart[k] + lane; idx < colstart[k + 1]; idx += 32) {
-        float* cn = con + order[idx] * CON_STRIDE;
-        int sA = __float_as_int(cn[CN_SLOTA]), sB = __float_as_int(cn[CN_SLOTB]);
-        float* bA = body + sA * BODY_STRIDE; float* bB = body + sB * BODY_STRIDE;
-        bool dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC, dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
-        float* row = cn;
-        float dl = (row[RW_BIAS] - row_jv(row, bA, bB)) * row[RW_INVD];
-        float nl = fmaxf(0.0f, row[RW_LAMBDA] + dl);
-        dl = nl - row[RW_LAMBDA];
-        row[RW_LAMBDA] = nl;
-        row_apply(row, bA, bB, bA[BO_INVM], bB[BO_INVM], dA, dB, dl);
-        float res = dl * row[RW_D];
-        maxres = fmaxf(maxres, res * res);
-      }
-      __syncwarp();
-    }
-    for (int k = 0; k < ncolours; ++k) {
-      for (int idx = colstart[k] + lane; idx < colstart[k + 1]; idx += 32) {
-        float* cn = con + order[idx] * CON_STRIDE;
-        int sA = __float_as_int(cn[CN_SLOTA]), sB = __float_as_int(cn[CN_SLOTB]);
-        float* bA = body + sA * BODY_STRIDE; float* bB = body + sB * BODY_STRIDE;
-        bool dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC, dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
-        float lim = cn[CN_MU] * cn[RW_LAMBDA];
-        for (int r = 1; r < nrows; ++r) {
-          float* row = cn + r * ROW_WORDS;
-          float dl = (0.0f - row_jv(row, bA, bB)) * row[RW_INVD];
-          float nl = fminf(lim, fmaxf(-lim, row[RW_LAMBDA] + dl));
-          dl = nl - row[RW_LAMBDA];
-          row[RW_LAMBDA] = nl;
-          row_apply(row, bA, bB, bA[BO_INVM], bB[BO_INVM], dA, dB, dl);
-          float res = dl * row[RW_D];
-          maxres = fmaxf(maxres, res * res);
-        }
-      }
-      __syncwarp();
-    }
-    iters_used = it + 1;
-    unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));   // residuals are >= 0: bit order == value order
-    if (__uint_as_float(mx) <= P.residual_threshold) break;
-  }
-  return iters_used;
-}
-
-// stages 7-9: colour, solve, write back impulses, integrate
-__device__ __noinline__ void substep_post(int e, int lane, int wib, int C, int newn) {
+__device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, int newn) {
   const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
   const float dt = (float)P.time_step;
@@ -1346,31 +1169,206 @@ __device__ __noinline__ void substep_post(int e, int lane, int wib, int C, int n
   const int nm = W.buf.num_movables[e];
   const int par = W.man_parity[e];          // already flipped: current buffer
   const size_t nbase = ((size_t)par * W.B + e) * P.max_manifolds;
-  int ncolours = colour_contacts(e, lane, wib, C);
-  int iters = pgs_solve(lane, S.body, S.con, S.order, S.colstart, C, ncolours);
+  const int nrows = 1 + P.friction_dirs;
+  float* rr = W.row_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * ((size_t)P.max_contacts * RB_WORDS);
+  unsigned short* T = (unsigned short*)S.con;                 // [64 colours][32 movables]: contact | side << 14 | coupled << 15
+  unsigned short* cinfo = (unsigned short*)(S.con + 1024);    // [C] movable of A (31 = none) | movable of B << 5 | dA << 10 | dB << 11
+  unsigned char* ccol = (unsigned char*)(S.con + 1024 + (P.max_contacts + 1) / 2);   // [C] colour, 0xff = none
+  const int mov0 = Ns + L;
+  __syncwarp();
+  // rows, 32 contacts at a time
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    if (c < C) {
+      const int mk = S.cmk[c];
+      const int m = mk >> 2, k = mk & 3;
+      const int key = W.man_keys[nbase + m];
+      const int a = key >> 16, b = key & 0xffff;
+      const int sA = __float_as_int(S.col[a * COL_STRIDE + CO_SLOT]), sB = __float_as_int(S.col[b * COL_STRIDE + CO_SLOT]);
+      const float* bA = S.body + sA * BODY_STRIDE;
+      const float* bB = S.body + sB * BODY_STRIDE;
+      const float* p = W.man_pts + ((nbase + m) * 4 + k) * B2S_CP_FLOATS;
+      V3 posA = LD3(bA + BO_POS), posB = LD3(bB + BO_POS);
+      V3 wA = posA + mmul(ldm3(bA + BO_R), v3(p[0], p[1], p[2]));
+      V3 wB = posB + mmul(ldm3(bB + BO_R), v3(p[3], p[4], p[5]));
+      V3 n = v3(p[6], p[7], p[8]);
+      V3 rA = wA - posA, rB = wB - posB;
+      V3 t1, t2;
+      plane_space(n, &t1, &t2);
+      const V3 velB = LD3(bB + BO_VEL), angvB = LD3(bB + BO_ANG);
+      if (P.friction_dirs == 1) {
+        V3 rel = (LD3(bA + BO_VEL) + cross(LD3(bA + BO_ANG), rA)) - (velB + cross(angvB, rB));
+        V3 lat = rel - n * dot(rel, n);
+        float l2 = len2(lat);
+        if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
+      }
+      const float imA = bA[BO_INVM], imB = bB[BO_INVM];
+      const bool dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC, dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
+      const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
+      float* rec1 = rr + (size_t)c * RB_WORDS;
+      float4* rec = (float4*)rec1;
+      const float pen = p[9] + P.linear_slop;
+      const float bias0 = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
+      const float mu = bA[BO_FRIC] * bB[BO_FRIC];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
+        const V3 angA = cross(rA, dir), angB = cross(rB, dir);
+        const V3 iangA = mmul(iA, angA), iangB = mmul(iB, angB);
+        const float d = ((imA + imB) + dot(iangA, angA)) + dot(iangB, angB);
+        const float inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
+        float l0 = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
+        if (r >= nrows) l0 = 0.0f;
+        rec[r * 4 + 0] = make_float4(dir.x, dir.y, dir.z, angA.x);
+        rec[r * 4 + 1] = make_float4(angA.y, angA.z, iangA.x, iangA.y);
+        rec[r * 4 + 2] = make_float4(iangA.z, inv_d, d, dot(dir, velB));
+        rec[r * 4 + 3] = make_float4(dot(angB, angvB), imA, (r == 0) ? bias0 : mu, imB);
+        rec1[RR_B + r * 6 + 0] = angB.x; rec1[RR_B + r * 6 + 1] = angB.y; rec1[RR_B + r * 6 + 2] = angB.z;
+        rec1[RR_B + r * 6 + 3] = iangB.x; rec1[RR_B + r * 6 + 4] = iangB.y; rec1[RR_B + r * 6 + 5] = iangB.z;
+        rec1[RB_LAM + r] = l0; rec1[RB_LAMB + r] = l0;
+      }
+      const int iA_ = dA ? sA - mov0 : 31, iB_ = dB ? sB - mov0 : 31;
+      rec1[RB_INFO] = __int_as_float(iA_ | (iB_ << 8));
+      cinfo[c] = (unsigned short)(iA_ | (iB_ << 5) | ((int)dA << 10) | ((int)dB << 11));
+      if (dB && !dA) W.error_flags[e] |= 64;     // cannot happen: movable colliders are numbered last
+    }
+  }
+  __syncwarp();
+  // greedy colouring in contact order; lane i keeps the colour mask of movable i
+  unsigned long long used = 0ull;
+  int ncolours = 0;
+  bool col_over = false;
+  for (int i = 0; i < C; ++i) {
+    const unsigned info = cinfo[i];
+    const int iA_ = info & 31, iB_ = (info >> 5) & 31;
+    const bool idA = (info >> 10) & 1, idB = (info >> 11) & 1;
+    const unsigned long long mA = __shfl_sync(FULL, used, iA_), mB = __shfl_sync(FULL, used, iB_);
+    const unsigned long long mask = (idA ? mA : 0ull) | (idB ? mB : 0ull);
+    if (mask == ~0ull) { col_over = true; if (lane == 0) ccol[i] = 0xff; continue; }
+    const int k = __ffsll((long long)~mask) - 1;
+    if (lane == 0) ccol[i] = (unsigned char)k;
+    if (k + 1 > ncolours) ncolours = k + 1;
+    if ((idA && lane == iA_) || (idB && lane == iB_)) used |= 1ull << k;
+  }
+  if (col_over && lane == 0) W.error_flags[e] |= 16;
+  for (int i = lane; i < ncolours * 16; i += 32) ((unsigned*)T)[i] = 0xffffffffu;
+  __syncwarp();
+  unsigned long long coupled = 0ull;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    unsigned cplk = 0xffu;
+    if (c < C && ccol[c] != 0xff) {
+      const unsigned info = cinfo[c];
+      const int k = ccol[c];
+      const bool dA = (info >> 10) & 1, dB = (info >> 11) & 1;
+      const unsigned cpl = (dA && dB) ? 0x8000u : 0u;
+      if (dA) T[k * 32 + (info & 31)] = (unsigned short)(c | cpl);
+      if (dB) T[k * 32 + ((info >> 5) & 31)] = (unsigned short)(c | 0x4000u | cpl);
+      if (cpl) cplk = k;
+    }
+    // colours that hold a contact between two dynamic bodies (warp-uniform mask)
+    for (unsigned mm = __ballot_sync(FULL, cplk != 0xffu); mm; mm &= mm - 1) coupled |= 1ull << __shfl_sync(FULL, cplk, __ffs(mm) - 1);
+  }
+  __syncwarp();
+  // ---- sweeps: lane = movable index
+  const bool dyn = lane < nm;
+  float* myb = S.body + (mov0 + (dyn ? lane : 0)) * BODY_STRIDE;
+  V3 vel = LD3(myb + BO_VEL), ang = LD3(myb + BO_ANG);
+  float maxres = 0.0f;
+  int iters = 0;
+#define BIG_STEP(PASS)                                                                                            \
+  {                                                                                                               \
+    const unsigned t = dyn ? (unsigned)T[k * 32 + lane] : 0xffffu;                                                \
+    const bool has = t != 0xffffu;                                                                                \
+    const int c = t & 0x3fff;                                                                                     \
+    const bool sideB = (t & 0x4000u) != 0u, cpl = (t & 0x8000u) != 0u;                                            \
+    float* rec1 = rr + (size_t)(has ? c : 0) * RB_WORDS;                                                          \
+    V3 ov = v3(0, 0, 0), ow = v3(0, 0, 0);                                                                        \
+    if ((coupled >> k) & 1ull) {                                                                                  \
+      int src = lane;                                                                                             \
+      if (has && cpl) { const int info = __float_as_int(rec1[RB_INFO]); src = sideB ? (info & 255) : (info >> 8); } \
+      ov = v3(__shfl_sync(FULL, vel.x, src), __shfl_sync(FULL, vel.y, src), __shfl_sync(FULL, vel.z, src));       \
+      ow = v3(__shfl_sync(FULL, ang.x, src), __shfl_sync(FULL, ang.y, src), __shfl_sync(FULL, ang.z, src));       \
+    }                                                                                                             \
+    if (has) {                                                                                                    \
+      const float4* rec = (const float4*)rec1;                                                                    \
+      float* ml = rec1 + (sideB ? RB_LAMB : RB_LAM);                                                              \
+      float lim = 0.0f;                                                                                           \
+      if (PASS == 2) lim = rec[7].z * ml[0];                                                                      \
+      _Pragma("unroll")                                                                                           \
+      for (int r = (PASS == 2) ? 1 : 0; r < ((PASS == 1) ? 1 : 3); ++r) {                                         \
+        if (r >= nrows) break;                                                                                    \
+        const float4 q0 = rec[r * 4], q1 = rec[r * 4 + 1], q2 = rec[r * 4 + 2], q3 = rec[r * 4 + 3];              \
+        const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
+        V3 angB = v3(0, 0, 0), iangB = v3(0, 0, 0);                                                               \
+        if (cpl || sideB) { angB = LD3(rec1 + RR_B + r * 6); iangB = LD3(rec1 + RR_B + r * 6 + 3); }              \
+        const float l = ml[r];                                                                                    \
+        float dl = l;                                                                                             \
+        if (PASS != 0) {                                                                                          \
+          const V3 vA = sideB ? ov : vel, wA = sideB ? ow : ang;                                                  \
+          const float a = dot(dir, vA) + dot(angA, wA);                                                           \
+          float k1 = q2.w, k2 = q3.x;                                                                             \
+          if (cpl) { k1 = dot(dir, sideB ? vel : ov); k2 = dot(angB, sideB ? ang : ow); }                         \
+          const float jv = (a - k1) - k2;                                                                         \
+          dl = (((PASS == 1) ? q3.z : 0.0f) - jv) * q2.y;                                                         \
+          float nl = l + dl;                                                                                      \
+          nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
+          dl = nl - l;                                                                                            \
+          ml[r] = nl;                                                                                             \
+          const float res = dl * q2.z;                                                                            \
+          maxres = fmaxf(maxres, res * res);                                                                      \
+        }                                                                                                         \
+        if (!sideB) {                                                                                             \
+          vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                            \
+          if (cpl) { ov = vmad(ov, dir, -(q3.w * dl)); ow = vmad(ow, iangB, -dl); }   /* what the partner does */ \
+        } else {                                                                                                  \
+          vel = vmad(vel, dir, -(q3.w * dl)); ang = vmad(ang, iangB, -dl);                                        \
+          ov = vmad(ov, dir, q3.y * dl); ow = vmad(ow, iangA, dl);                                                \
+        }                                                                                                         \
+      }                                                                                                           \
+    }                                                                                                             \
+  }
+#pragma unroll 1
+  for (int k = 0; k < ncolours; ++k) BIG_STEP(0)
+  __syncwarp();
+  for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
+    maxres = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < ncolours; ++k) BIG_STEP(1)
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k < ncolours; ++k) BIG_STEP(2)
+    __syncwarp();
+    iters = it + 1;
+    unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
+    if (__uint_as_float(mx) <= P.residual_threshold) break;
+  }
+#undef BIG_STEP
+  if (dyn) { ST3(myb + BO_VEL, vel); ST3(myb + BO_ANG, ang); }
+  __syncwarp();
   for (int c = lane; c < C; c += 32) {
-    const float* cn = S.con + c * CON_STRIDE;
-    int mk = __float_as_int(cn[CN_MK]);
+    const int mk = S.cmk[c];
+    const float* rec1 = rr + (size_t)c * RB_WORDS;
     float* p = W.man_pts + ((nbase + (mk >> 2)) * 4 + (mk & 3)) * B2S_CP_FLOATS;
-    p[10] = cn[RW_LAMBDA]; p[11] = cn[ROW_WORDS + RW_LAMBDA]; p[12] = cn[2 * ROW_WORDS + RW_LAMBDA];
+    p[10] = rec1[RB_LAM]; p[11] = rec1[RB_LAM + 1]; p[12] = rec1[RB_LAM + 2];
   }
   if (lane == 0) {
     int32_t* st = W.solver_stats + (size_t)e * 4;
-    st[0] = C * (1 + P.friction_dirs); st[1] = ncolours; st[2] = iters; st[3] = C;
+    st[0] = C * nrows; st[1] = ncolours; st[2] = iters; st[3] = C;
   }
   __syncwarp();
   bool bad = false;
   for (int i = lane; i < nm; i += 32) {
     const float* b = S.body + (Ns + L + i) * BODY_STRIDE;
-    V3 ang = LD3(b + BO_ANG), vel = LD3(b + BO_VEL);
-    float wl = len(ang);
-    if (wl * dt > B2S_HALF_PI) ang = ang * (B2S_HALF_PI / (wl * dt));
-    V3 pos = LD3(b + BO_POS) + vel * dt;
-    Q4 qq = q_integrate(q4(b[BO_QUAT], b[BO_QUAT + 1], b[BO_QUAT + 2], b[BO_QUAT + 3]), ang, dt);
+    V3 ang_ = LD3(b + BO_ANG), vel_ = LD3(b + BO_VEL);
+    float wl = len(ang_);
+    if (wl * dt > B2S_HALF_PI) ang_ = ang_ * (B2S_HALF_PI / (wl * dt));
+    V3 pos = LD3(b + BO_POS) + vel_ * dt;
+    Q4 qq = q_integrate(q4(b[BO_QUAT], b[BO_QUAT + 1], b[BO_QUAT + 2], b[BO_QUAT + 3]), ang_, dt);
     BS(0, i) = pos.x; BS(1, i) = pos.y; BS(2, i) = pos.z;
     BS(3, i) = qq.x; BS(4, i) = qq.y; BS(5, i) = qq.z; BS(6, i) = qq.w;
-    BS(7, i) = vel.x; BS(8, i) = vel.y; BS(9, i) = vel.z;
-    BS(10, i) = ang.x; BS(11, i) = ang.y; BS(12, i) = ang.z;
+    BS(7, i) = vel_.x; BS(8, i) = vel_.y; BS(9, i) = vel_.z;
+    BS(10, i) = ang_.x; BS(11, i) = ang_.y; BS(12, i) = ang_.z;
     float chk = (pos.x + pos.y) + pos.z;
     if (!(fabsf(chk) < 1e6f)) bad = true;
   }
@@ -1401,7 +1399,6 @@ __device__ __noinline__ void substep_post(int e, int lane, int wib, int C, int n
 // record of one contact, in float4 units: row r at [4r .. 4r+3] =
 //   (dir.xyz, angA.x) (angA.yz, iangA.xy) (iangA.z, 1/d, d, k1) (k2, imA, bias0 | mu, imB)
 // then, as scalars from word 48, angB.xyz iangB.xyz of every row (only read for a dynamic body B)
-#define RR_B 48
 #define RR_WORDS 68                     // per contact (272 B, 16-byte aligned)
 #define SOLVE_T_WORDS 512               // byte table [64 colours][32 slots] in the warp's `con` scratch
 #define SOLVE_LAM (SOLVE_T_WORDS)       // float lambda [3][32], the B lane's copy of it [3][32], slotA [32], slotB [32]
@@ -1813,7 +1810,7 @@ __device__ __noinline__ void finish_action(int e, int lane) {
 // Hand-out of environments inside a stage: dynamic (shared counter) when the solver rows live in registers;
 // with rows in per-warp shared memory an environment must stay with one warp for the whole substep.
 __device__ __forceinline__ int grab_slot(int* counter, int lane, int wib, int E, bool first) {
-  if (!W.reg_rows) return first ? wib : E;
+  (void)wib; (void)first;
   int slot = 0;
   if (lane == 0) slot = atomicAdd(counter, 1);
   return __shfl_sync(FULL, slot, 0);
@@ -1911,7 +1908,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       const int sw = slot | (wib << 16);
       const int ph = (mode == MODE_ENV) ? W.phase[e] : B2S_PHASE_IDLE;
       if (W.reg_rows) substep_post_reg(e, lane, sw, meta[META_C], meta[META_NEWN]);
-      else substep_post(e, lane, sw, meta[META_C], meta[META_NEWN]);
+      else substep_post_big(e, lane, sw, meta[META_C], meta[META_NEWN]);
       ++done_steps;
       bool nxt = (s + 1 < n);
       if (mode == MODE_ENV) {
