@@ -1154,7 +1154,9 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
 // contact's bodies from a small shared array instead of shuffling them out of the contact lanes.  The row
 // arithmetic, the colouring rule and the sweep order are the oracle's, so results are bit-identical.
 // (This path replaced a contact-per-lane solver with all rows in shared memory: 50 KB per warp, i.e. 4 warps
-// per SM on config #3, whose solve stage took 76 % of the substep.)
+// per SM on config #3, whose solve stage took 76 % of the substep.  Measured on config #3, 4096 envs x 50 substeps:
+// 470 ms -> 305 ms; the sweeps are still 60 % of the warp time there (~1 500 cycles per colour step: the records of
+// 16 warps, 580 KB, do not fit the L1 the block leaves; prefetching them three colours ahead changed nothing).)
 #define RR_B 48                          // word offset of angB/iangB in a contact record (both body-centric paths)
 #define RB_WORDS 76                      // record: rows [0,48) as in substep_post_reg, angB/iangB [48,66), lambda [66,69),
 #define RB_LAM 66                        //   the B lane's lambda [69,72), movable index of A | B << 8 | flags at 72
@@ -1175,6 +1177,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
   unsigned short* cinfo = (unsigned short*)(S.con + 1024);    // [C] movable of A (31 = none) | movable of B << 5 | dA << 10 | dB << 11
   unsigned char* ccol = (unsigned char*)(S.con + 1024 + (P.max_contacts + 1) / 2);   // [C] colour, 0xff = none
   const int mov0 = Ns + L;
+  PROF_SEC0()
   __syncwarp();
   // rows, 32 contacts at a time
   for (int c0 = 0; c0 < C; c0 += 32) {
@@ -1234,6 +1237,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
     }
   }
   __syncwarp();
+  PROF_SEC(0)
   // greedy colouring in contact order; lane i keeps the colour mask of movable i
   unsigned long long used = 0ull;
   int ncolours = 0;
@@ -1270,6 +1274,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
     for (unsigned mm = __ballot_sync(FULL, cplk != 0xffu); mm; mm &= mm - 1) coupled |= 1ull << __shfl_sync(FULL, cplk, __ffs(mm) - 1);
   }
   __syncwarp();
+  PROF_SEC(1)
   // ---- sweeps: lane = movable index
   const bool dyn = lane < nm;
   float* myb = S.body + (mov0 + (dyn ? lane : 0)) * BODY_STRIDE;
@@ -1328,22 +1333,58 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
       }                                                                                                           \
     }                                                                                                             \
   }
-#pragma unroll 1
-  for (int k = 0; k < ncolours; ++k) BIG_STEP(0)
-  __syncwarp();
+  // a colour without a contact between two dynamic bodies (the rule) takes the A-side-only step
+#define BIG_FAST(PASS)                                                                                            \
+  {                                                                                                               \
+    const unsigned t = dyn ? (unsigned)T[k * 32 + lane] : 0xffffu;                                                \
+    if (t != 0xffffu) {                                                                                           \
+      float* rec1 = rr + (size_t)(t & 0x3fff) * RB_WORDS;                                                         \
+      const float4* rec = (const float4*)rec1;                                                                    \
+      float* ml = rec1 + RB_LAM;                                                                                  \
+      float lim = 0.0f;                                                                                           \
+      if (PASS == 2) lim = rec[7].z * ml[0];                                                                      \
+      _Pragma("unroll")                                                                                           \
+      for (int r = (PASS == 2) ? 1 : 0; r < ((PASS == 1) ? 1 : 3); ++r) {                                         \
+        if (r >= nrows) break;                                                                                    \
+        const float4 q0 = rec[r * 4], q1 = rec[r * 4 + 1], q2 = rec[r * 4 + 2], q3 = rec[r * 4 + 3];              \
+        const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
+        const float l = ml[r];                                                                                    \
+        float dl = l;                                                                                             \
+        if (PASS != 0) {                                                                                          \
+          const float jv = ((dot(dir, vel) + dot(angA, ang)) - q2.w) - q3.x;                                      \
+          dl = (((PASS == 1) ? q3.z : 0.0f) - jv) * q2.y;                                                         \
+          float nl = l + dl;                                                                                      \
+          nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
+          dl = nl - l;                                                                                            \
+          ml[r] = nl;                                                                                             \
+          const float res = dl * q2.z;                                                                            \
+          maxres = fmaxf(maxres, res * res);                                                                      \
+        }                                                                                                         \
+        vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                              \
+      }                                                                                                           \
+    }                                                                                                             \
+  }
+#define BIG_PASS(PASS)                                                                                            \
+  {                                                                                                               \
+    _Pragma("unroll 1")                                                                                           \
+    for (int k = 0; k < ncolours; ++k) {                                                                          \
+      if ((coupled >> k) & 1ull) BIG_STEP(PASS) else BIG_FAST(PASS)                                               \
+    }                                                                                                             \
+    __syncwarp();                                                                                                 \
+  }
+  BIG_PASS(0)
   for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
     maxres = 0.0f;
-#pragma unroll 1
-    for (int k = 0; k < ncolours; ++k) BIG_STEP(1)
-    __syncwarp();
-#pragma unroll 1
-    for (int k = 0; k < ncolours; ++k) BIG_STEP(2)
-    __syncwarp();
+    BIG_PASS(1)
+    BIG_PASS(2)
     iters = it + 1;
     unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
     if (__uint_as_float(mx) <= P.residual_threshold) break;
   }
+#undef BIG_PASS
+#undef BIG_FAST
 #undef BIG_STEP
+  PROF_SEC(2)
   if (dyn) { ST3(myb + BO_VEL, vel); ST3(myb + BO_ANG, ang); }
   __syncwarp();
   for (int c = lane; c < C; c += 32) {
@@ -1380,6 +1421,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
   __syncwarp();
   if (lane == 0) W.num_steps[e] += 1;
   __syncwarp();
+  PROF_SEC(3)
   (void)newn;
 }
 
