@@ -74,11 +74,11 @@ struct DLayout {
 // A warp may pick up any environment of its block in any stage, so everything that has to survive from
 // one stage to the next (body table, colliders, pair list, contact list) is per environment; GJK, manifold
 // staging, FK scratch and the B-side row data are per warp.  `con` aliases the narrow-phase scratch
-// (oldkeys .. simplex): rows are only alive in the solve stage.  The EPA polytope (rare path, 4 KB per
+// (stage .. simplex): the solve-stage tables are only alive in the solve stage.  The EPA polytope (rare path, 4 KB per
 // warp) lives in global memory so that the block leaves more of the SM's 256 KB to the L1 cache.
 struct SmemLayout {
   int body, col, pairs, cmk, words_env;                        // per environment
-  int oldkeys, con, stage, fk, simplex, words_warp;            // per warp: scratch
+  int con, stage, fk, simplex, words_warp;                     // per warp: scratch
 };
 #define META_ACTIVE 0
 #define META_NP 1
@@ -146,6 +146,7 @@ struct DWorld {
   float* epa_scratch;             // [blocks][warps][EP_WORDS] EPA polytope (rare path: lives in L2, not in shared memory)
   int32_t* env_map;               // [blocks][E] environment stepped in a block slot (-1 none), re-dealt before every launch
   unsigned long long* prof;       // [8] stage timing counters (only written by -DB2S_PROF builds)
+  float* pair_stage;              // [blocks][E][max_pairs][68] narrow-phase result of every candidate pair of the substep
   float* row_scratch;             // [blocks][warps][32][68] solver rows of the environment a warp is solving (L1/L2 resident)
   SmemLayout sm;
   int max_ray_planes;    // raster: upper bound of hull face planes / hulls in one environment

@@ -75,7 +75,7 @@ __device__ __forceinline__ Xf xf_mul(Xf a, Xf b) { Xf t; t.p = a.p + qrot(a.q, b
 __device__ __forceinline__ void xf_store(Xf t, float* o) { o[0] = t.p.x; o[1] = t.p.y; o[2] = t.p.z; o[3] = t.q.x; o[4] = t.q.y; o[5] = t.q.z; o[6] = t.q.w; }
 
 struct WarpSmem {
-  float* body; float* col; int* pairs; int* oldkeys; int* cmk; float* con; float* stage; float* fk; float* sx;
+  float* body; float* col; int* pairs; int* cmk; float* con; float* stage; float* fk; float* sx;
 };
 
 // `sw` packs (environment slot of the block) | (warp in block) << 16
@@ -89,7 +89,7 @@ __device__ __forceinline__ WarpSmem carve(int sw) {
   float* wb = b2s_smem + (size_t)W.envs_per_block * W.sm.words_env + (size_t)(sw >> 16) * W.sm.words_warp;
   WarpSmem s;
   s.body = eb + W.sm.body; s.col = eb + W.sm.col; s.pairs = (int*)(eb + W.sm.pairs); s.cmk = (int*)(eb + W.sm.cmk);
-  s.oldkeys = (int*)(wb + W.sm.oldkeys); s.con = wb + W.sm.con;
+  s.con = wb + W.sm.con;
   s.stage = wb + W.sm.stage; s.fk = wb + W.sm.fk; s.sx = wb + W.sm.simplex;
   return s;
 }
@@ -1007,126 +1007,153 @@ __device__ __noinline__ int stage_scene(int e, int lane, int wib) {
   return np;
 }
 
-// stage B: narrow phase + persistent manifolds (ping-pong buffers in HBM/L2) -> contact list
-__device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int* nc_out, int* newn_out, bool build_rows) {
+// stage B: narrow phase + persistent manifolds (ping-pong buffers in HBM/L2) -> contact list.
+// The unit of work is one candidate PAIR of one environment (any warp of the block takes any pair): refresh of the
+// pair's cached manifold, GJK/EPA, manifold update.  The result goes to a staging record of the pair; the warp
+// that later solves the environment (stage C) merges the records in pair order into the new side of the
+// ping-pong buffers, which reproduces the oracle's sequential compaction exactly.  With environments as the
+// unit, a block with few active environments -- the last 11 of the 24 launches of a bench step carry < 6 % of
+// the environments -- spent 3-4 pairs' worth of latency in this stage; now it is one pair's worth.
+#define PS_WORDS 68                      // staging record: the manifold (64 words, GJK cache in 13..15), point count at 64
+__device__ __forceinline__ float* pair_stage(int sw, int p) {
+  return W.pair_stage + (((size_t)blockIdx.x * W.envs_per_block + (sw & 0xffff)) * W.P.max_pairs + p) * PS_WORDS;
+}
+
+__device__ __noinline__ void stage_narrow_pair(int e, int lane, int wib, int p) {
   const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
-  const float dt = (float)P.time_step;
   const unsigned lt = (1u << lane) - 1u;
   const int M = P.max_manifolds;
   const int par = W.man_parity[e];
-  const size_t obase = ((size_t)par * W.B + e) * M, nbase = ((size_t)(par ^ 1) * W.B + e) * M;
+  const size_t obase = ((size_t)par * W.B + e) * M;
   const int old_n = W.num_manifolds[e];
-  for (int k = lane; k < old_n; k += 32) S.oldkeys[k] = W.man_keys[obase + k];
-  __syncwarp();
-  int newn = 0, ncon = 0, cflags = 0;
-  bool man_over = false, con_over = false;
   float* stg = S.stage;   // [4][16]
   PROF_SEC0()
   float* epa_scr = W.epa_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * EP_WORDS;
+  const int key = S.pairs[p];
+  const int a = key >> 16, b = key & 0xffff;
+  ColRef A = col_ref(S.col, S.body, a), Bc = col_ref(S.col, S.body, b);
+  const float* ca = S.col + a * COL_STRIDE;
+  const float* cb = S.col + b * COL_STRIDE;
+  const float threshold = P.breaking_factor * fminf(ca[CO_RAD], cb[CO_RAD]);
+  // old manifold lookup
+  int found = 0x7fffffff;
+  for (int k = lane; k < old_n; k += 32) if (W.man_keys[obase + k] == key) found = min(found, k);
+  found = (int)__reduce_min_sync(FULL, (unsigned)found);
+  int n = 0;
+  __syncwarp();
+  if (found != 0x7fffffff) {
+    n = W.man_npts[obase + found];
+    const float* src = W.man_pts + (obase + found) * 4 * B2S_CP_FLOATS;
+    const float s0 = src[lane];
+    stg[lane] = s0; stg[lane + 32] = src[lane + 32];
+    if (lane >= 13 && lane < 16) S.sx[SX_CACHE + lane - 13] = s0;      // GJK simplex of the previous substep
+  } else if (lane < 3) S.sx[SX_CACHE + lane] = __int_as_float(0);
+  __syncwarp();
+  // refresh (one point per lane), compaction keeps the order
+  {
+    float pt[B2S_CP_FLOATS];
+    bool keep = false;
+    if (lane < n) {
+#pragma unroll
+      for (int t = 0; t < B2S_CP_FLOATS; ++t) pt[t] = stg[lane * B2S_CP_FLOATS + t];
+      V3 wA = cr_pos(A) + mmul(cr_R(A), v3(pt[0], pt[1], pt[2]));
+      V3 wB = cr_pos(Bc) + mmul(cr_R(Bc), v3(pt[3], pt[4], pt[5]));
+      V3 nn = v3(pt[6], pt[7], pt[8]);
+      float dist = dot(wA - wB, nn);
+      if (!(dist > threshold)) {
+        V3 proj = wA - nn * dist;
+        V3 dd = wB - proj;
+        if (!(len2(dd) > threshold * threshold)) { keep = true; pt[9] = dist; }
+      }
+    }
+    unsigned km = __ballot_sync(FULL, keep);
+    __syncwarp();
+    if (keep) {
+      int dst = __popc(km & lt);
+#pragma unroll
+      for (int t = 0; t < B2S_CP_FLOATS; ++t) stg[dst * B2S_CP_FLOATS + t] = pt[t];
+    }
+    n = __popc(km);
+    __syncwarp();
+  }
+  PROF_SEC(4)
+  V3 pA, pB, nrm;
+  float dist;
+  const int hit_ = collide_pair(A, Bc, threshold, S.sx, epa_scr, &pA, &pB, &nrm, &dist, lane);
+  PROF_SEC(5)
+  if (hit_) {
+    V3 lA = mtmul(cr_R(A), pA - cr_pos(A));
+    V3 lB = mtmul(cr_R(Bc), pB - cr_pos(Bc));
+    // manifold_add (uniform decisions, lane 0 writes)
+    int nearest = -1;
+    float shortest = threshold * threshold;
+    for (int k = 0; k < n; ++k) {
+      V3 d = LD3(stg + k * B2S_CP_FLOATS) - lA;
+      float dd = len2(d);
+      if (dd < shortest) { shortest = dd; nearest = k; }
+    }
+    int idx; bool keepl = false;
+    if (nearest >= 0) { idx = nearest; keepl = true; }
+    else if (n < 4) { idx = n; n = n + 1; }
+    else {
+      V3 PP[4]; float DD[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { PP[k] = LD3(stg + k * B2S_CP_FLOATS); DD[k] = stg[k * B2S_CP_FLOATS + 9]; }
+      idx = b2s_manifold_replace_index(PP, DD, lA, dist);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      float* pp = stg + idx * B2S_CP_FLOATS;
+      pp[0] = lA.x; pp[1] = lA.y; pp[2] = lA.z; pp[3] = lB.x; pp[4] = lB.y; pp[5] = lB.z;
+      pp[6] = nrm.x; pp[7] = nrm.y; pp[8] = nrm.z; pp[9] = dist;
+      if (!keepl) { pp[10] = 0.0f; pp[11] = 0.0f; pp[12] = 0.0f; }
+      pp[13] = 0.0f; pp[14] = 0.0f; pp[15] = 0.0f;
+    }
+    __syncwarp();
+  }
+  float* dst = pair_stage(wib, p);
+  if (n > 0) {
+    dst[lane] = (lane >= 13 && lane < 16) ? S.sx[SX_CACHE + lane - 13] : ((lane < n * B2S_CP_FLOATS) ? stg[lane] : 0.0f);
+    dst[lane + 32] = (lane + 32 < n * B2S_CP_FLOATS) ? stg[lane + 32] : 0.0f;
+  }
+  if (lane == 0) dst[64] = __int_as_float(n);
+  __syncwarp();
+  PROF_SEC(6)
+}
+
+// merge of the staged pairs of one environment, in pair order (start of stage C, by the warp that solves it)
+__device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np, int* nc_out, int* newn_out) {
+  const WarpSmem S = carve(wib);
+  const B2SParams& P = W.P;
+  const int M = P.max_manifolds;
+  const int par = W.man_parity[e];
+  const size_t nbase = ((size_t)(par ^ 1) * W.B + e) * M;
+  int newn = 0, ncon = 0, cflags = 0;
+  bool man_over = false, con_over = false;
+  PROF_SEC0()
   for (int p = 0; p < np; ++p) {
-    const int key = S.pairs[p];
-    const int a = key >> 16, b = key & 0xffff;
-    ColRef A = col_ref(S.col, S.body, a), Bc = col_ref(S.col, S.body, b);
-    const float* ca = S.col + a * COL_STRIDE;
-    const float* cb = S.col + b * COL_STRIDE;
-    const float threshold = P.breaking_factor * fminf(ca[CO_RAD], cb[CO_RAD]);
-    const int sA = __float_as_int(ca[CO_SLOT]), sB = __float_as_int(cb[CO_SLOT]);
-    // old manifold lookup
-    int found = 0x7fffffff;
-    for (int k = lane; k < old_n; k += 32) if (S.oldkeys[k] == key) found = min(found, k);
-    found = (int)__reduce_min_sync(FULL, (unsigned)found);
-    int n = 0;
-    __syncwarp();
-    if (found != 0x7fffffff) {
-      n = W.man_npts[obase + found];
-      const float* src = W.man_pts + (obase + found) * 4 * B2S_CP_FLOATS;
-      const float s0 = src[lane];
-      stg[lane] = s0; stg[lane + 32] = src[lane + 32];
-      if (lane >= 13 && lane < 16) S.sx[SX_CACHE + lane - 13] = s0;      // GJK simplex of the previous substep
-    } else if (lane < 3) S.sx[SX_CACHE + lane] = __int_as_float(0);
-    __syncwarp();
-    // refresh (one point per lane), compaction keeps the order
-    {
-      float pt[B2S_CP_FLOATS];
-      bool keep = false;
-      if (lane < n) {
-#pragma unroll
-        for (int t = 0; t < B2S_CP_FLOATS; ++t) pt[t] = stg[lane * B2S_CP_FLOATS + t];
-        V3 wA = cr_pos(A) + mmul(cr_R(A), v3(pt[0], pt[1], pt[2]));
-        V3 wB = cr_pos(Bc) + mmul(cr_R(Bc), v3(pt[3], pt[4], pt[5]));
-        V3 nn = v3(pt[6], pt[7], pt[8]);
-        float dist = dot(wA - wB, nn);
-        if (!(dist > threshold)) {
-          V3 proj = wA - nn * dist;
-          V3 dd = wB - proj;
-          if (!(len2(dd) > threshold * threshold)) { keep = true; pt[9] = dist; }
-        }
+    const float* src = pair_stage(wib, p);
+    const int n = __float_as_int(src[64]);
+    if (n <= 0) continue;
+    if (newn < M) {
+      const int key = S.pairs[p];
+      const float* ca = S.col + (key >> 16) * COL_STRIDE;
+      const float* cb = S.col + (key & 0xffff) * COL_STRIDE;
+      float* dst = W.man_pts + (nbase + newn) * 4 * B2S_CP_FLOATS;
+      dst[lane] = src[lane];
+      dst[lane + 32] = src[lane + 32];
+      if (lane == 0) { W.man_keys[nbase + newn] = key; W.man_npts[nbase + newn] = n; }
+      const int tA = __float_as_int(ca[CO_TYPE]) & 255, tfB = __float_as_int(cb[CO_TYPE]);
+      const int tB = tfB & 255;
+      if (tA == B2S_TYPE_KINEMATIC && ((tfB >> 8) & B2S_STATIC_IS_TABLE)) cflags |= 1;
+      if (tA == B2S_TYPE_DYNAMIC && tB == B2S_TYPE_KINEMATIC) cflags |= 2;
+      if (tA == B2S_TYPE_DYNAMIC || tB == B2S_TYPE_DYNAMIC) {
+        if (lane < n) { if (ncon + lane < P.max_contacts) S.cmk[ncon + lane] = (newn << 2) | lane; }
+        if (ncon + n > P.max_contacts) { con_over = true; ncon = P.max_contacts; } else ncon += n;
       }
-      unsigned km = __ballot_sync(FULL, keep);
-      __syncwarp();
-      if (keep) {
-        int dst = __popc(km & lt);
-#pragma unroll
-        for (int t = 0; t < B2S_CP_FLOATS; ++t) stg[dst * B2S_CP_FLOATS + t] = pt[t];
-      }
-      n = __popc(km);
-      __syncwarp();
-    }
-    PROF_SEC(4)
-    V3 pA, pB, nrm;
-    float dist;
-    const int hit_ = collide_pair(A, Bc, threshold, S.sx, epa_scr, &pA, &pB, &nrm, &dist, lane);
-    PROF_SEC(5)
-    if (hit_) {
-      V3 lA = mtmul(cr_R(A), pA - cr_pos(A));
-      V3 lB = mtmul(cr_R(Bc), pB - cr_pos(Bc));
-      // manifold_add (uniform decisions, lane 0 writes)
-      int nearest = -1;
-      float shortest = threshold * threshold;
-      for (int k = 0; k < n; ++k) {
-        V3 d = LD3(stg + k * B2S_CP_FLOATS) - lA;
-        float dd = len2(d);
-        if (dd < shortest) { shortest = dd; nearest = k; }
-      }
-      int idx; bool keepl = false;
-      if (nearest >= 0) { idx = nearest; keepl = true; }
-      else if (n < 4) { idx = n; n = n + 1; }
-      else {
-        V3 PP[4]; float DD[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { PP[k] = LD3(stg + k * B2S_CP_FLOATS); DD[k] = stg[k * B2S_CP_FLOATS + 9]; }
-        idx = b2s_manifold_replace_index(PP, DD, lA, dist);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        float* pp = stg + idx * B2S_CP_FLOATS;
-        pp[0] = lA.x; pp[1] = lA.y; pp[2] = lA.z; pp[3] = lB.x; pp[4] = lB.y; pp[5] = lB.z;
-        pp[6] = nrm.x; pp[7] = nrm.y; pp[8] = nrm.z; pp[9] = dist;
-        if (!keepl) { pp[10] = 0.0f; pp[11] = 0.0f; pp[12] = 0.0f; }
-        pp[13] = 0.0f; pp[14] = 0.0f; pp[15] = 0.0f;
-      }
-      __syncwarp();
-    }
-    if (n > 0) {
-      if (newn < M) {
-        float* dst = W.man_pts + (nbase + newn) * 4 * B2S_CP_FLOATS;
-        dst[lane] = (lane >= 13 && lane < 16) ? S.sx[SX_CACHE + lane - 13] : ((lane < n * B2S_CP_FLOATS) ? stg[lane] : 0.0f);
-        dst[lane + 32] = (lane + 32 < n * B2S_CP_FLOATS) ? stg[lane + 32] : 0.0f;
-        if (lane == 0) { W.man_keys[nbase + newn] = key; W.man_npts[nbase + newn] = n; }
-        const int tA = __float_as_int(ca[CO_TYPE]) & 255, tfB = __float_as_int(cb[CO_TYPE]);
-        const int tB = tfB & 255;
-        if (tA == B2S_TYPE_KINEMATIC && ((tfB >> 8) & B2S_STATIC_IS_TABLE)) cflags |= 1;
-        if (tA == B2S_TYPE_DYNAMIC && tB == B2S_TYPE_KINEMATIC) cflags |= 2;
-        if (tA == B2S_TYPE_DYNAMIC || tB == B2S_TYPE_DYNAMIC) {
-          if (lane < n) { if (ncon + lane < P.max_contacts) S.cmk[ncon + lane] = (newn << 2) | lane; }
-          if (ncon + n > P.max_contacts) { con_over = true; ncon = P.max_contacts; } else ncon += n;
-        }
-        ++newn;
-      } else man_over = true;
-    }
-    (void)sA; (void)sB;
-    PROF_SEC(6)
+      ++newn;
+    } else man_over = true;
   }
   __syncwarp();
   for (int k = newn + lane; k < M; k += 32) { W.man_keys[nbase + k] = -1; W.man_npts[nbase + k] = 0; }
@@ -1138,8 +1165,6 @@ __device__ __noinline__ void stage_narrow(int e, int lane, int wib, int np, int*
     if (ef) W.error_flags[e] |= ef;
   }
   __syncwarp();
-
-  (void)build_rows; (void)dt;
   PROF_SEC(7)
   *nc_out = ncon;
   *newn_out = newn;
@@ -1858,6 +1883,31 @@ __device__ __forceinline__ int grab_slot(int* counter, int lane, int wib, int E,
   return __shfl_sync(FULL, slot, 0);
 }
 
+// Next candidate pair of the block: unit u of the concatenated pair lists of the active environments.
+// Returns the environment slot (-1: none left) and the pair index in *p_out.
+__device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_out) {
+  int u = 0;
+  if (lane == 0) u = atomicAdd(counter, 1);
+  u = __shfl_sync(FULL, u, 0);
+  int base = 0;
+  for (int s0 = 0; s0 < E; s0 += 32) {
+    const int slot = s0 + lane;
+    int cnt = 0;
+    if (slot < E) { const int* m = env_meta(slot); if (m[META_ACTIVE]) cnt = m[META_NP]; }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (u < base + total) {
+      const int l = __ffs(__ballot_sync(FULL, u < base + incl)) - 1;
+      *p_out = u - base - __shfl_sync(FULL, incl - cnt, l);
+      return s0 + l;
+    }
+    base += total;
+  }
+  return -1;
+}
+
 // Block = Wn warps stepping E environments.  Every substep runs three stages separated by block barriers
 // (scene -> narrow phase -> solve/integrate/phase logic); inside a stage the warps take environments from
 // a shared counter, so a warp stuck on a long solve does not hold the others back, and all warps of the
@@ -1921,16 +1971,12 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     __syncthreads();
     PROF_MARK(0)
     if (threadIdx.x == 0) s_cnt[0] = 0;
-    // ---- stage B: narrow phase + manifolds
+    // ---- stage B: narrow phase, one candidate pair per grab
     for (;;) {
-      const int slot = grab_slot(&s_cnt[1], lane, wib, E, first1);
-      first1 = false;
-      if (slot >= E) break;
-      int* meta = env_meta(slot);
-      if (!meta[META_ACTIVE]) continue;
-      int C = 0, newn = 0;
-      stage_narrow(meta[META_ENV], lane, slot | (wib << 16), meta[META_NP], &C, &newn, !W.reg_rows);
-      if (lane == 0) { meta[META_C] = C; meta[META_NEWN] = newn; }
+      int pp = 0;
+      const int slot = grab_pair(&s_cnt[1], lane, E, &pp);
+      if (slot < 0) break;
+      stage_narrow_pair(env_meta(slot)[META_ENV], lane, slot | (wib << 16), pp);
     }
     PROF_STAGE(1)
     __syncthreads();
@@ -1949,8 +1995,10 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       const int e = meta[META_ENV];
       const int sw = slot | (wib << 16);
       const int ph = (mode == MODE_ENV) ? W.phase[e] : B2S_PHASE_IDLE;
-      if (W.reg_rows) substep_post_reg(e, lane, sw, meta[META_C], meta[META_NEWN]);
-      else substep_post_big(e, lane, sw, meta[META_C], meta[META_NEWN]);
+      int C = 0, newn = 0;
+      stage_narrow_merge(e, lane, sw, meta[META_NP], &C, &newn);
+      if (W.reg_rows) substep_post_reg(e, lane, sw, C, newn);
+      else substep_post_big(e, lane, sw, C, newn);
       ++done_steps;
       bool nxt = (s + 1 < n);
       if (mode == MODE_ENV) {
