@@ -417,7 +417,10 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
   __syncthreads();
   // blocks of the expensive class: one environment per warp; bounded by what the other blocks can still take
   int Hb = 0;
-  if (E > Wn && nblocks > 1) {
+  // (only when the stepping environments need more than one wave per block anyway: a sparse launch -- the tail of
+  // a batched PushEnv.step -- is fastest with the environments spread one per block)
+  const int stepping = W.B - hist[255];
+  if (E > Wn && nblocks > 1 && stepping > nblocks * Wn) {
     const int hb_max = (nblocks * E - W.B) / (E - Wn);
     Hb = min(min((s_heavy + Wn - 1) / Wn, hb_max), nblocks - 1);
     if (Hb < 0) Hb = 0;
