@@ -7,17 +7,19 @@
 // persistent manifolds, PGS contact/friction solve, integration) and the PushEnv
 // phase machine (push_env.py:631-937).
 //
-// Design: a warp owns one environment for the whole launch and loops over the
-// requested substeps with every intermediate (body table, collider AABBs, pair
-// list, contact rows) in its slice of shared memory; only the persistent state
-// (13 floats per movable, 14 per arm, the <=4-point manifolds) goes back to HBM.
-// Lanes split the work inside a stage: one hull vertex per lane in the GJK/EPA
-// support function (exact warp max via redux on order-preserving keys), one
-// collider per lane for AABBs, ballot-compacted pair lists, one contact per lane
-// for Jacobian rows, and the PGS sweep runs one colour of body-disjoint contacts
-// per step so Gauss-Seidel order is preserved exactly.  The residual test is a
-// warp reduce.  All fp32 arithmetic is ordered exactly as in oracle/ (no FMA
-// contraction) so integer outputs match bit for bit.
+// Design: one environment is stepped by one warp at a time.  A block of 16 warps owns up to E environments (dealt
+// to the blocks before every launch, k_assign_envs) and advances them in lock-step rounds of three stages
+// separated by block barriers -- scene (controller, FK, body table, AABBs, broad phase), narrow phase, solve +
+// integration + phase machine -- with dynamic hand-out of the work inside a stage: environments in the first and
+// the last stage, single candidate PAIRS in the narrow phase.  All per-substep intermediates (body table,
+// collider AABBs, pair list, contact list) live in the block's shared memory; only the persistent state (13
+// floats per movable, 14 per arm, the <=4-point manifolds) goes back to HBM/L2.  Lanes split the work inside a
+// unit: one hull vertex per lane in the GJK/EPA support function (exact warp max via redux on order-preserving
+// keys), one collider per lane for AABBs, ballot-compacted pair lists, one contact per lane for Jacobian rows
+// and colouring, one BODY per lane in the Gauss-Seidel sweeps (velocities in registers), which run the oracle's
+// colour order exactly.  The residual test is a warp reduce.  All fp32 arithmetic is ordered exactly as in
+// oracle/ (no FMA contraction), so every output matches bit for bit.  Why stages and barriers at all when the
+// environments never interact: the kernel is ~10x the instruction cache, see the note above k_substeps.
 #include "b2s_dev.cuh"
 
 #define LD3(p) v3((p)[0], (p)[1], (p)[2])
