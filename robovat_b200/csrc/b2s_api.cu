@@ -286,9 +286,9 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   sm.words_env = o;
   o = 0;
   const int x0 = o;                 // region shared by the narrow-phase scratch and the solver rows
-  sm.stage = take(4 * B2S_CP_FLOATS);
+  sm.stage = take(4 * B2S_CP_FLOATS * UNITS_PER_WARP);
   sm.fk = take(FK_WORDS);
-  sm.simplex = take(48);
+  sm.simplex = take(48 * UNITS_PER_WARP);
   sm.con = x0;
   // solve-stage scratch: small path = colour table (bytes) + lambda x2 + slots; big path = colour table (16 bit) +
   // bodies and colour of every contact
@@ -320,7 +320,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     if (P.reserved_i[0] <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7));
     d.envs_per_block = E;
     const size_t blocks = d.num_blocks;
-    if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
+    if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * UNITS_PER_WARP * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
     if ((rc = dalloc(w, &d.pair_stage, blocks * (size_t)E * P.max_pairs * 68, 0))) return rc;
     if ((rc = dalloc(w, &d.env_map, blocks * (size_t)E, 0xff))) return rc;
     if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)std::max(32 * 68, P.max_contacts * 76), 0))) return rc;

@@ -27,6 +27,27 @@ typedef b2s_m3 M3;
 #define B2S_TYPE_KINEMATIC 1
 #define B2S_TYPE_DYNAMIC 2
 
+// narrow-phase unit: the lanes that work on one candidate pair.  B2S_HALF = log2(units per warp): 0 = the whole warp
+// on one pair, 1 = two pairs of 16 lanes, 2 = four pairs of 8 lanes.  Hulls have 8..64 vertices and most of GJK is
+// uniform simplex arithmetic, so narrow units waste fewer lanes; the halves diverge only where their pairs differ.
+#ifndef B2S_HALF
+#define B2S_HALF 1
+#endif
+#if B2S_HALF
+#define UW (32 >> B2S_HALF)
+#define UL (lane & (UW - 1))
+#define UB (lane & ~(UW - 1))
+#define UM ((0xffffffffu >> (32 - UW)) << UB)
+#define UH (lane / UW)
+#define UNITS_PER_WARP (1 << B2S_HALF)
+#else
+#define UW 32
+#define UL lane
+#define UB 0
+#define UM FULL
+#define UH 0
+#define UNITS_PER_WARP 1
+#endif
 #define EPA_MAXV 32
 #define EPA_MAXF 96
 #define FULL 0xffffffffu

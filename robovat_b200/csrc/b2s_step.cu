@@ -341,6 +341,12 @@ __device__ void arm_set_joint_target(int e, int lane, const float* q) {
 }
 
 // -------------------------------------------------------------- support ----
+// Narrow-phase units.  A unit (one candidate pair) is processed by UW consecutive lanes: the whole warp, or with
+// -DB2S_HALF=1 a half warp, so that one warp works on two pairs at once (the support function of an 8-vertex
+// box keeps 8 lanes busy either way; everything else in GJK/EPA is scalar work replicated on the lanes).
+// UL = lane within the unit, UB = first lane of the unit, UM = member mask of the unit, UH = unit index in the warp.
+// unit macros (UW, UL, UB, UM, UH): b2s_dev.cuh
+
 
 // pose of the collider's body is read from the shared body table through `b` (broadcast LDS): keeping pos/R
 // in the struct made it 20 words, which the compiler parked in local memory around the noinline EPA calls
@@ -360,26 +366,22 @@ __device__ __forceinline__ ColRef col_ref(const float* col, const float* body, i
   return r;
 }
 
-// argmax_i v_i . d over the hull's vertices (first maximum), one or two vertices per lane
+// argmax_i v_i . d over the hull's vertices (first maximum), vertices dealt round-robin to the unit's lanes
 __device__ __forceinline__ int support(const ColRef& c, V3 d, V3* p, int lane) {
   const M3 R = cr_R(c);
   V3 dl = mtmul(R, d);
   float best = 0.0f;
   int bi = 0x7fffffff;
   bool has = false;
-  if (lane < c.vcnt) {
-    float4 v = __ldg(W.verts + c.voff + lane);
-    best = dot(v3(v.x, v.y, v.z), dl); bi = lane; has = true;
-  }
-  if (lane + 32 < c.vcnt) {
-    float4 v = __ldg(W.verts + c.voff + lane + 32);
+  for (int i = UL; i < c.vcnt; i += UW) {
+    float4 v = __ldg(W.verts + c.voff + i);
     float t = dot(v3(v.x, v.y, v.z), dl);
-    if (t > best) { best = t; bi = lane + 32; }
+    if (!has || t > best) { best = t; bi = i; has = true; }
   }
   unsigned key = has ? f2ord(best + 0.0f) : 0u;
-  unsigned m = __reduce_max_sync(FULL, key);
+  unsigned m = __reduce_max_sync(UM, key);
   unsigned cand = (has && key == m) ? (unsigned)bi : 0x7fffffffu;
-  int idx = (int)__reduce_min_sync(FULL, cand);
+  int idx = (int)__reduce_min_sync(UM, cand);
   float4 v = __ldg(W.verts + c.voff + idx);
   *p = cr_pos(c) + mmul(R, v3(v.x, v.y, v.z) * c.scale);
   return idx;
@@ -479,25 +481,25 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
   bool have = false;
   float bary0 = 0, bary1 = 0, bary2 = 0, bary3 = 0;
   int status = 1;
-  __syncwarp();
+  __syncwarp(UM);
   const int cn = __float_as_int(sx[SX_CACHE]);
   bool warm = cn > 0;
   if (warm) {
     ids = (unsigned long long)(unsigned)__float_as_int(sx[SX_CACHE + 1]) | ((unsigned long long)(unsigned)__float_as_int(sx[SX_CACHE + 2]) << 32);
-    __syncwarp();
-    if (lane < cn) {
-      const unsigned id = (unsigned)((ids >> (16 * lane)) & 0xffffull);
+    __syncwarp(UM);
+    if (UL < cn) {
+      const unsigned id = (unsigned)((ids >> (16 * UL)) & 0xffffull);
       const int ia = (int)(id & 255u), ib = (int)(id >> 8);
       const V3 a = vertex_world(A, ia), b = vertex_world(B, ib);
-      ST3(sx + SX_W + lane * 3, a - b); ST3(sx + SX_A + lane * 3, a); ST3(sx + SX_B + lane * 3, b);
-      sx[SX_IA + lane] = __int_as_float(ia); sx[SX_IB + lane] = __int_as_float(ib);
+      ST3(sx + SX_W + UL * 3, a - b); ST3(sx + SX_A + UL * 3, a); ST3(sx + SX_B + UL * 3, b);
+      sx[SX_IA + UL] = __int_as_float(ia); sx[SX_IB + UL] = __int_as_float(ib);
     }
     n = cn;
     perm = 0xE4u;                        // logical entry k in physical slot k
   }
-  __syncwarp();
-  if (lane == 0) { sx[SX_CACHE] = __int_as_float(0); sx[SX_CACHE + 1] = __int_as_float(0); sx[SX_CACHE + 2] = __int_as_float(0); }
-  __syncwarp();
+  __syncwarp(UM);
+  if (UL == 0) { sx[SX_CACHE] = __int_as_float(0); sx[SX_CACHE + 1] = __int_as_float(0); sx[SX_CACHE + 2] = __int_as_float(0); }
+  __syncwarp(UM);
   for (int it = 0; it < W.P.gjk_max_iters; ++it) {
     float vv = 0.0f;
     if (!warm) {
@@ -519,12 +521,12 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (k < n) usedp |= 1u << ((perm >> (2 * k)) & 3u);
       const int ps = __ffs(~usedp) - 1;
-      __syncwarp();
-      if (lane == 0) {
+      __syncwarp(UM);
+      if (UL == 0) {
         ST3(sx + SX_W + ps * 3, ww); ST3(sx + SX_A + ps * 3, a); ST3(sx + SX_B + ps * 3, b);
         sx[SX_IA + ps] = __int_as_float(ia); sx[SX_IB + ps] = __int_as_float(ib);
       }
-      __syncwarp();
+      __syncwarp(UM);
       perm = (perm & ~(3u << (2 * n))) | ((unsigned)ps << (2 * n));
       ids = (ids & ~(0xffffull << (16 * n))) | ((unsigned long long)id << (16 * n));
       n = n + 1;
@@ -561,21 +563,21 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
   if (status == 2) {
     // EPA wants the simplex in logical order at slots 0..n-1
     float rec[11];
-    const int src = (lane < 4) ? (int)((perm >> (2 * lane)) & 3u) : 0;
-    __syncwarp();
-    if (lane < 4) {
+    const int src = (UL < 4) ? (int)((perm >> (2 * UL)) & 3u) : 0;
+    __syncwarp(UM);
+    if (UL < 4) {
 #pragma unroll
       for (int t = 0; t < 3; ++t) { rec[t] = sx[SX_W + src * 3 + t]; rec[3 + t] = sx[SX_A + src * 3 + t]; rec[6 + t] = sx[SX_B + src * 3 + t]; }
       rec[9] = sx[SX_IA + src]; rec[10] = sx[SX_IB + src];
     }
-    __syncwarp();
-    if (lane < 4) {
+    __syncwarp(UM);
+    if (UL < 4) {
 #pragma unroll
-      for (int t = 0; t < 3; ++t) { sx[SX_W + lane * 3 + t] = rec[t]; sx[SX_A + lane * 3 + t] = rec[3 + t]; sx[SX_B + lane * 3 + t] = rec[6 + t]; }
-      sx[SX_IA + lane] = rec[9]; sx[SX_IB + lane] = rec[10];
+      for (int t = 0; t < 3; ++t) { sx[SX_W + UL * 3 + t] = rec[t]; sx[SX_A + UL * 3 + t] = rec[3 + t]; sx[SX_B + UL * 3 + t] = rec[6 + t]; }
+      sx[SX_IA + UL] = rec[9]; sx[SX_IB + UL] = rec[10];
     }
-    if (lane == 0) sx[SX_N] = __int_as_float(n);
-    __syncwarp();
+    if (UL == 0) sx[SX_N] = __int_as_float(n);
+    __syncwarp(UM);
     return 2;
   }
   if (!have) return 0;
@@ -590,13 +592,13 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
     }
   }
   *pa = xa; *pb = xb; *v_out = v;
-  __syncwarp();
-  if (lane == 0) {
+  __syncwarp(UM);
+  if (UL == 0) {
     sx[SX_CACHE] = __int_as_float(n);
     sx[SX_CACHE + 1] = __int_as_float((int)(unsigned)(ids & 0xffffffffull));
     sx[SX_CACHE + 2] = __int_as_float((int)(unsigned)(ids >> 32));
   }
-  __syncwarp();
+  __syncwarp(UM);
   return 1;
 }
 
@@ -631,13 +633,13 @@ __device__ __noinline__ bool sx_add(const ColRef& A, const ColRef& B, float* sx,
   int ia = support(A, d, &a, lane);
   int ib = support(B, -d, &b, lane);
   for (int k = 0; k < *n; ++k) if (__float_as_int(sx[SX_IA + k]) == ia && __float_as_int(sx[SX_IB + k]) == ib) return false;
-  __syncwarp();
-  if (lane == 0) {
+  __syncwarp(UM);
+  if (UL == 0) {
     int k = *n;
     ST3(sx + SX_W + k * 3, a - b); ST3(sx + SX_A + k * 3, a); ST3(sx + SX_B + k * 3, b);
     sx[SX_IA + k] = __int_as_float(ia); sx[SX_IB + k] = __int_as_float(ib);
   }
-  __syncwarp();
+  __syncwarp(UM);
   *n = *n + 1;
   return true;
 }
@@ -689,44 +691,44 @@ __device__ __noinline__ int epa(const ColRef& A, const ColRef& B, float* sx, flo
                    V3* pa, V3* pb, int lane) {
   int sn = __float_as_int(sx[SX_N]);
   if (sn < 4 && !epa_complete(A, B, sx, &sn, lane)) return 0;
-  __syncwarp();
-  if (lane < 4) {
-    ST3(ep + EP_W + lane * 3, LD3(sx + SX_W + lane * 3));
-    ST3(ep + EP_PA + lane * 3, LD3(sx + SX_A + lane * 3));
-    ST3(ep + EP_PB + lane * 3, LD3(sx + SX_B + lane * 3));
-    ep[EP_IA + lane] = sx[SX_IA + lane]; ep[EP_IB + lane] = sx[SX_IB + lane];
+  __syncwarp(UM);
+  if (UL < 4) {
+    ST3(ep + EP_W + UL * 3, LD3(sx + SX_W + UL * 3));
+    ST3(ep + EP_PA + UL * 3, LD3(sx + SX_A + UL * 3));
+    ST3(ep + EP_PB + UL * 3, LD3(sx + SX_B + UL * 3));
+    ep[EP_IA + UL] = sx[SX_IA + UL]; ep[EP_IB + UL] = sx[SX_IB + UL];
   }
-  __syncwarp();
+  __syncwarp(UM);
   int nv = 4, nf = 4;
   bool bad = false;
-  if (lane < 4) {
-    const int t0 = (lane == 3) ? 1 : 0, t1 = (lane == 0) ? 1 : (lane == 1) ? 3 : (lane == 2) ? 2 : 3;
-    const int t2 = (lane == 0) ? 2 : (lane == 1) ? 1 : (lane == 2) ? 3 : 2, t3 = (lane == 0) ? 3 : (lane == 1) ? 2 : (lane == 2) ? 1 : 0;
+  if (UL < 4) {
+    const int t0 = (UL == 3) ? 1 : 0, t1 = (UL == 0) ? 1 : (UL == 1) ? 3 : (UL == 2) ? 2 : 3;
+    const int t2 = (UL == 0) ? 2 : (UL == 1) ? 1 : (UL == 2) ? 3 : 2, t3 = (UL == 0) ? 3 : (UL == 1) ? 2 : (UL == 2) ? 1 : 0;
     V3 n; float d;
     int i0 = t0, i1 = t1, i2 = t2;
     if (!epa_face_plane(ep, i0, i1, i2, &n, &d)) bad = true;
     else {
       if (dot(n, LD3(ep + EP_W + t3 * 3)) - d > 0.0f) { int t = i1; i1 = i2; i2 = t; n = -n; d = -d; }
-      ep[EP_FI + lane] = __int_as_float(i0 | (i1 << 8) | (i2 << 16) | (1 << 24));
-      ST3(ep + EP_FN + lane * 3, n); ep[EP_FD + lane] = d;
+      ep[EP_FI + UL] = __int_as_float(i0 | (i1 << 8) | (i2 << 16) | (1 << 24));
+      ST3(ep + EP_FN + UL * 3, n); ep[EP_FD + UL] = d;
     }
   }
-  if (__any_sync(FULL, bad)) return 0;
-  __syncwarp();
+  if (__any_sync(UM, bad)) return 0;
+  __syncwarp(UM);
   int best = 0;
   for (int it = 0; it < W.P.epa_max_iters; ++it) {
     // closest alive face (first minimum)
     float bd = 3e38f; int bf = 0x7fffffff;
-    for (int f = lane; f < nf; f += 32) {
+    for (int f = UL; f < nf; f += UW) {
       int fi = __float_as_int(ep[EP_FI + f]);
       float d = ep[EP_FD + f];
       if ((fi >> 24) && d < bd) { bd = d; bf = f; }
     }
     unsigned key = (bf != 0x7fffffff) ? f2ord(bd + 0.0f) : 0xffffffffu;
-    unsigned mk = __reduce_min_sync(FULL, key);
+    unsigned mk = __reduce_min_sync(UM, key);
     if (mk == 0xffffffffu) return 0;
     unsigned cand = (key == mk && bf != 0x7fffffff) ? (unsigned)bf : 0x7fffffffu;
-    best = (int)__reduce_min_sync(FULL, cand);
+    best = (int)__reduce_min_sync(UM, cand);
     bd = ep[EP_FD + best];
     V3 n = LD3(ep + EP_FN + best * 3);
     V3 a, b;
@@ -736,18 +738,18 @@ __device__ __noinline__ int epa(const ColRef& A, const ColRef& B, float* sx, flo
     float s = dot(ww, n);
     if (s - bd < 1e-6f) break;
     bool dup = false;
-    for (int k = lane; k < nv; k += 32) if (__float_as_int(ep[EP_IA + k]) == ia && __float_as_int(ep[EP_IB + k]) == ib) dup = true;
-    if (__any_sync(FULL, dup) || nv >= EPA_MAXV) break;
+    for (int k = UL; k < nv; k += UW) if (__float_as_int(ep[EP_IA + k]) == ia && __float_as_int(ep[EP_IB + k]) == ib) dup = true;
+    if (__any_sync(UM, dup) || nv >= EPA_MAXV) break;
     // visibility
-    for (int f = lane; f < nf; f += 32) {
+    for (int f = UL; f < nf; f += UW) {
       int fi = __float_as_int(ep[EP_FI + f]);
       int vis = (fi >> 24) && (dot(LD3(ep + EP_FN + f * 3), ww) - ep[EP_FD + f] > 0.0f);
       ep[EP_VIS + f] = __int_as_float(vis);
     }
-    __syncwarp();
+    __syncwarp(UM);
     // horizon (sequential, lane 0)
     int ne = 0;
-    if (lane == 0) {
+    if (UL == 0) {
       for (int f = 0; f < nf; ++f) {
         if (!__float_as_int(ep[EP_VIS + f])) continue;
         int fi = __float_as_int(ep[EP_FI + f]);
@@ -763,17 +765,17 @@ __device__ __noinline__ int epa(const ColRef& A, const ColRef& B, float* sx, flo
         }
       }
     }
-    ne = __shfl_sync(FULL, ne, 0);
-    __syncwarp();
+    ne = __shfl_sync(UM, ne, 0, UW);
+    __syncwarp(UM);
     if (ne < 3 || nf + ne > EPA_MAXF) break;
-    if (lane == 0) {
+    if (UL == 0) {
       ST3(ep + EP_W + nv * 3, ww); ST3(ep + EP_PA + nv * 3, a); ST3(ep + EP_PB + nv * 3, b);
       ep[EP_IA + nv] = __int_as_float(ia); ep[EP_IB + nv] = __int_as_float(ib);
     }
-    __syncwarp();
+    __syncwarp(UM);
     // new faces: one horizon edge per lane; staged after the current faces, committed only if all are sound
     bool ok = true;
-    for (int j = lane; j < ne; j += 32) {
+    for (int j = UL; j < ne; j += UW) {
       int ed = __float_as_int(ep[EP_ED + j]);
       int u = ed & 255, vtx = (ed >> 8) & 255;
       V3 fn; float fd;
@@ -783,14 +785,14 @@ __device__ __noinline__ int epa(const ColRef& A, const ColRef& B, float* sx, flo
         ST3(ep + EP_FN + (nf + j) * 3, fn); ep[EP_FD + nf + j] = fd;
       }
     }
-    if (!__all_sync(FULL, ok)) break;
-    for (int f = lane; f < nf; f += 32)
+    if (!__all_sync(UM, ok)) break;
+    for (int f = UL; f < nf; f += UW)
       if (__float_as_int(ep[EP_VIS + f])) ep[EP_FI + f] = __int_as_float(__float_as_int(ep[EP_FI + f]) & 0x00ffffff);
-    __syncwarp();
+    __syncwarp(UM);
     nf += ne;
     ++nv;
   }
-  __syncwarp();
+  __syncwarp(UM);
   int fi = __float_as_int(ep[EP_FI + best]);
   int i0 = fi & 255, i1 = (fi >> 8) & 255, i2 = (fi >> 16) & 255;
   V3 fn = LD3(ep + EP_FN + best * 3);
@@ -802,7 +804,7 @@ __device__ __noinline__ int epa(const ColRef& A, const ColRef& B, float* sx, flo
   *pb = (LD3(ep + EP_PB + i0 * 3) * r.bary[0] + LD3(ep + EP_PB + i1 * 3) * r.bary[1]) + LD3(ep + EP_PB + i2 * 3) * r.bary[2];
   *n_out = fn;
   *depth = fd;
-  __syncwarp();
+  __syncwarp(UM);
   return 1;
 }
 
@@ -1024,14 +1026,15 @@ __device__ __forceinline__ float* pair_stage(int sw, int p) {
 __device__ __noinline__ void stage_narrow_pair(int e, int lane, int wib, int p) {
   const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
-  const unsigned lt = (1u << lane) - 1u;
+  const unsigned lt = (1u << UL) - 1u;
   const int M = P.max_manifolds;
   const int par = W.man_parity[e];
   const size_t obase = ((size_t)par * W.B + e) * M;
   const int old_n = W.num_manifolds[e];
-  float* stg = S.stage;   // [4][16]
+  float* stg = S.stage + UH * 64;   // [4][16] of this unit
+  float* sxu = S.sx + UH * 48;
   PROF_SEC0()
-  float* epa_scr = W.epa_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * EP_WORDS;
+  float* epa_scr = W.epa_scratch + (((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * UNITS_PER_WARP + UH) * EP_WORDS;
   const int key = S.pairs[p];
   const int a = key >> 16, b = key & 0xffff;
   ColRef A = col_ref(S.col, S.body, a), Bc = col_ref(S.col, S.body, b);
@@ -1040,25 +1043,27 @@ __device__ __noinline__ void stage_narrow_pair(int e, int lane, int wib, int p) 
   const float threshold = P.breaking_factor * fminf(ca[CO_RAD], cb[CO_RAD]);
   // old manifold lookup
   int found = 0x7fffffff;
-  for (int k = lane; k < old_n; k += 32) if (W.man_keys[obase + k] == key) found = min(found, k);
-  found = (int)__reduce_min_sync(FULL, (unsigned)found);
+  for (int k = UL; k < old_n; k += UW) if (W.man_keys[obase + k] == key) found = min(found, k);
+  found = (int)__reduce_min_sync(UM, (unsigned)found);
   int n = 0;
-  __syncwarp();
+  __syncwarp(UM);
   if (found != 0x7fffffff) {
     n = W.man_npts[obase + found];
     const float* src = W.man_pts + (obase + found) * 4 * B2S_CP_FLOATS;
-    const float s0 = src[lane];
-    stg[lane] = s0; stg[lane + 32] = src[lane + 32];
-    if (lane >= 13 && lane < 16) S.sx[SX_CACHE + lane - 13] = s0;      // GJK simplex of the previous substep
-  } else if (lane < 3) S.sx[SX_CACHE + lane] = __int_as_float(0);
-  __syncwarp();
+    for (int i = UL; i < 4 * B2S_CP_FLOATS; i += UW) {
+      const float s0 = src[i];
+      stg[i] = s0;
+      if (i >= 13 && i < 16) sxu[SX_CACHE + i - 13] = s0;             // GJK simplex of the previous substep
+    }
+  } else if (UL < 3) sxu[SX_CACHE + UL] = __int_as_float(0);
+  __syncwarp(UM);
   // refresh (one point per lane), compaction keeps the order
   {
     float pt[B2S_CP_FLOATS];
     bool keep = false;
-    if (lane < n) {
+    if (UL < n) {
 #pragma unroll
-      for (int t = 0; t < B2S_CP_FLOATS; ++t) pt[t] = stg[lane * B2S_CP_FLOATS + t];
+      for (int t = 0; t < B2S_CP_FLOATS; ++t) pt[t] = stg[UL * B2S_CP_FLOATS + t];
       V3 wA = cr_pos(A) + mmul(cr_R(A), v3(pt[0], pt[1], pt[2]));
       V3 wB = cr_pos(Bc) + mmul(cr_R(Bc), v3(pt[3], pt[4], pt[5]));
       V3 nn = v3(pt[6], pt[7], pt[8]);
@@ -1069,20 +1074,20 @@ __device__ __noinline__ void stage_narrow_pair(int e, int lane, int wib, int p) 
         if (!(len2(dd) > threshold * threshold)) { keep = true; pt[9] = dist; }
       }
     }
-    unsigned km = __ballot_sync(FULL, keep);
-    __syncwarp();
+    const unsigned km = (__ballot_sync(UM, keep) >> UB) & (UM >> UB);
+    __syncwarp(UM);
     if (keep) {
       int dst = __popc(km & lt);
 #pragma unroll
       for (int t = 0; t < B2S_CP_FLOATS; ++t) stg[dst * B2S_CP_FLOATS + t] = pt[t];
     }
     n = __popc(km);
-    __syncwarp();
+    __syncwarp(UM);
   }
   PROF_SEC(4)
   V3 pA, pB, nrm;
   float dist;
-  const int hit_ = collide_pair(A, Bc, threshold, S.sx, epa_scr, &pA, &pB, &nrm, &dist, lane);
+  const int hit_ = collide_pair(A, Bc, threshold, sxu, epa_scr, &pA, &pB, &nrm, &dist, lane);
   PROF_SEC(5)
   if (hit_) {
     V3 lA = mtmul(cr_R(A), pA - cr_pos(A));
@@ -1104,23 +1109,23 @@ __device__ __noinline__ void stage_narrow_pair(int e, int lane, int wib, int p) 
       for (int k = 0; k < 4; ++k) { PP[k] = LD3(stg + k * B2S_CP_FLOATS); DD[k] = stg[k * B2S_CP_FLOATS + 9]; }
       idx = b2s_manifold_replace_index(PP, DD, lA, dist);
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncwarp(UM);
+    if (UL == 0) {
       float* pp = stg + idx * B2S_CP_FLOATS;
       pp[0] = lA.x; pp[1] = lA.y; pp[2] = lA.z; pp[3] = lB.x; pp[4] = lB.y; pp[5] = lB.z;
       pp[6] = nrm.x; pp[7] = nrm.y; pp[8] = nrm.z; pp[9] = dist;
       if (!keepl) { pp[10] = 0.0f; pp[11] = 0.0f; pp[12] = 0.0f; }
       pp[13] = 0.0f; pp[14] = 0.0f; pp[15] = 0.0f;
     }
-    __syncwarp();
+    __syncwarp(UM);
   }
   float* dst = pair_stage(wib, p);
   if (n > 0) {
-    dst[lane] = (lane >= 13 && lane < 16) ? S.sx[SX_CACHE + lane - 13] : ((lane < n * B2S_CP_FLOATS) ? stg[lane] : 0.0f);
-    dst[lane + 32] = (lane + 32 < n * B2S_CP_FLOATS) ? stg[lane + 32] : 0.0f;
+    for (int i = UL; i < 4 * B2S_CP_FLOATS; i += UW)
+      dst[i] = (i >= 13 && i < 16) ? sxu[SX_CACHE + i - 13] : ((i < n * B2S_CP_FLOATS) ? stg[i] : 0.0f);
   }
-  if (lane == 0) dst[64] = __int_as_float(n);
-  __syncwarp();
+  if (UL == 0) dst[64] = __int_as_float(n);
+  __syncwarp(UM);
   PROF_SEC(6)
 }
 
@@ -1887,6 +1892,38 @@ __device__ __forceinline__ int grab_slot(int* counter, int lane, int wib, int E,
 
 // Next candidate pair of the block: unit u of the concatenated pair lists of the active environments.
 // Returns the environment slot (-1: none left) and the pair index in *p_out.
+#if B2S_HALF
+// UNITS_PER_WARP units per grab: unit k of the warp (lanes k*UW..) takes pair u0 + k; a unit may come back with -1
+__device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_out) {
+  int u0 = 0;
+  if (lane == 0) u0 = atomicAdd(counter, UNITS_PER_WARP);
+  u0 = __shfl_sync(FULL, u0, 0);
+  int base = 0;
+  int res = -1, pidx = 0;
+  for (int s0 = 0; s0 < E; s0 += 32) {
+    const int slot = s0 + lane;
+    int cnt = 0;
+    if (slot < E) { const int* m = env_meta(slot); if (m[META_ACTIVE]) cnt = m[META_NP]; }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+    const int total = __shfl_sync(FULL, incl, 31);
+#pragma unroll
+    for (int k = 0; k < UNITS_PER_WARP; ++k) {
+      const int u = u0 + k;
+      if (u >= base && u < base + total) {            // uniform over the warp
+        const int l = __ffs(__ballot_sync(FULL, u < base + incl)) - 1;
+        const int pk = u - base - __shfl_sync(FULL, incl - cnt, l);
+        if (UH == k) { res = s0 + l; pidx = pk; }
+      }
+    }
+    base += total;
+    if (u0 + UNITS_PER_WARP - 1 < base) break;
+  }
+  *p_out = pidx;
+  return res;
+}
+#else
 __device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_out) {
   int u = 0;
   if (lane == 0) u = atomicAdd(counter, 1);
@@ -1909,6 +1946,8 @@ __device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_o
   }
   return -1;
 }
+
+#endif
 
 // Block = Wn warps stepping E environments.  Every substep runs three stages separated by block barriers
 // (scene -> narrow phase -> solve/integrate/phase logic); inside a stage the warps take environments from
@@ -1977,8 +2016,14 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     for (;;) {
       int pp = 0;
       const int slot = grab_pair(&s_cnt[1], lane, E, &pp);
+#if B2S_HALF
+      if (__all_sync(FULL, slot < 0)) break;
+      if (slot >= 0) stage_narrow_pair(env_meta(slot)[META_ENV], lane, slot | (wib << 16), pp);
+      __syncwarp();
+#else
       if (slot < 0) break;
       stage_narrow_pair(env_meta(slot)[META_ENV], lane, slot | (wib << 16), pp);
+#endif
     }
     PROF_STAGE(1)
     __syncthreads();
