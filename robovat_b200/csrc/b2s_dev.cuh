@@ -31,7 +31,7 @@ typedef b2s_m3 M3;
 // on one pair, 1 = two pairs of 16 lanes, 2 = four pairs of 8 lanes.  Hulls have 8..64 vertices and most of GJK is
 // uniform simplex arithmetic, so narrow units waste fewer lanes; the halves diverge only where their pairs differ.
 #ifndef B2S_HALF
-#define B2S_HALF 1
+#define B2S_HALF 2
 #endif
 #if B2S_HALF
 #define UW (32 >> B2S_HALF)
