@@ -420,12 +420,22 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
   // (only when the stepping environments need more than one wave per block anyway: a sparse launch -- the tail of
   // a batched PushEnv.step -- is fastest with the environments spread one per block)
   const int stepping = W.B - hist[255];
+  // B2S_HW expensive environments per block of that class (default: one per warp), topped up with B2S_LF of the
+  // cheapest ones (default: none)
+#ifndef B2S_HW
+#define B2S_HW Wn
+#endif
+#ifndef B2S_LF
+#define B2S_LF 0
+#endif
+  const int HW = min(B2S_HW, Wn), LF = min(B2S_LF, E - HW);
   if (E > Wn && nblocks > 1 && stepping > nblocks * Wn) {
-    const int hb_max = (nblocks * E - W.B) / (E - Wn);
-    Hb = min(min((s_heavy + Wn - 1) / Wn, hb_max), nblocks - 1);
+    const int hb_max = (nblocks * E - W.B) / (E - HW - LF);
+    Hb = min(min((s_heavy + HW - 1) / HW, hb_max), nblocks - 1);
     if (Hb < 0) Hb = 0;
   }
-  const int hcap = Hb * Wn, Lb = nblocks - Hb;
+  const int hcap = Hb * HW, Lb = nblocks - Hb;
+  const int nl = W.B - min(hcap, W.B), fill = min(Hb * LF, nl);
   for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
     const int32_t* st = W.solver_stats + (size_t)e * 4;
     int key = 1 + min(254, st[1] * st[2]);
@@ -433,7 +443,11 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
     const int p = atomicAdd(&base[255 - key], 1);
     int block, slot;
     if (p < hcap) { block = p % Hb; slot = p / Hb; }
-    else { const int q = p - hcap; block = Hb + q % Lb; slot = q / Lb; }
+    else {
+      const int q = p - hcap, qr = nl - 1 - q;          // qr: rank from the cheap end
+      if (qr < fill) { block = qr % Hb; slot = HW + qr / Hb; }
+      else { block = Hb + q % Lb; slot = q / Lb; }
+    }
     W.env_map[(size_t)block * E + slot] = e;
   }
 }

@@ -11,10 +11,11 @@
 // to the blocks before every launch, k_assign_envs) and advances them in lock-step rounds of three stages
 // separated by block barriers -- scene (controller, FK, body table, AABBs, broad phase), narrow phase, solve +
 // integration + phase machine -- with dynamic hand-out of the work inside a stage: environments in the first and
-// the last stage, single candidate PAIRS in the narrow phase.  All per-substep intermediates (body table,
+// the last stage, single candidate PAIRS in the narrow phase (a warp takes UNITS_PER_WARP pairs per grab and works
+// them side by side in units of UW lanes, b2s_dev.cuh).  All per-substep intermediates (body table,
 // collider AABBs, pair list, contact list) live in the block's shared memory; only the persistent state (13
 // floats per movable, 14 per arm, the <=4-point manifolds) goes back to HBM/L2.  Lanes split the work inside a
-// unit: one hull vertex per lane in the GJK/EPA support function (exact warp max via redux on order-preserving
+// unit: one hull vertex per lane in the GJK/EPA support function (exact max via redux on order-preserving
 // keys), one collider per lane for AABBs, ballot-compacted pair lists, one contact per lane for Jacobian rows
 // and colouring, one BODY per lane in the Gauss-Seidel sweeps (velocities in registers), which run the oracle's
 // colour order exactly.  The residual test is a warp reduce.  All fp32 arithmetic is ordered exactly as in
