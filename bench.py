@@ -215,7 +215,28 @@ def main():
     gen = torch.Generator(device=dev)
     gen.manual_seed(args.seed + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    returns_all = torch.zeros(world_size * B, dtype=torch.float32, device=dev)
+    # Returns of all ranks (tools/parallel_run.py:54-90 collects the workers' results; its workers never wait for one
+    # another).  The all-gather of rollout k is asynchronous and double buffered: it travels on NCCL's stream while
+    # rollout k+1 runs, so a rank only waits for a peer that is two rollouts behind; the last ones are waited for
+    # inside the timed region.
+    returns_all = [torch.zeros(world_size * B, dtype=torch.float32, device=dev) for _ in range(2)]
+    returns_mine = [torch.zeros(B, dtype=torch.float32, device=dev) for _ in range(2)]
+    gathers = [None, None]
+    gather_count = [0]
+
+    def gather_returns(last=False):
+        if world_size == 1:
+            return
+        i = gather_count[0] & 1
+        gather_count[0] += 1
+        if gathers[i] is not None:
+            gathers[i].wait()
+        returns_mine[i].copy_(w.episode_return.reshape(-1))
+        gathers[i] = dist.all_gather_into_tensor(returns_all[i], returns_mine[i], async_op=True)
+        if last:
+            for g in gathers:
+                if g is not None:
+                    g.wait()
 
     def barrier():
         if world_size > 1:
@@ -224,7 +245,7 @@ def main():
 
     kernel_events = []
 
-    def device_step(timed):
+    def device_step(timed, last=False):
         act = heuristic_actions_torch(w.obs_position, w.body_mask, cfg, gen)
         w.action.copy_(act)
         w.set_action()
@@ -242,8 +263,7 @@ def main():
                 break
         w.observe()
         w.reward()
-        if world_size > 1:
-            dist.all_gather_into_tensor(returns_all, w.episode_return)
+        gather_returns(last)
 
     # ---- device-resident leg -------------------------------------------------------------
     for _ in range(args.warmup):
@@ -254,11 +274,11 @@ def main():
     sampler.start()
     step_events = []
     barrier()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        device_step(True)
+        device_step(True, last=(k == args.steps - 1))
         b.record()
         step_events.append((a, b))
     barrier()
@@ -281,12 +301,11 @@ def main():
         barrier()
         s1 = w.substeps_executed()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for k in range(args.steps):
             env._done[:] = False
             act = heuristic_actions_np(np.asarray(obs['position']).reshape(B, -1, 3), np.asarray(obs['body_mask']).reshape(B, -1), cfg, rs)
             obs, rew, done, _ = env.step(act)
-            if world_size > 1:
-                dist.all_gather_into_tensor(returns_all, w.episode_return)
+            gather_returns(last=(k == args.steps - 1))
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e_sub = w.substeps_executed() - s1

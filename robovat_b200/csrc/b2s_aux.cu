@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
 #ifndef B2S_LF
 #define B2S_LF 0
 #endif
-  const int HW = min(B2S_HW, Wn), LF = min(B2S_LF, E - HW);
+  const int HW = min(B2S_HW, Wn), LF = max(0, min(B2S_LF, E - HW));
   if (E > Wn && nblocks > 1 && stepping > nblocks * Wn) {
     const int hb_max = (nblocks * E - W.B) / (E - HW - LF);
     Hb = min(min((s_heavy + HW - 1) / HW, hb_max), nblocks - 1);
