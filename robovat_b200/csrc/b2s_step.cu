@@ -1894,10 +1894,17 @@ __device__ __forceinline__ int grab_slot(int* counter, int lane, int wib, int E,
 // Next candidate pair of the block: unit u of the concatenated pair lists of the active environments.
 // Returns the environment slot (-1: none left) and the pair index in *p_out.
 #if B2S_HALF
-// UNITS_PER_WARP units per grab: unit k of the warp (lanes k*UW..) takes pair u0 + k; a unit may come back with -1
-__device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_out) {
+// nu <= UNITS_PER_WARP units per grab: unit k of the warp (lanes k*UW..) takes pair u0 + k; a unit may come back with
+// -1.  nu follows the block's pair count of this round (block_pairs, summed in stage A): a block with few pairs -- a
+// sparse launch, a single environment -- spreads them over its warps instead of serialising four on one.
+__device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_out, int block_pairs, int Wn) {
+#ifdef B2S_FIXED_NU
+  const int nu = UNITS_PER_WARP;
+#else
+  const int nu = max(1, min(UNITS_PER_WARP, (block_pairs + Wn - 1) / Wn));
+#endif
   int u0 = 0;
-  if (lane == 0) u0 = atomicAdd(counter, UNITS_PER_WARP);
+  if (lane == 0) u0 = atomicAdd(counter, nu);
   u0 = __shfl_sync(FULL, u0, 0);
   int base = 0;
   int res = -1, pidx = 0;
@@ -1912,14 +1919,14 @@ __device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_o
 #pragma unroll
     for (int k = 0; k < UNITS_PER_WARP; ++k) {
       const int u = u0 + k;
-      if (u >= base && u < base + total) {            // uniform over the warp
+      if (k < nu && u >= base && u < base + total) {  // uniform over the warp
         const int l = __ffs(__ballot_sync(FULL, u < base + incl)) - 1;
         const int pk = u - base - __shfl_sync(FULL, incl - cnt, l);
         if (UH == k) { res = s0 + l; pidx = pk; }
       }
     }
     base += total;
-    if (u0 + UNITS_PER_WARP - 1 < base) break;
+    if (u0 + nu - 1 < base) break;
   }
   *p_out = pidx;
   return res;
@@ -1959,7 +1966,7 @@ __device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_o
 // (2.0x slower: 16 warps in 16 code regions), warps leaving the barrier protocol during long solves
 // (1.15-1.25x slower: persistent stragglers become the tail of the launch), two 8-warp blocks per SM (1.2x).
 __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps) {
-  __shared__ int s_cnt[3];
+  __shared__ int s_cnt[4];    // hand-out counters of the three stages, candidate pairs of the block in this round
 #ifdef B2S_PROF
   __shared__ int s_maxc;
   if (threadIdx.x == 0) s_maxc = 0;
@@ -1972,7 +1979,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
   const B2SParams& P = W.P;
   for (int slot = wib; slot < E; slot += Wn)
     if (lane < META_WORDS) env_meta(slot)[lane] = 0;
-  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
+  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; }
   __syncthreads();
   int done_steps = 0;
   int any_next = 0;
@@ -2007,7 +2014,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       int* meta = env_meta(slot);
       if (!meta[META_ACTIVE]) continue;
       const int np = stage_scene(meta[META_ENV], lane, slot | (wib << 16));
-      if (lane == 0) meta[META_NP] = np;
+      if (lane == 0) { meta[META_NP] = np; atomicAdd(&s_cnt[3], np); }
     }
     PROF_STAGE(0)
     __syncthreads();
@@ -2016,12 +2023,13 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     // ---- stage B: narrow phase, one candidate pair per grab
     for (;;) {
       int pp = 0;
-      const int slot = grab_pair(&s_cnt[1], lane, E, &pp);
 #if B2S_HALF
+      const int slot = grab_pair(&s_cnt[1], lane, E, &pp, s_cnt[3], Wn);
       if (__all_sync(FULL, slot < 0)) break;
       if (slot >= 0) stage_narrow_pair(env_meta(slot)[META_ENV], lane, slot | (wib << 16), pp);
       __syncwarp();
 #else
+      const int slot = grab_pair(&s_cnt[1], lane, E, &pp);
       if (slot < 0) break;
       stage_narrow_pair(env_meta(slot)[META_ENV], lane, slot | (wib << 16), pp);
 #endif
@@ -2029,7 +2037,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     PROF_STAGE(1)
     __syncthreads();
     PROF_MARK(1)
-    if (threadIdx.x == 0) s_cnt[1] = 0;
+    if (threadIdx.x == 0) { s_cnt[1] = 0; s_cnt[3] = 0; }
     // ---- stage C: solve, integrate, phase machine / settle bookkeeping
     for (;;) {
       const int slot = grab_slot(&s_cnt[2], lane, wib, E, first2);
