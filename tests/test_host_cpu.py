@@ -220,3 +220,36 @@ def test_two_rank_sharding_allgathers_the_same_returns(tmp_path):
         pass
     w.reward()
     helpers.assert_bits_equal(gathered, w.array('episode_return'), 'all-gathered returns')
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the CUDA path): one JSON line with the contract
+    keys on rank 0, silence and exit 0 on every other rank."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--cpu-seconds', '1']
+    env = dict(os.environ, RANK='0', WORLD_SIZE='1', LOCAL_RANK='0')
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'PushEnv substeps/sec at 4096 envs' and line['unit'] == 'substeps/s'
+    assert line['higher_is_better'] is True and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1 and line['cpu_baseline']['value'] == line['value']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'substeps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    env['RANK'] = '1'
+    env['WORLD_SIZE'] = '2'
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=env, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_bench_cuda_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: the CUDA arm of bench.py refuses to run when there is no device (skipped on a GPU box)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode != 0 and 'no CPU fallback' in out.stderr and out.stdout.strip() == ''
