@@ -317,7 +317,12 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     d.num_blocks = (d.B + E - 1) / E;
     // spare slots: the deal (k_assign_envs) gives the blocks that hold the expensive environments at most one
     // environment per warp and lets the cheap blocks take the rest
-    if (P.reserved_i[0] <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7));
+    // (B2S_EXTRA_SLOTS: tuning knob for variant builds -- more spare slots let the deal form more, smaller blocks of
+    // expensive environments, see B2S_HW in b2s_aux.cu)
+#ifndef B2S_EXTRA_SLOTS
+#define B2S_EXTRA_SLOTS 0
+#endif
+    if (P.reserved_i[0] <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7) + B2S_EXTRA_SLOTS);
     d.envs_per_block = E;
     const size_t blocks = d.num_blocks;
     if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * UNITS_PER_WARP * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
