@@ -92,7 +92,10 @@ typedef struct B2SParams {
   int32_t max_contacts;            /* contact points per env handed to the solver */
   int32_t max_colliders;           /* convex hulls per env (statics + arm links + movable hulls) */
   int32_t warps_per_block;         /* warps per block of the substep kernel; 0 = what the library was built for */
-  int32_t reserved_i[4];
+  int32_t envs_per_block;          /* environment slots per block of the substep kernel; 0 = derived from num_envs and the SM count */
+  int32_t export_debug;            /* 1: every substep also writes the inspection arrays (B2S_ARR_PAIR_KEYS, LINK_POSES, LINK_VEL);
+                                      0 (product default): they are only refreshed by the calls that need them */
+  int32_t reserved_i[2];
 
   double time_step;                /* dt; reference default 1e-3 (simulator.py:26) */
   float gravity[3];                /* (0,0,-9.8) simulator.py:27 */
@@ -209,24 +212,26 @@ enum {
   B2S_ARR_MANIFOLD_NPTS = 1,   /* int32 [B][max_manifolds] */
   B2S_ARR_MANIFOLD_PTS = 2,    /* float [B][max_manifolds][4][B2S_CP_FLOATS] */
   B2S_ARR_NUM_MANIFOLDS = 3,   /* int32 [B] */
-  B2S_ARR_PAIR_KEYS = 4,       /* int32 [B][max_pairs] broad-phase pairs of the last substep */
+  B2S_ARR_PAIR_KEYS = 4,       /* int32 [B][max_pairs] broad-phase pairs of the last substep (written when params.export_debug) */
   B2S_ARR_NUM_PAIRS = 5,       /* int32 [B] */
   B2S_ARR_PHASE = 6,           /* int32 [B] */
   B2S_ARR_NUM_STEPS = 7,       /* int32 [B] substeps executed since reset (Simulator.num_steps) */
   B2S_ARR_CTRL = 8,            /* float [B][B2S_CTRL_FLOATS] controller targets */
   B2S_ARR_CTRL_FLAGS = 9,      /* int32 [B][4] link_target_active, joint_target_active, qd_target_is_none, interrupt */
-  B2S_ARR_LINK_POSES = 10,     /* float [B][num_links+1][7] world collision frames, last = end effector */
+  B2S_ARR_LINK_POSES = 10,     /* float [B][num_links+1][7] world collision frames, last = end effector (refreshed by
+                                  b2s_forward_kinematics / b2s_render / b2s_reset; every substep when params.export_debug) */
   B2S_ARR_MOV_PARAMS = 11,     /* float [4][B][Nmax] asset(as int bits), scale, mass, friction */
   B2S_ARR_TABLE_DZ = 12,       /* float [B] */
   B2S_ARR_ERROR_FLAGS = 13,    /* int32 [B] bit0 pair overflow, bit1 manifold overflow, bit2 non-finite state,
-                                  bit3 contact overflow, bit4 colour overflow, bit5 collider overflow, bit6 solver invariant */
+                                  bit3 contact overflow, bit4 colour overflow, bit5 collider overflow, bit6 solver invariant,
+                                  bit7 reset found no placement with the MARGIN clearance (re-sample the env) */
   B2S_ARR_WAYPOINTS = 14,      /* float [B][2][7] start / end gripper poses */
   B2S_ARR_STATUS = 15,         /* float [B][2][Nmax][4] start/end status: pos3 + yaw (push_env.py:925-937) */
   B2S_ARR_CONTACT_FLAGS = 16,  /* int32 [B] bit0 arm-table, bit1 arm-movable, per last substep */
   B2S_ARR_PHASE_STATE = 17,    /* int32 [B][8] max_phase_steps, num_waypoints, settle_steps, stable_steps, ... */
   B2S_ARR_SOLVER_STATS = 18,   /* int32 [B][4] rows, colours, iterations used, contacts of the last substep */
   B2S_ARR_CTRL_TIME = 19,      /* double [B][5] link start/stop, joint start/stop, gripper-ready time */
-  B2S_ARR_LINK_VEL = 20,       /* float [B][num_links][6] linear + angular velocity of the collision frames */
+  B2S_ARR_LINK_VEL = 20,       /* float [B][num_links][6] linear + angular velocity of the collision frames (as LINK_POSES) */
   B2S_ARR_NUM_COLLIDERS = 21,  /* int32 [B] */
   B2S_ARR_COL_SLOT = 22,       /* int32 [B][max_colliders] body slot of each collider */
   B2S_ARR_COL_HULL = 23,       /* int32 [B][max_colliders] hull id of each collider */
@@ -259,11 +264,19 @@ int b2s_get_params(const B2SWorld* world, B2SParams* out);
 int b2s_reset(B2SWorld* world, const uint8_t* env_mask_dev, uint64_t seed, void* stream);
 /* Simulator.wait_until_stable(movables, lin, ang, max_steps) for every env (simulator.py:325-376) */
 int b2s_settle(B2SWorld* world, float lin_threshold, float ang_threshold, int max_steps, void* stream);
+/* the same for the envs of env_mask_dev only (device uint8 [B], NULL = all): a partial reset must not step the
+ * physics of the other envs (the reference has one world per env, so its wait never touches another env) */
+int b2s_settle_masked(B2SWorld* world, const uint8_t* env_mask_dev, float lin_threshold, float ang_threshold, int max_steps,
+                      void* stream);
+/* end of RobotEnv.reset (robot_env.py:224-235): the settled scene becomes the episode's first observation, i.e. the
+ * `prev_obs_data` of the first PushReward.get_reward (push_reward.py:396-405).  Stores the current movable xy as the
+ * reward's previous state for the envs of env_mask_dev (NULL = all). */
+int b2s_begin_episode(B2SWorld* world, const uint8_t* env_mask_dev, void* stream);
 
 /* Simulator.step x n for every env, phase machine untouched
  * (= ControllableBody.update + pybullet.stepSimulation; simulator.py:94-103).  THE benchmarked call. */
 int b2s_step(B2SWorld* world, int n_substeps, void* stream);
-/* same kernels, one launch per stage per substep (profiling / per-stage parity) */
+/* the same substeps as n launches of one substep each (launch-granular profiling; results identical to b2s_step) */
 int b2s_step_staged(B2SWorld* world, int n_substeps, void* stream);
 
 /* PushEnv._execute_action (push_env.py:631-733): b2s_set_action computes the waypoints from

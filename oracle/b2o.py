@@ -96,8 +96,16 @@ class OracleWorld(object):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
         self._chk(self.lib.b2o_reset(self.h, m, C.c_uint64(seed)))
 
-    def settle(self, lin=0.005, ang=0.005, max_steps=2000):
-        self._chk(self.lib.b2o_settle(self.h, C.c_float(lin), C.c_float(ang), int(max_steps)))
+    def settle(self, lin=0.005, ang=0.005, max_steps=2000, mask=None):
+        if mask is None:
+            self._chk(self.lib.b2o_settle(self.h, C.c_float(lin), C.c_float(ang), int(max_steps)))
+        else:
+            m = np.ascontiguousarray(mask, np.uint8)
+            self._chk(self.lib.b2o_settle_masked(self.h, m.ctypes.data_as(C.c_void_p), C.c_float(lin), C.c_float(ang), int(max_steps)))
+
+    def begin_episode(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
+        self._chk(self.lib.b2o_begin_episode(self.h, m))
 
     def step(self, n=1):
         self._chk(self.lib.b2o_step(self.h, int(n)))

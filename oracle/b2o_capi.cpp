@@ -137,13 +137,13 @@ static void run_env(World* w, int e, int n, int mode, float lin, float ang, int 
   }
 }
 
-static void run_all(World* w, int n, int mode, float lin, float ang, int max_steps) {
+static void run_all(World* w, int n, int mode, float lin, float ang, int max_steps, const uint8_t* mask = nullptr) {
   const int B = w->B;
   /* substep() bumps w->substeps_executed; under OpenMP that would race, so save and
    * recompute it from the per-env step counters, which are private to each env. */
   int64_t base = w->substeps_executed;
   std::vector<int32_t> before(w->num_steps);
-  parallel_envs(B, [&](int e) { run_env(w, e, n, mode, lin, ang, max_steps); });
+  parallel_envs(B, [&](int e) { if (!mask || mask[e]) run_env(w, e, n, mode, lin, ang, max_steps); });
   int64_t add = 0;
   for (int e = 0; e < B; ++e) add += (int64_t)(w->num_steps[e] - before[e]);
   w->substeps_executed = base + add;
@@ -151,6 +151,17 @@ static void run_all(World* w, int n, int mode, float lin, float ang, int max_ste
 
 int b2o_step(World* w, int n) { run_all(w, n, 0, 0, 0, 0); return 0; }
 int b2o_settle(World* w, float lin, float ang, int max_steps) { run_all(w, 0, 2, lin, ang, max_steps); return 0; }
+int b2o_settle_masked(World* w, const uint8_t* mask, float lin, float ang, int max_steps) { run_all(w, 0, 2, lin, ang, max_steps, mask); return 0; }
+/* end of RobotEnv.reset (robot_env.py:224-235): the settled scene is the first step's prev_obs_data */
+int b2o_begin_episode(World* w, const uint8_t* mask) {
+  for (int e = 0; e < w->B; ++e) if (!mask || mask[e])
+    for (int i = 0; i < w->Nmax; ++i) {
+      const bool live = i < w->num_movables[e];
+      w->prev_xy[((size_t)e * w->Nmax + i) * 2] = live ? w->body_state[((size_t)0 * w->B + e) * w->Nmax + i] : 0.0f;
+      w->prev_xy[((size_t)e * w->Nmax + i) * 2 + 1] = live ? w->body_state[((size_t)1 * w->B + e) * w->Nmax + i] : 0.0f;
+    }
+  return 0;
+}
 int b2o_set_action(World* w) { for (int e = 0; e < w->B; ++e) set_action(*w, e); return 0; }
 int b2o_env_substeps(World* w, int n, int* unfinished) {
   run_all(w, n, 1, 0, 0, 0);

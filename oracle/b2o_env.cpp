@@ -55,6 +55,7 @@ void reset_env(World& w, int e, uint64_t seed) {
   float table_z = 0.0f;
   for (int s = 0; s < w.Ns; ++s) if (w.S.static_flags[s] & B2S_STATIC_IS_TABLE) table_z = w.S.static_pose[s * 7 + 2] + dz;
   float px[64], py[64], pz[64], er[64], ep[64], ey[64];
+  bool placed = false;
   for (int round = 0; round < 64; ++round) {
     bool all_ok = true;
     for (int i = 0; i < n; ++i) {
@@ -85,7 +86,7 @@ void reset_env(World& w, int e, uint64_t seed) {
       }
       if (!ok) { all_ok = false; break; }
     }
-    if (all_ok) break;
+    if (all_ok) { placed = true; break; }
   }
   for (int i = 0; i < Nmax; ++i) {
     for (int c = 0; c < 13; ++c) bs(w, c, e, i) = 0.0f;
@@ -112,7 +113,7 @@ void reset_env(World& w, int e, uint64_t seed) {
   for (int k = 0; k < P.max_manifolds; ++k) { w.man_keys[(size_t)e * P.max_manifolds + k] = -1; w.man_npts[(size_t)e * P.max_manifolds + k] = 0; }
   memset(&w.man_pts[(size_t)e * P.max_manifolds * 4 * B2S_CP_FLOATS], 0, sizeof(float) * P.max_manifolds * 4 * B2S_CP_FLOATS);
   w.num_pairs[e] = 0;
-  w.error_flags[e] = 0;
+  w.error_flags[e] = placed ? 0 : 128;      /* no arrangement with MARGIN clearance in 64 rounds */
   w.contact_flags[e] = 0;
   memset(&w.ctrl[(size_t)e * B2S_CTRL_FLOATS], 0, sizeof(float) * B2S_CTRL_FLOATS);
   memset(&w.ctrl_flags[(size_t)e * 4], 0, sizeof(int32_t) * 4);

@@ -50,7 +50,7 @@ class B2SParams(C.Structure):
         ('stable_check_after', i32), ('stable_min_steps', i32), ('stable_max_steps', i32),
         ('clamp_joint_velocity', i32), ('cam_height', i32), ('cam_width', i32),
         ('num_points', i32), ('task', i32), ('max_contacts', i32), ('max_colliders', i32),
-        ('warps_per_block', i32), ('reserved_i', i32 * 4),
+        ('warps_per_block', i32), ('envs_per_block', i32), ('export_debug', i32), ('reserved_i', i32 * 2),
         ('time_step', f64), ('gravity', f32 * 3), ('erp2', f32), ('linear_slop', f32),
         ('warmstart', f32), ('residual_threshold', f32), ('linear_damping', f32),
         ('angular_damping', f32), ('breaking_factor', f32), ('ik_damping', f32),
@@ -120,6 +120,8 @@ SYMBOLS = {
     'b2s_get_params': (C.c_int, [_vp, P(B2SParams)]),
     'b2s_reset': (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     'b2s_settle': (C.c_int, [_vp, C.c_float, C.c_float, C.c_int, _vp]),
+    'b2s_settle_masked': (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_int, _vp]),
+    'b2s_begin_episode': (C.c_int, [_vp, _vp, _vp]),
     'b2s_step': (C.c_int, [_vp, C.c_int, _vp]),
     'b2s_step_staged': (C.c_int, [_vp, C.c_int, _vp]),
     'b2s_set_action': (C.c_int, [_vp, _vp]),

@@ -244,7 +244,8 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     p.max_colliders = scene.fixed_colliders + movable_hulls
     p.max_manifolds = max(32, 6 * movable_hulls)
     p.max_pairs = max(64, 2 * p.max_manifolds)
-    p.reserved_i[0] = int(os.environ.get('B2S_EPB', 0))      # envs per block (0 = library default)
+    p.envs_per_block = int(os.environ.get('B2S_EPB', 0))     # 0 = library default
+    p.export_debug = int(os.environ.get('B2S_EXPORT_DEBUG', 0))
     # <= 32 contact points keeps the solver's Jacobian rows in registers (one contact per lane)
     p.max_contacts = max(32, 8 * movable_hulls)
     p.solver_iterations, p.friction_dirs = int(phys.SOLVER_ITERATIONS), int(phys.FRICTION_DIRS)

@@ -45,10 +45,20 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 #define NEED(w) \
   if (!(w)) return fail(B2S_E_INVALID, "%s: world is NULL", __func__)
+// every entry point works on the world's device whatever the caller's current device is, and leaves the
+// caller's current device as it found it (torch keeps its own notion of it)
+struct DeviceGuard {
+  int prev; bool changed;
+  explicit DeviceGuard(int dev) : prev(dev), changed(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
 #define NEED_READY(w)                                                                            \
   NEED(w);                                                                                       \
   if (!(w)->scene_loaded) return fail(B2S_E_STATE, "%s: call b2s_load_scene first", __func__);   \
-  if (!(w)->buffers_bound) return fail(B2S_E_STATE, "%s: call b2s_bind_buffers first", __func__)
+  if (!(w)->buffers_bound) return fail(B2S_E_STATE, "%s: call b2s_bind_buffers first", __func__); \
+  DeviceGuard device_guard_((w)->device)
 
 template <class T>
 static int dalloc(B2SWorld* w, T** p, size_t n, int fill = 0) {
@@ -118,7 +128,6 @@ int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(B2S_E_CUDA, "b2s_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return fail(B2S_E_INVALID, "b2s_create: device %d of %d", device, ndev);
-  CU(cudaSetDevice(device));
   B2SWorld* w = new B2SWorld();
   memset(&w->d, 0, sizeof(w->d));
   w->d.P = *p;
@@ -133,7 +142,7 @@ int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
 
 int b2s_destroy(B2SWorld* w) {
   if (!w) return 0;
-  cudaSetDevice(w->device);
+  DeviceGuard device_guard_(w->device);
   for (void* p : w->allocs) cudaFree(p);
   if (w->unfinished_pinned) cudaFreeHost(w->unfinished_pinned);
   delete w;
@@ -153,7 +162,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   if (s->num_links < 1 || s->num_links > B2S_MAX_LINKS) return fail(B2S_E_INVALID, "b2s_load_scene: num_links out of range");
   if (s->num_statics < 0 || s->num_hulls <= 0 || s->num_assets <= 0 || s->num_verts <= 0) return fail(B2S_E_INVALID, "b2s_load_scene: empty hull library");
   if (s->num_movable_assets <= 0) return fail(B2S_E_INVALID, "b2s_load_scene: no movable assets (reference asserts len(movable_paths) > 0, push_env.py:107)");
-  CU(cudaSetDevice(w->device));
+  DeviceGuard device_guard_(w->device);
   DWorld& d = w->d;
   const B2SParams& P = d.P;
   // hull library: derived quantities (local AABB, bounding radius, inertia box)
@@ -304,7 +313,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     int maxE = 4 * wpb;
     while (maxE > 1 && ((size_t)maxE * (sm.words_env + META_WORDS) + (size_t)wpb * sm.words_warp) * 4 > 220 * 1024) --maxE;
     int E;
-    if (P.reserved_i[0] > 0) E = P.reserved_i[0];
+    if (P.envs_per_block > 0) E = P.envs_per_block;
     else {
       // fill whole waves of SMs (one block per SM): B = 4096 -> 28 per block -> 147 blocks
       int dev_sms = 148;
@@ -322,7 +331,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
 #ifndef B2S_EXTRA_SLOTS
 #define B2S_EXTRA_SLOTS 0
 #endif
-    if (P.reserved_i[0] <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7) + B2S_EXTRA_SLOTS);
+    if (P.envs_per_block <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7) + B2S_EXTRA_SLOTS);
     d.envs_per_block = E;
     const size_t blocks = d.num_blocks;
     if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * UNITS_PER_WARP * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
@@ -368,18 +377,27 @@ int b2s_reset(B2SWorld* w, const uint8_t* mask, uint64_t seed, void* stream) {
   return check_launch(w, "reset");
 }
 
-int b2s_settle(B2SWorld* w, float lin, float ang, int max_steps, void* stream) {
+int b2s_settle_masked(B2SWorld* w, const uint8_t* mask, float lin, float ang, int max_steps, void* stream) {
   NEED_READY(w);
   if (max_steps < 1) return fail(B2S_E_INVALID, "b2s_settle: max_steps < 1");
-  b2s_launch_substeps(w->d, 0, MODE_SETTLE, lin, ang, max_steps, (cudaStream_t)stream);
+  b2s_launch_substeps(w->d, 0, MODE_SETTLE, lin, ang, max_steps, mask, (cudaStream_t)stream);
   return check_launch(w, "settle", 2);      // deal of the environments + substep kernel
+}
+int b2s_settle(B2SWorld* w, float lin, float ang, int max_steps, void* stream) {
+  return b2s_settle_masked(w, nullptr, lin, ang, max_steps, stream);
+}
+
+int b2s_begin_episode(B2SWorld* w, const uint8_t* mask, void* stream) {
+  NEED_READY(w);
+  b2s_launch_begin_episode(w->d, mask, (cudaStream_t)stream);
+  return check_launch(w, "begin_episode");
 }
 
 int b2s_step(B2SWorld* w, int n, void* stream) {
   NEED_READY(w);
   if (n < 0) return fail(B2S_E_INVALID, "b2s_step: n < 0");
   if (n == 0) return 0;
-  b2s_launch_substeps(w->d, n, MODE_RAW, 0, 0, 0, (cudaStream_t)stream);
+  b2s_launch_substeps(w->d, n, MODE_RAW, 0, 0, 0, nullptr, (cudaStream_t)stream);
   return check_launch(w, "step", 2);
 }
 
@@ -402,7 +420,7 @@ int b2s_env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream) {
   if (n < 0) return fail(B2S_E_INVALID, "b2s_env_substeps: n < 0");
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaMemsetAsync(w->d.unfinished, 0, sizeof(int), s));
-  b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, s);
+  b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
   int rc = check_launch(w, "env_substeps", 2);
   if (rc) return rc;
   if (unfinished_host) {
@@ -493,7 +511,7 @@ int b2s_set_camera(B2SWorld* w, const float* K, const float* R, const float* t, 
     size_t o = per_env ? (size_t)e : 0;
     memcpy(&cam[(size_t)e * 21], K + o * 9, 36); memcpy(&cam[(size_t)e * 21 + 9], R + o * 9, 36); memcpy(&cam[(size_t)e * 21 + 18], t + o * 3, 12);
   }
-  CU(cudaSetDevice(w->device));
+  DeviceGuard device_guard_(w->device);
   CU(cudaMemcpy(w->d.cam, cam.data(), cam.size() * 4, cudaMemcpyHostToDevice));
   return 0;
 }
@@ -543,7 +561,7 @@ int b2s_array(B2SWorld* w, int which, void** dev_ptr, int64_t* bytes) {
   if (which < 0 || which >= B2S_ARR_COUNT || !dev_ptr || !bytes) return fail(B2S_E_INVALID, "b2s_array: bad id %d", which);
   if (which == B2S_ARR_MANIFOLD_KEYS || which == B2S_ARR_MANIFOLD_NPTS || which == B2S_ARR_MANIFOLD_PTS) {
     // gather the current ping-pong side into the export arrays (default stream, synchronous)
-    CU(cudaSetDevice(w->device));
+    DeviceGuard device_guard_(w->device);
     CU(cudaDeviceSynchronize());
     b2s_launch_export_manifolds(w->d, w->exp_keys, w->exp_npts, w->exp_pts, 0);
     int rc = check_launch(w, "export_manifolds");
@@ -559,6 +577,7 @@ int64_t b2s_launch_count(const B2SWorld* w) { return w ? w->launches : 0; }
 
 int64_t b2s_substeps_executed(B2SWorld* w, void* stream) {
   if (!w || !w->scene_loaded) return -1;
+  DeviceGuard device_guard_(w->device);
   unsigned long long v = 0;
   cudaStreamSynchronize((cudaStream_t)stream);
   if (cudaMemcpy(&v, w->d.substeps, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;

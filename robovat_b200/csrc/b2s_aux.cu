@@ -84,6 +84,7 @@ __global__ void k_reset(const __grid_constant__ DWorld W, const uint8_t* mask, u
   float table_z = 0.0f;
   for (int s = 0; s < W.Ns; ++s) if (W.static_flags[s] & B2S_STATIC_IS_TABLE) table_z = W.static_pose[s * 7 + 2] + dz;
   float px[64], py[64], pz[64], er[64], ep[64], ey[64];
+  bool placed = false;
   for (int round = 0; round < 64; ++round) {
     bool all_ok = true;
     for (int i = 0; i < n; ++i) {
@@ -114,7 +115,7 @@ __global__ void k_reset(const __grid_constant__ DWorld W, const uint8_t* mask, u
       }
       if (!ok) { all_ok = false; break; }
     }
-    if (all_ok) break;
+    if (all_ok) { placed = true; break; }
   }
   for (int i = 0; i < Nmax; ++i) {
     for (int c = 0; c < 13; ++c) BSX(c, e, i) = 0.0f;
@@ -142,7 +143,7 @@ __global__ void k_reset(const __grid_constant__ DWorld W, const uint8_t* mask, u
   for (int par = 0; par < 2; ++par)
     for (int k = 0; k < M; ++k) { W.man_keys[((size_t)par * W.B + e) * M + k] = -1; W.man_npts[((size_t)par * W.B + e) * M + k] = 0; }
   W.num_pairs[e] = 0;
-  W.error_flags[e] = 0;
+  W.error_flags[e] = placed ? 0 : 128;     // no arrangement with MARGIN clearance in 64 rounds: the host re-samples
   W.contact_flags[e] = 0;
   for (int k = 0; k < B2S_CTRL_FLOATS; ++k) W.ctrl[(size_t)e * B2S_CTRL_FLOATS + k] = 0.0f;
   for (int k = 0; k < 4; ++k) W.ctrl_flags[(size_t)e * 4 + k] = 0;
@@ -217,6 +218,18 @@ __global__ void k_set_action(const __grid_constant__ DWorld W) {
       s[0] = BSX(0, e, i); s[1] = BSX(1, e, i); s[2] = BSX(2, e, i);
       s[3] = yaw_from_q(q4(BSX(3, e, i), BSX(4, e, i), BSX(5, e, i), BSX(6, e, i)));
     } else { s[0] = s[1] = s[2] = s[3] = 0.0f; }
+  }
+}
+
+// end of RobotEnv.reset: the settled xy of the movables is the reward's "previous state" of the first step
+__global__ void k_begin_episode(const __grid_constant__ DWorld W, const uint8_t* mask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= W.B) return;
+  if (mask && !mask[e]) return;
+  const int n = W.buf.num_movables[e];
+  for (int i = 0; i < W.Nmax; ++i) {
+    W.prev_xy[((size_t)e * W.Nmax + i) * 2] = (i < n) ? BSX(0, e, i) : 0.0f;
+    W.prev_xy[((size_t)e * W.Nmax + i) * 2 + 1] = (i < n) ? BSX(1, e, i) : 0.0f;
   }
 }
 
@@ -525,8 +538,9 @@ __global__ void k_export_manifolds(const __grid_constant__ DWorld W, int32_t* ke
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int e = (int)(i / M), k = (int)(i % M);
     size_t src = ((size_t)W.man_parity[e] * W.B + e) * M + k;
-    int n = W.man_npts[src];
-    keys[i] = W.man_keys[src]; npts[i] = n;
+    const bool live = k < W.num_manifolds[e];       // slots past the count hold leftovers of earlier substeps
+    int n = live ? W.man_npts[src] : 0;
+    keys[i] = live ? W.man_keys[src] : -1; npts[i] = n;
     for (int t = 0; t < 4 * B2S_CP_FLOATS; ++t) pts[i * 4 * B2S_CP_FLOATS + t] = (t < n * B2S_CP_FLOATS) ? W.man_pts[src * 4 * B2S_CP_FLOATS + t] : 0.0f;
   }
 }
@@ -570,6 +584,7 @@ void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s) {
 }
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s) { k_reset<<<blocks_for(W.B, 64), 64, 0, s>>>(W, mask, seed); }
 void b2s_launch_set_action(const DWorld& W, cudaStream_t s) { k_set_action<<<blocks_for(W.B, 128), 128, 0, s>>>(W); }
+void b2s_launch_begin_episode(const DWorld& W, const uint8_t* mask, cudaStream_t s) { k_begin_episode<<<blocks_for(W.B, 128), 128, 0, s>>>(W, mask); }
 void b2s_launch_observe(const DWorld& W, cudaStream_t s) { k_observe<<<blocks_for(W.B, 128), 128, 0, s>>>(W); }
 void b2s_launch_reward(const DWorld& W, const float* p, const float* n, cudaStream_t s) { k_reward<<<blocks_for(W.B, 128), 128, 0, s>>>(W, p, n); }
 void b2s_launch_arm_cmd(const DWorld& W, int cmd, const float* data, const uint8_t* mask, uint8_t* out, cudaStream_t s) {

@@ -179,8 +179,23 @@ struct DWorld {
 
 enum { MODE_RAW = 0, MODE_ENV = 1, MODE_SETTLE = 2 };
 
+// The opt-in to more than 48 KB of dynamic shared memory is an attribute of (function, device): remember what was
+// configured per device, not per process (a second world on another GPU would launch unconfigured otherwise).
+#define B2S_MAX_DEVICES 64
+template <class K>
+static inline void b2s_opt_in_smem(K kernel, size_t smem, size_t* configured /* [B2S_MAX_DEVICES], zero initialised */) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= B2S_MAX_DEVICES) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); return; }
+  if (smem > configured[dev]) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured[dev] = smem;
+  }
+}
+
 // host launchers (defined next to their kernels)
-void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, cudaStream_t s);
+void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s);
+void b2s_launch_begin_episode(const DWorld& W, const uint8_t* mask, cudaStream_t s);
 void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s);
 void b2s_launch_staged(const DWorld& W, int n, cudaStream_t s, int64_t* launches);
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s);

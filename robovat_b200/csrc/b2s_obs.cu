@@ -203,8 +203,8 @@ void b2s_launch_render(const DWorld& W, cudaStream_t s) {
   const int tiles_x = (W.P.cam_width + TILE_W - 1) / TILE_W, tiles_y = (W.P.cam_height + TILE_H - 1) / TILE_H;
   const int max_cols = W.max_ray_cols;
   size_t smem = (size_t)W.max_ray_planes * sizeof(float4) + (size_t)max_cols * sizeof(RayCol);
-  static size_t configured = 0;
-  if (smem > configured) { cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+  static size_t configured[B2S_MAX_DEVICES];
+  b2s_opt_in_smem(k_render, smem, configured);
   b2s_launch_fk(W, s);                      // link poses of the current joint state
   // blocks per environment: enough blocks to fill the GPU a few times over, at most one per tile
   const int num_tiles = tiles_x * tiles_y;
@@ -219,13 +219,13 @@ void b2s_launch_render(const DWorld& W, cudaStream_t s) {
 void b2s_launch_point_cloud(const DWorld& W, uint64_t seed, cudaStream_t s) {
   const int nchunk = (W.P.cam_height * W.P.cam_width + 31) / 32;
   size_t smem = (size_t)(nchunk + 1) * sizeof(int);
-  static size_t configured = 0;
-  if (smem > configured) { cudaFuncSetAttribute(k_point_cloud, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+  static size_t configured[B2S_MAX_DEVICES];
+  b2s_opt_in_smem(k_point_cloud, smem, configured);
   k_point_cloud<<<dim3(W.B, W.Nmax), 32, smem, s>>>(W, seed);
 }
 
 // staged stepping: one launch per substep (per-substep launch/timing granularity for profiling)
 void b2s_launch_staged(const DWorld& W, int n, cudaStream_t s, int64_t* launches) {
-  for (int i = 0; i < n; ++i) b2s_launch_substeps(W, 1, MODE_RAW, 0, 0, 0, s);
+  for (int i = 0; i < n; ++i) b2s_launch_substeps(W, 1, MODE_RAW, 0, 0, 0, nullptr, s);
   *launches = n;
 }

@@ -21,6 +21,8 @@
 // colour order exactly.  The residual test is a warp reduce.  All fp32 arithmetic is ordered exactly as in
 // oracle/ (no FMA contraction), so every output matches bit for bit.  Why stages and barriers at all when the
 // environments never interact: the kernel is ~10x the instruction cache, see the note above k_substeps.
+#include <mutex>
+
 #include "b2s_dev.cuh"
 
 #define LD3(p) v3((p)[0], (p)[1], (p)[2])
@@ -191,10 +193,12 @@ __device__ __noinline__ void arm_fk_links(int e, int lane, const float* q, const
       v = v + cross(a, T.p - o) * qd[i];
       om = om + a * qd[i];
     }
-    float* lp = W.link_poses + ((size_t)e * (L + 1) + k) * 7;
-    xf_store(T, lp);
-    float* lv = W.link_vel + ((size_t)e * L + k) * 6;
-    lv[0] = v.x; lv[1] = v.y; lv[2] = v.z; lv[3] = om.x; lv[4] = om.y; lv[5] = om.z;
+    if (W.P.export_debug) {
+      float* lp = W.link_poses + ((size_t)e * (L + 1) + k) * 7;
+      xf_store(T, lp);
+      float* lv = W.link_vel + ((size_t)e * L + k) * 6;
+      lv[0] = v.x; lv[1] = v.y; lv[2] = v.z; lv[3] = om.x; lv[4] = om.y; lv[5] = om.z;
+    }
     if (body) {
       float* b = body + (W.Ns + k) * BODY_STRIDE;
       ST3(b + BO_POS, T.p);
@@ -207,7 +211,7 @@ __device__ __noinline__ void arm_fk_links(int e, int lane, const float* q, const
       b[BO_TYPE] = __int_as_float(B2S_TYPE_KINEMATIC);
       b[BO_QUAT] = T.q.x; b[BO_QUAT + 1] = T.q.y; b[BO_QUAT + 2] = T.q.z; b[BO_QUAT + 3] = T.q.w;
     }
-  } else if (lane == L) {
+  } else if (lane == L && W.P.export_debug) {
     Xf T = xf_mul(xf_from(fk + 6 * 7), xf_from(arm->ee));
     xf_store(T, W.link_poses + ((size_t)e * (L + 1) + L) * 7);
   }
@@ -1004,7 +1008,7 @@ __device__ __noinline__ int stage_scene(int e, int lane, int wib) {
   }
   if (np > P.max_pairs) { pair_over = true; np = P.max_pairs; }
   __syncwarp();
-  for (int p = lane; p < np; p += 32) W.pair_keys[(size_t)e * P.max_pairs + p] = S.pairs[p];
+  if (P.export_debug) for (int p = lane; p < np; p += 32) W.pair_keys[(size_t)e * P.max_pairs + p] = S.pairs[p];
   if (lane == 0) { W.num_pairs[e] = np; if (pair_over) W.error_flags[e] |= 1; }
   __syncwarp();
   PROF_SEC(11)
@@ -1051,7 +1055,7 @@ __device__ __noinline__ void stage_narrow_pair(int e, int lane, int wib, int p) 
   if (found != 0x7fffffff) {
     n = W.man_npts[obase + found];
     const float* src = W.man_pts + (obase + found) * 4 * B2S_CP_FLOATS;
-    for (int i = UL; i < 4 * B2S_CP_FLOATS; i += UW) {
+    for (int i = UL; i < n * B2S_CP_FLOATS; i += UW) {
       const float s0 = src[i];
       stg[i] = s0;
       if (i >= 13 && i < 16) sxu[SX_CACHE + i - 13] = s0;             // GJK simplex of the previous substep
@@ -1122,8 +1126,8 @@ __device__ __noinline__ void stage_narrow_pair(int e, int lane, int wib, int p) 
   }
   float* dst = pair_stage(wib, p);
   if (n > 0) {
-    for (int i = UL; i < 4 * B2S_CP_FLOATS; i += UW)
-      dst[i] = (i >= 13 && i < 16) ? sxu[SX_CACHE + i - 13] : ((i < n * B2S_CP_FLOATS) ? stg[i] : 0.0f);
+    for (int i = UL; i < n * B2S_CP_FLOATS; i += UW)
+      dst[i] = (i >= 13 && i < 16) ? sxu[SX_CACHE + i - 13] : stg[i];
   }
   if (UL == 0) dst[64] = __int_as_float(n);
   __syncwarp(UM);
@@ -1149,8 +1153,8 @@ __device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np
       const float* ca = S.col + (key >> 16) * COL_STRIDE;
       const float* cb = S.col + (key & 0xffff) * COL_STRIDE;
       float* dst = W.man_pts + (nbase + newn) * 4 * B2S_CP_FLOATS;
-      dst[lane] = src[lane];
-      dst[lane + 32] = src[lane + 32];
+      if (lane < n * B2S_CP_FLOATS) dst[lane] = src[lane];
+      if (lane + 32 < n * B2S_CP_FLOATS) dst[lane + 32] = src[lane + 32];
       if (lane == 0) { W.man_keys[nbase + newn] = key; W.man_npts[nbase + newn] = n; }
       const int tA = __float_as_int(ca[CO_TYPE]) & 255, tfB = __float_as_int(cb[CO_TYPE]);
       const int tB = tfB & 255;
@@ -1164,7 +1168,6 @@ __device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np
     } else man_over = true;
   }
   __syncwarp();
-  for (int k = newn + lane; k < M; k += 32) { W.man_keys[nbase + k] = -1; W.man_npts[nbase + k] = 0; }
   if (lane == 0) {
     W.num_manifolds[e] = newn;
     W.man_parity[e] = par ^ 1;
@@ -1965,7 +1968,8 @@ __device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_o
 // on 4096 envs x 100 substeps mid-push: no barriers + a ready ring of environments
 // (2.0x slower: 16 warps in 16 code regions), warps leaving the barrier protocol during long solves
 // (1.15-1.25x slower: persistent stragglers become the tail of the launch), two 8-warp blocks per SM (1.2x).
-__global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps) {
+__global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps,
+                                                                                 const uint8_t* __restrict__ env_mask) {
   __shared__ int s_cnt[4];    // hand-out counters of the three stages, candidate pairs of the block in this round
 #ifdef B2S_PROF
   __shared__ int s_maxc;
@@ -1993,7 +1997,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
         bool active;
         if (mode == MODE_RAW) active = valid && n > 0;
         else if (mode == MODE_ENV) active = valid && n > 0 && W.phase[valid ? e : 0] != B2S_PHASE_IDLE;
-        else active = valid;
+        else active = valid && (!env_mask || env_mask[valid ? e : 0]);
         if (lane == 0) env_meta(slot)[META_ACTIVE] = active ? 1 : 0;
         any |= active ? 1 : 0;
       }
@@ -2116,18 +2120,32 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
 }
 
 #undef W
-void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, cudaStream_t s) {
+// The world description of a launch sits in the device's constant bank (g_W).  One copy per device serves every
+// world and stream of the process, so launches that do not follow each other on one stream are ordered here:
+// before g_W is overwritten for a launch on another stream (or for another world), that stream waits for the last
+// kernel that read it.  Worlds on different devices never meet (a __constant__ symbol exists once per device).
+struct DevLaunch { cudaEvent_t done; cudaStream_t stream; bool have; };
+static DevLaunch g_launch[B2S_MAX_DEVICES];
+static size_t g_smem_configured[B2S_MAX_DEVICES];
+static std::mutex g_launch_mutex;
+
+void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(g_launch_mutex);
   const int wpb = W.P.warps_per_block;
   const int blocks = W.num_blocks;
   size_t smem = b2s_smem_bytes(W);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  b2s_opt_in_smem(k_substeps, smem, g_smem_configured);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevLaunch* L = (dev >= 0 && dev < B2S_MAX_DEVICES) ? &g_launch[dev] : nullptr;
+  if (L && L->have && L->stream != s) cudaStreamWaitEvent(s, L->done, 0);
   b2s_launch_assign_envs(W, mode, s);
   cudaMemcpyToSymbolAsync(g_W, &W, sizeof(DWorld), 0, cudaMemcpyHostToDevice, s);
-  k_substeps<<<blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps);
+  k_substeps<<<blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask);
+  if (L) {
+    if (!L->have) { if (cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming) == cudaSuccess) L->have = true; }
+    if (L->have) { cudaEventRecord(L->done, s); L->stream = s; }
+  }
 }
 
 size_t b2s_smem_bytes(const DWorld& W) {

@@ -212,11 +212,14 @@ class PushEnv(object):
         self._pc_seed = getattr(self, '_pc_seed', 0) + 1
         return self.world.point_cloud(seed=self.seed * 7919 + self._pc_seed).cpu().numpy()
 
-    def _refresh_attributes(self):
+    def _refresh_attributes(self, counters=True):
+        """`attributes` as PushEnv._execute_action keeps them (push_env.py:637-644, 715, 727): the counters are
+        snapshotted when the action STARTS (before `_num_steps += 1`, robot_env.py:245-246), the flags when it ends."""
         w = self.world
+        old = self.attributes or {}
         self.attributes = {
-            'num_episodes': self._num_episodes.copy(),
-            'num_steps': self._num_steps.copy(),
+            'num_episodes': self._num_episodes.copy() if counters else old['num_episodes'],
+            'num_steps': self._num_steps.copy() if counters else old['num_steps'],
             'layout_id': self.layout_id,
             'movable_body_mask': w.body_mask.cpu().numpy(),
             'is_safe': w.is_safe.cpu().numpy().astype(bool),
@@ -250,9 +253,10 @@ class PushEnv(object):
         if np.all(self._done):
             raise ValueError('The environment is done. Forget to reset?')
         active = ~self._done
+        self._refresh_attributes()                     # counters as of the start of the action
         self._execute_action(action)
         self._num_steps[active] += 1
-        self._refresh_attributes()
+        self._refresh_attributes(counters=False)       # flags as of its end
         observation = self.get_observation(force=True)
         reward, termination = self._reward_fns[0].get_reward()
         reward = np.atleast_1d(np.asarray(reward, np.float64))

@@ -163,24 +163,32 @@ class Simulator(object):
 
     def reset_scene(self, seed=0, mask=None, max_retries=8):
         """RobotEnv.reset's scene part: sample, drop, settle; re-sample envs whose bodies fell off
-        (`body.position.z < table.position.z`, push_env.py:460-468)."""
+        (`body.position.z < table.position.z`, push_env.py:460-468) or that found no placement with the MARGIN
+        clearance.  Only the envs being reset are stepped.  Raises if an env is still invalid after
+        `max_retries` re-samples (the reference would loop forever)."""
         w = self.world
         self._reset_calls += 1
-        w.reset(seed=seed * 1000003 + self._reset_calls, mask=mask)
-        for attempt in range(max_retries):
+        todo = None if mask is None else torch.as_tensor(np.asarray(mask, bool), device=w.device)
+        table_z = torch.as_tensor(self.scene.statics[self._static_index['table']]['pose'][2], device=w.device)
+        for attempt in range(max_retries + 1):
+            m8 = None if todo is None else todo.to(torch.uint8)
+            w.reset(seed=seed * 1000003 + self._reset_calls, mask=m8)
             # drop settle (0.1 / 0.1 thresholds, <=500 substeps, push_env.py:443-447) then the final wait
-            w.settle(0.1, 0.1, 500)
-            w.settle()
+            w.settle(0.1, 0.1, 500, mask=m8)
+            w.settle(mask=m8)
             z = w.body_state[2]                                   # [B, N]
-            table_z = torch.as_tensor(self.scene.statics[self._static_index['table']]['pose'][2], device=z.device) \
-                + w.array(_capi.ARR_TABLE_DZ)
             live = w.body_mask.bool()
-            bad = ((z < table_z[:, None]) & live).any(dim=1)
-            if mask is not None:
-                bad &= torch.as_tensor(mask, dtype=torch.bool, device=bad.device)
+            bad = ((z < (table_z + w.array(_capi.ARR_TABLE_DZ))[:, None]) & live).any(dim=1)
+            bad |= (w.array(_capi.ARR_ERROR_FLAGS) & 128) != 0
+            if todo is not None:
+                bad &= todo
             if not bool(bad.any()):
                 break
-            w.reset(seed=seed * 1000003 + self._reset_calls, mask=bad.to(torch.uint8))
+            todo = bad
+        else:
+            raise RuntimeError('reset_scene: %d environments have no valid arrangement after %d re-samples'
+                               % (int(bad.sum()), max_retries))
+        w.begin_episode(mask=None if mask is None else np.asarray(mask, bool))
         w.observe()
 
     def check_contact(self, entity_a, entity_b=None):

@@ -120,8 +120,14 @@ class World(object):
         m = self._mask(mask)
         self._chk(self.lib.b2s_reset(self.h, self._ptr(m), C.c_uint64(int(seed)), self._stream()))
 
-    def settle(self, lin=0.005, ang=0.005, max_steps=2000):
-        self._chk(self.lib.b2s_settle(self.h, C.c_float(lin), C.c_float(ang), int(max_steps), self._stream()))
+    def settle(self, lin=0.005, ang=0.005, max_steps=2000, mask=None):
+        m = self._mask(mask)
+        self._chk(self.lib.b2s_settle_masked(self.h, self._ptr(m), C.c_float(lin), C.c_float(ang), int(max_steps), self._stream()))
+
+    def begin_episode(self, mask=None):
+        """End of RobotEnv.reset: the settled movable xy becomes the reward's previous state."""
+        m = self._mask(mask)
+        self._chk(self.lib.b2s_begin_episode(self.h, self._ptr(m), self._stream()))
 
     def step(self, n=1):
         self._chk(self.lib.b2s_step(self.h, int(n), self._stream()))

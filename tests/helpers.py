@@ -5,7 +5,10 @@ from robovat_b200 import _capi, config
 
 
 def make_inputs(num_envs, **bindings):
-    overrides = bindings.pop('params', {})
+    overrides = dict(bindings.pop('params', {}))
+    # the parity tests look at the inspection arrays too (pair keys, link poses / velocities of every substep); the
+    # product default leaves them out of the substep kernel (params.export_debug = 0, covered by its own test)
+    overrides.setdefault('export_debug', 1)
     cfg = config.default_push_env_config(**bindings)
     scene = config.build_scene(cfg)
     params = config.build_params(cfg, scene, num_envs=num_envs, **overrides)

@@ -2,10 +2,8 @@
 stand-in env (tests/golden/episodes.json, written by oracle/gen_golden.py)."""
 import json
 import os
-import pickle
 
 import numpy as np
-import pytest
 
 from robovat_b200 import episodes
 
@@ -32,67 +30,65 @@ class ScriptedPolicy(object):
         return [observation['position'][1] * 0.5, 1.0]
 
 
-def test_generate_episode_matches_reference_driver():
+def test_batched_driver_with_one_env_matches_reference_driver():
+    """The reference's generate_episode(s) (golden, run from /root/reference on the scripted env) is the B = 1 case of
+    the batched driver: same transitions, same episode lengths over two consecutive episodes."""
     with open(GOLDEN) as f:
         cases = json.load(f)
     assert len(cases) == 3
     for case in cases:
         script = [tuple(x) for x in case['script']]
-        ep = episodes.generate_episode(ScriptedEnv(script), ScriptedPolicy(), num_steps=case['num_steps'])
+        env = ScriptedEnv(script)
+        batch = episodes.collect(env, ScriptedPolicy(), num_steps=case['num_steps'])
+        ep = batch.episodes()[0]
         assert sorted(ep.keys()) == case['keys']
-        got = [{'state': t['state'], 'action': t['action'], 'reward': t['reward'], 'info': t['info']} for t in ep['transitions']]
+        got = [{'state': {k: np.asarray(v).tolist() for k, v in t['state'].items()}, 'action': np.asarray(t['action'], np.float64).tolist(),
+                'reward': t['reward'], 'info': t['info']} for t in ep['transitions']]
         assert got == case['transitions']
-        gen = episodes.generate_episodes(ScriptedEnv(script), ScriptedPolicy(), num_steps=case['num_steps'], debug=True)
-        two = [next(gen), next(gen)]
-        assert [i for i, _ in two] == case['indices']
-        assert [len(e['transitions']) for _, e in two] == case['lengths']
+        second = episodes.collect(env, ScriptedPolicy(), num_steps=case['num_steps'])
+        assert [int(batch.lengths[0]), int(second.lengths[0])] == case['lengths']
+        assert np.isclose(batch.returns[0], sum(t['reward'] for t in case['transitions']))
 
 
-def test_generate_episodes_discards_failed_episodes_and_can_stop():
-    class Flaky(ScriptedEnv):
-        def step(self, action):
-            if self.resets == 2:
-                raise RuntimeError('boom')
-            return ScriptedEnv.step(self, action)
-    gen = episodes.generate_episodes(Flaky([(1.0, True)]), ScriptedPolicy(), num_episodes=3, timeout=0, strict=True)
-    out = list(gen)
-    assert [i for i, _ in out] == [0, 1, 2]          # the failed second attempt is discarded, indices stay dense
+class BatchEnv(object):
+    num_envs = 3
+
+    def reset(self):
+        self.t = 0
+        return {'position': np.zeros((3, 2, 3)), 'body_mask': np.ones((3, 2))}
+
+    def step(self, action):
+        self.t += 1
+        done = np.array([self.t >= 1, self.t >= 2, self.t >= 3])
+        return {'position': np.full((3, 2, 3), float(self.t)), 'body_mask': np.ones((3, 2))}, np.arange(3.0) + self.t, done, None
+
+
+class BatchPolicy(object):
+    def action(self, observation):
+        return np.tile(np.arange(4, dtype=np.float32), (3, 1)) + observation['position'][:, 0, :1]
 
 
 def test_batched_driver_slices_per_environment():
-    class BatchEnv(object):
-        num_envs = 3
-
-        def reset(self):
-            self.t = 0
-            return {'position': np.zeros((3, 2, 3)), 'body_mask': np.ones((3, 2))}
-
-        def step(self, action):
-            self.t += 1
-            done = np.array([self.t >= 1, self.t >= 2, self.t >= 3])
-            return {'position': np.full((3, 2, 3), float(self.t)), 'body_mask': np.ones((3, 2))}, np.arange(3.0) + self.t, done, None
-
-    class BatchPolicy(object):
-        def action(self, observation):
-            return np.tile(np.arange(4, dtype=np.float32), (3, 1)) + observation['position'][:, 0, :1]
-    eps = episodes.generate_batched_episodes(BatchEnv(), BatchPolicy())
+    batch = episodes.collect(BatchEnv(), BatchPolicy())
+    assert batch.lengths.tolist() == [1, 2, 3] and batch.actions.shape == (3, 3, 4)
+    np.testing.assert_allclose(batch.returns, [1.0, 2.0 + 3.0, 3.0 + 4.0 + 5.0])     # rewards after an env's done do not count
+    eps = batch.episodes()
     assert [len(e['transitions']) for e in eps] == [1, 2, 3]
     assert eps[2]['transitions'][1]['state']['position'].shape == (2, 3)
     assert eps[1]['transitions'][1]['reward'] == 3.0 and eps[1]['transitions'][1]['action'].shape == (4,)
+    assert episodes.generate_batched_episodes(BatchEnv(), BatchPolicy(), num_steps=2)[2]['transitions'][1]['reward'] == 4.0
 
 
-def test_pickle_writer_file_format(tmp_path):
-    writer = episodes.PickleWriter(str(tmp_path), num_entries_per_file=2, use_random_name=False)
-    for i in range(5):
-        writer({'timestamp': str(i), 'transitions': [{'reward': float(i)}]})
-    writer.close()
-    files = sorted(os.listdir(str(tmp_path)))
-    assert files == ['data_000000.pickle', 'data_000001.pickle', 'data_000002.pickle']
-    assert [len(episodes.read_all(str(tmp_path / f))) for f in files] == [2, 2, 1]
-    with open(str(tmp_path / files[0]), 'rb') as f:          # a plain stream of pickles, as the reference reads it
-        assert pickle.load(f)['timestamp'] == '0' and pickle.load(f)['timestamp'] == '1'
-        with pytest.raises(EOFError):
-            pickle.load(f)
+def test_shard_round_trip(tmp_path):
+    writer = episodes.ShardWriter(str(tmp_path))
+    batch = episodes.collect(BatchEnv(), BatchPolicy())
+    paths = [writer(batch), writer(batch)]
+    assert sorted(os.listdir(str(tmp_path))) == ['episodes_000000.npz', 'episodes_000001.npz']
+    back = episodes.read_shard(paths[1])
+    assert back.lengths.tolist() == [1, 2, 3] and back.timestamp == batch.timestamp
+    np.testing.assert_array_equal(back.actions, batch.actions)
+    np.testing.assert_array_equal(back.states['position'], batch.states['position'])
+    np.testing.assert_array_equal(back.final['position'], batch.final['position'])
 
 
 def test_batched_sampler_is_distribution_equivalent_to_the_scalar_one():

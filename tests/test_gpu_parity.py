@@ -255,23 +255,24 @@ def test_physics_plugin_calls_match():
     helpers.assert_bits_equal(outs[0], outs[1], 'plugin trace')
 
 
-def test_episode_drivers_on_the_cuda_env():
-    """robovat_b200.episodes over the CUDA PushEnv: the reference's single-env loop with HeuristicPushPolicy and the
-    batched loop with the vectorised policy."""
+def test_episode_driver_on_the_cuda_env():
+    """robovat_b200.episodes over the CUDA PushEnv: a single env with the reference-identical HeuristicPushPolicy and a
+    batch with the vectorised policy."""
     from robovat_b200 import config, episodes, policies
     from robovat_b200.envs import PushEnv
     cfg = config.default_push_env_config()
     env = PushEnv(config=cfg, num_envs=1, seed=3)
-    ep = episodes.generate_episode(env, policies.HeuristicPushPolicy(env), num_steps=2)
+    ep = episodes.collect(env, policies.HeuristicPushPolicy(env), num_steps=2).episodes()[0]
     assert 1 <= len(ep['transitions']) <= 2
     t0 = ep['transitions'][0]
     assert np.asarray(t0['action']).shape[-1] == 4 and np.isfinite(t0['reward'])
     assert np.asarray(t0['state']['position']).shape == (int(cfg.MAX_MOVABLE_BODIES), 3)
     env.close()
     env = PushEnv(config=cfg, num_envs=8, seed=3)
-    eps = episodes.generate_batched_episodes(env, policies.BatchedHeuristicPolicy(seed=1), num_steps=2)
+    batch = episodes.collect(env, policies.BatchedHeuristicPolicy(seed=1), num_steps=2)
+    eps = batch.episodes()
     assert len(eps) == 8 and all(1 <= len(e['transitions']) <= 2 for e in eps)
-    assert all(np.isfinite(t['reward']) for e in eps for t in e['transitions'])
+    assert np.isfinite(batch.returns).all()
     assert eps[0]['transitions'][0]['state']['position'].shape == (int(cfg.MAX_MOVABLE_BODIES), 3)
     env.close()
 
