@@ -59,6 +59,10 @@ B2S_HD float vget(b2s_v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z);
 /* sin and cos of x (|x| < ~1e4), Cody-Waite reduction to [-pi/4, pi/4] and
  * the classic single-precision minimax polynomials. */
 B2S_HD void b2s_sincos(float x, float* s, float* c) {
+#ifdef B2S_F64
+  *s = sin(x); *c = cos(x);       /* double-precision oracle build (oracle/b2o_f64.h): libm, not the fp32 polynomials */
+  return;
+#endif
   float k = rintf(x * 0.63661977236758134308f);       /* x * 2/pi */
   float r = x - k * 1.5703125f;
   r = r - k * 4.837512969970703125e-4f;
@@ -89,6 +93,9 @@ B2S_HD float b2s_atan_pos(float x) {
 }
 
 B2S_HD float b2s_atan2(float y, float x) {
+#ifdef B2S_F64
+  if (x != 0.0f) return atan2(y, x);
+#endif
   if (x == 0.0f) {
     if (y > 0.0f) return B2S_HALF_PI;
     if (y < 0.0f) return -B2S_HALF_PI;

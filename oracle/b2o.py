@@ -14,6 +14,7 @@ from robovat_b200 import _capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libb2o.so')
+LIB64_PATH = os.path.join(HERE, 'libb2o64.so')      # the same sources in double precision (b2o_f64.h)
 
 BUF_IDS = {'body_state': 100, 'joint_state': 101, 'action': 102, 'obs_position': 103,
            'num_movables': 104, 'body_mask': 105, 'depth': 106, 'segmask': 107, 'point_cloud': 108,
@@ -31,27 +32,33 @@ DTYPES = {
     106: np.float32, 107: np.uint8, 108: np.float32, 109: np.float32, 110: np.uint8, 111: np.uint8,
     112: np.uint8, 113: np.float32,
 }
-_lib = None
+_libs = {}
 
 
 def build():
-    subprocess.check_call(['make', '-s', '-C', HERE])
+    subprocess.check_call(['make', '-s', '-C', HERE, 'all'])
 
 
-def load():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def load(f64=False):
+    if f64 not in _libs:
+        path = LIB64_PATH if f64 else LIB_PATH
+        if not os.path.exists(path):
             build()
-        _lib = C.CDLL(LIB_PATH)
-        _lib.b2o_last_error.restype = C.c_char_p
-        _lib.b2o_substeps_executed.restype = C.c_int64
-    return _lib
+        lib = C.CDLL(path)
+        lib.b2o_last_error.restype = C.c_char_p
+        lib.b2o_substeps_executed.restype = C.c_int64
+        _libs[f64] = lib
+    return _libs[f64]
 
 
 class OracleWorld(object):
-    def __init__(self, params, scene, threads=1):
-        self.lib = load()
+    """f64=True: the double-precision build; every float array / argument of this wrapper is then float64."""
+
+    def __init__(self, params, scene, threads=1, f64=False):
+        self.lib = load(f64)
+        self.f64 = bool(f64)
+        self.real = np.float64 if f64 else np.float32
+        self.creal = C.c_double if f64 else C.c_float
         self.params = params
         self.scene = scene
         self.h = C.c_void_p()
@@ -75,6 +82,8 @@ class OracleWorld(object):
         ptr, nbytes = C.c_void_p(), C.c_int64()
         self._chk(self.lib.b2o_array(self.h, which, C.byref(ptr), C.byref(nbytes)))
         dt = np.dtype(DTYPES[which])
+        if dt == np.float32:
+            dt = np.dtype(self.real)
         n = nbytes.value // dt.itemsize
         if n == 0:
             return np.zeros(0, dtype=dt)
@@ -98,10 +107,10 @@ class OracleWorld(object):
 
     def settle(self, lin=0.005, ang=0.005, max_steps=2000, mask=None):
         if mask is None:
-            self._chk(self.lib.b2o_settle(self.h, C.c_float(lin), C.c_float(ang), int(max_steps)))
+            self._chk(self.lib.b2o_settle(self.h, self.creal(lin), self.creal(ang), int(max_steps)))
         else:
             m = np.ascontiguousarray(mask, np.uint8)
-            self._chk(self.lib.b2o_settle_masked(self.h, m.ctypes.data_as(C.c_void_p), C.c_float(lin), C.c_float(ang), int(max_steps)))
+            self._chk(self.lib.b2o_settle_masked(self.h, m.ctypes.data_as(C.c_void_p), self.creal(lin), self.creal(ang), int(max_steps)))
 
     def begin_episode(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
@@ -120,18 +129,18 @@ class OracleWorld(object):
         return u.value
 
     def move_to_gripper_pose(self, pose, mask=None):
-        p = np.ascontiguousarray(pose, np.float32)
+        p = np.ascontiguousarray(pose, self.real)
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
         self._chk(self.lib.b2o_arm_move_to_gripper_pose(self.h, p.ctypes.data_as(C.c_void_p), m))
 
     def move_to_joint_positions(self, q, mask=None):
-        p = np.ascontiguousarray(q, np.float32)
+        p = np.ascontiguousarray(q, self.real)
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
         self._chk(self.lib.b2o_arm_move_to_joint_positions(self.h, p.ctypes.data_as(C.c_void_p), m))
 
     def set_motor_targets(self, q, qd=None, mask=None):
-        a = np.ascontiguousarray(q, np.float32)
-        b = None if qd is None else np.ascontiguousarray(qd, np.float32)
+        a = np.ascontiguousarray(q, self.real)
+        b = None if qd is None else np.ascontiguousarray(qd, self.real)
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p)
         self._chk(self.lib.b2o_set_motor_targets(self.h, a.ctypes.data_as(C.c_void_p),
                                                  None if b is None else b.ctypes.data_as(C.c_void_p), m))
@@ -153,9 +162,9 @@ class OracleWorld(object):
         return out
 
     def inverse_kinematics(self, pose, q_start):
-        p = np.ascontiguousarray(pose, np.float32)
-        qs = np.ascontiguousarray(q_start, np.float32)
-        out = np.zeros((7, self.B), np.float32)
+        p = np.ascontiguousarray(pose, self.real)
+        qs = np.ascontiguousarray(q_start, self.real)
+        out = np.zeros((7, self.B), self.real)
         self._chk(self.lib.b2o_inverse_kinematics(self.h, p.ctypes.data_as(C.c_void_p), qs.ctypes.data_as(C.c_void_p),
                                                   out.ctypes.data_as(C.c_void_p)))
         return out
@@ -169,15 +178,15 @@ class OracleWorld(object):
         return self.array('obs_position').reshape(self.B, self.N, 3)
 
     def reward(self, prev_xy=None, next_xy=None):
-        a = None if prev_xy is None else np.ascontiguousarray(prev_xy, np.float32)
-        b = None if next_xy is None else np.ascontiguousarray(next_xy, np.float32)
+        a = None if prev_xy is None else np.ascontiguousarray(prev_xy, self.real)
+        b = None if next_xy is None else np.ascontiguousarray(next_xy, self.real)
         self._chk(self.lib.b2o_reward(self.h, None if a is None else a.ctypes.data_as(C.c_void_p),
                                       None if b is None else b.ctypes.data_as(C.c_void_p)))
         return self.array('reward').copy(), self.array('termination').copy()
 
     def set_camera(self, K, R, t, per_env=False):
-        K, R, t = (np.ascontiguousarray(x, np.float32) for x in (K, R, t))
-        fp = C.POINTER(C.c_float)
+        K, R, t = (np.ascontiguousarray(x, self.real) for x in (K, R, t))
+        fp = C.POINTER(self.creal)
         self._chk(self.lib.b2o_set_camera(self.h, K.ctypes.data_as(fp), R.ctypes.data_as(fp), t.ctypes.data_as(fp),
                                           int(bool(per_env))))
 

@@ -25,6 +25,9 @@ namespace b2o {
 
 struct Xf { V3 p; Q4 q; };
 static Xf xf_from(const float* a) { Xf t; t.p = v3(a[0], a[1], a[2]); t.q = q4(a[3], a[4], a[5], a[6]); return t; }
+#ifdef B2S_F64
+static Xf xf_from(const abi_float* a) { Xf t; t.p = v3(a[0], a[1], a[2]); t.q = q4(a[3], a[4], a[5], a[6]); return t; }
+#endif
 static Xf xf_mul(Xf a, Xf b) { Xf t; t.p = a.p + qrot(a.q, b.p); t.q = qmul(a.q, b.q); return t; }
 static void xf_store(Xf t, float* o) { o[0] = t.p.x; o[1] = t.p.y; o[2] = t.p.z; o[3] = t.q.x; o[4] = t.q.y; o[5] = t.q.z; o[6] = t.q.w; }
 

@@ -234,7 +234,8 @@ int b2o_set_camera(World* w, const float* K, const float* R, const float* t, int
   w->cam_per_env = per_env;
   for (int e = 0; e < w->B; ++e) {
     size_t o = per_env ? (size_t)e : 0;
-    memcpy(&w->cam[(size_t)e * 21], K + o * 9, 36); memcpy(&w->cam[(size_t)e * 21 + 9], R + o * 9, 36); memcpy(&w->cam[(size_t)e * 21 + 18], t + o * 3, 12);
+    memcpy(&w->cam[(size_t)e * 21], K + o * 9, sizeof(float) * 9); memcpy(&w->cam[(size_t)e * 21 + 9], R + o * 9, sizeof(float) * 9);
+    memcpy(&w->cam[(size_t)e * 21 + 18], t + o * 3, sizeof(float) * 3);
   }
   return 0;
 }

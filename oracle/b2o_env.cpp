@@ -65,7 +65,7 @@ void reset_env(World& w, int e, uint64_t seed) {
         const bool use_target = (i == 0 && d.num_target > 0);
         const int nt = use_target ? d.num_target : d.num_obstacle;
         if (nt > 0) {
-          const float(*tiles)[2] = use_target ? d.target : d.obstacle;
+          const abi_float(*tiles)[2] = use_target ? d.target : d.obstacle;
           int t = rng.below(nt);
           x = rng.uni(d.tile_offset[0] + (tiles[t][0] - 0.5f) * d.tile_size, d.tile_offset[0] + (tiles[t][0] + 0.5f) * d.tile_size);
           y = rng.uni(d.tile_offset[1] + (tiles[t][1] - 0.5f) * d.tile_size, d.tile_offset[1] + (tiles[t][1] + 0.5f) * d.tile_size);
@@ -125,10 +125,10 @@ void reset_env(World& w, int e, uint64_t seed) {
   w.episode_return[e] = 0.0f; w.reward[e] = 0.0f; w.termination[e] = 0;
   build_colliders(w, e);
   /* ArmEnv._reset_robot: move_to_joint_positions(OFFSTAGE_POSITIONS) (arm_env.py:101-107) */
-  arm_reset_targets(w, e);
-  arm_set_joint_target(w, e, P.offstage_positions);
   float q[7], qd[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int j = 0; j < 7; ++j) q[j] = P.offstage_positions[j];
+  arm_reset_targets(w, e);
+  arm_set_joint_target(w, e, q);
   arm_fk(w, q, qd, &w.link_poses[(size_t)e * (w.L + 1) * 7], &w.link_vel[(size_t)e * w.L * 6]);
   observe(w, e);
   for (int i = 0; i < Nmax; ++i) { w.prev_xy[((size_t)e * Nmax + i) * 2] = w.obs_position[((size_t)e * Nmax + i) * 3]; w.prev_xy[((size_t)e * Nmax + i) * 2 + 1] = w.obs_position[((size_t)e * Nmax + i) * 3 + 1]; }
@@ -202,11 +202,15 @@ static void phase_logic(World& w, int e) {
     ps[0] = nsteps + (ph == B2S_PHASE_MOTION ? P.max_motion_steps : ph == B2S_PHASE_OFFSTAGE ? P.max_offstage_steps : P.max_phase_steps);
     const float* wp = &w.waypoints[(size_t)e * 14];
     float pose[7];
-    if (ph == B2S_PHASE_PRE) { memcpy(pose, wp, 28); pose[2] = P.gripper_safe_height; arm_reset_targets(w, e); arm_set_link_target(w, e, pose); }
+    if (ph == B2S_PHASE_PRE) { memcpy(pose, wp, sizeof(float) * 7); pose[2] = P.gripper_safe_height; arm_reset_targets(w, e); arm_set_link_target(w, e, pose); }
     else if (ph == B2S_PHASE_START) { arm_reset_targets(w, e); arm_set_link_target(w, e, wp); }
     else if (ph == B2S_PHASE_MOTION) { arm_reset_targets(w, e); arm_set_link_target(w, e, wp + 7); }
-    else if (ph == B2S_PHASE_POST) { ps[1] += 1; memcpy(pose, ee, 28); pose[2] = P.gripper_safe_height; arm_reset_targets(w, e); arm_set_link_target(w, e, pose); }
-    else if (ph == B2S_PHASE_OFFSTAGE) { arm_reset_targets(w, e); arm_set_joint_target(w, e, P.offstage_positions); }
+    else if (ph == B2S_PHASE_POST) { ps[1] += 1; memcpy(pose, ee, sizeof(float) * 7); pose[2] = P.gripper_safe_height; arm_reset_targets(w, e); arm_set_link_target(w, e, pose); }
+    else if (ph == B2S_PHASE_OFFSTAGE) {
+      float qo[7];
+      for (int j = 0; j < 7; ++j) qo[j] = P.offstage_positions[j];
+      arm_reset_targets(w, e); arm_set_joint_target(w, e, qo);
+    }
   }
   interrupt = false;
   const int cf = w.contact_flags[e];
@@ -278,7 +282,7 @@ void env_substep(World& w, int e) {
 }
 
 /* ------------------------------------------------------------- reward ---- */
-static bool on_tiles(float x, float y, const float (*tiles)[2], int nt, float size, const float* off, float max_dist) {
+static bool on_tiles(float x, float y, const abi_float (*tiles)[2], int nt, float size, const abi_float* off, float max_dist) {
   /* check_on_tiles (push_reward.py:57-67) */
   bool any = false;
   for (int t = 0; t < nt; ++t) {
@@ -287,7 +291,7 @@ static bool on_tiles(float x, float y, const float (*tiles)[2], int nt, float si
   }
   return any;
 }
-static float tile_dist(float x, float y, const float (*tiles)[2], int nt, float size, const float* off) {
+static float tile_dist(float x, float y, const abi_float (*tiles)[2], int nt, float size, const abi_float* off) {
   /* get_tile_dists (push_reward.py:70-75) */
   float best = 3e38f;
   for (int t = 0; t < nt; ++t) {

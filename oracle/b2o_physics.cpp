@@ -153,6 +153,8 @@ static int gjk(const World& w, const ColX& A, const ColX& B, float limit, Simple
     for (int k = 0; k < sx->n; ++k) if (sx->ia[k] == ia && sx->ib[k] == ib) dup = true;
     if (dup) break;
     if (have && (vv - vw) <= vv * 1e-6f) break;
+    const Simplex prev = *sx;                   /* the simplex v was computed from, and its weights */
+    const float pb0 = bary[0], pb1 = bary[1], pb2 = bary[2], pb3 = bary[3];
     int n = sx->n;
     sx->w[n] = ww; sx->a[n] = a; sx->b[n] = b; sx->ia[n] = ia; sx->ib[n] = ib;
     sx->n = n + 1;
@@ -172,7 +174,13 @@ static int gjk(const World& w, const ColX& A, const ColX& B, float limit, Simple
     sx->n = m;
     float nv = len2(r.v);
     if (nv < 1e-14f) { status = 2; break; }
-    if (have && nv >= vv) { v = r.v; break; }   /* no progress: keep the newest consistent state */
+    if (have && nv >= vv) {
+      /* no progress (converged to rounding, or the new vertex made a flat simplex whose sub-simplex search lost
+       * ground): the previous simplex stays the answer -- v, witness weights and cache all refer to it */
+      *sx = prev;
+      bary[0] = pb0; bary[1] = pb1; bary[2] = pb2; bary[3] = pb3;
+      break;
+    }
     v = r.v;
     have = true;
   }

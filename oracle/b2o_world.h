@@ -29,6 +29,10 @@
 #include "../include/b2s_geom.h"
 #include "../include/b2s_math.h"
 
+#ifndef B2S_F64
+typedef float abi_float;     /* the float of the C-ABI structures (only differs from `float` in the double build, b2o_f64.h) */
+#endif
+
 namespace b2o {
 
 typedef b2s_v3 V3;

@@ -556,11 +556,13 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
         ++m;
       }
     }
+    float nv = len2(r.v);
+    // no progress (converged to rounding, or the new vertex made a flat simplex whose sub-simplex search lost ground):
+    // the previous simplex stays the answer -- perm / ids / n / weights still describe it, its slots were not touched
+    if (!warm && have && nv >= vv && nv >= 1e-14f) break;
     perm = nperm; ids = nids; n = m;
     bary0 = nb0; bary1 = nb1; bary2 = nb2; bary3 = nb3;
-    float nv = len2(r.v);
     if (nv < 1e-14f) { status = 2; break; }
-    if (!warm && have && nv >= vv) { v = r.v; break; }
     v = r.v;
     have = true;
     if (warm) { warm = false; --it; }    // the warm start is not one of the gjk_max_iters iterations
