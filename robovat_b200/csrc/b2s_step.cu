@@ -559,7 +559,12 @@ __device__ __noinline__ int gjk(const ColRef& A_in, const ColRef& B_in, float li
     float nv = len2(r.v);
     // no progress (converged to rounding, or the new vertex made a flat simplex whose sub-simplex search lost ground):
     // the previous simplex stays the answer -- perm / ids / n / weights still describe it, its slots were not touched
-    if (!warm && have && nv >= vv && nv >= 1e-14f) break;
+    if (!warm && have && nv >= vv && nv >= 1e-14f) {
+      n = n - 1;                                   // drop the vertex appended above (logical entry n)
+      ids &= ~(0xffffull << (16 * n));
+      perm &= ~(3u << (2 * n));
+      break;
+    }
     perm = nperm; ids = nids; n = m;
     bary0 = nb0; bary1 = nb1; bary2 = nb2; bary3 = nb3;
     if (nv < 1e-14f) { status = 2; break; }

@@ -1,9 +1,10 @@
 #!/bin/bash
-# quick GPU iteration: parity tests + mid-push timing (+ optional ncu full capture when $2 = ncu)
-TAG=${1:-q}; OUT=gpurun_out/$TAG; mkdir -p $OUT
-timeout -s KILL 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee $OUT/pytest.log
-timeout -s KILL 120 python tools/profile_step.py 4096 100 4 600 2>&1 | tail -4 | tee $OUT/profile_step.log
-if [ "$2" = "ncu" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_substeps -c 1 \
-    -o $OUT/k_substeps_full -f python tools/profile_step.py 4096 50 3 600 > $OUT/ncu.log 2>&1; echo "ncu rc=$?"
-fi
+# One short gpurun call: GPU parity tests, smoke, a 3-step bench.   usage: gpurun --timeout 900 -- 'bash tools/gpu_quick.sh [tag]'
+TAG=${1:-quick}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+tail -40 $OUT/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
+timeout 600 python bench.py --steps 3 --warmup 3 ${BENCH_ARGS} > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err
