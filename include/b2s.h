@@ -50,7 +50,10 @@ enum {
   B2S_PHASE_INITIAL = 0, B2S_PHASE_PRE = 1, B2S_PHASE_START = 2, B2S_PHASE_MOTION = 3,
   B2S_PHASE_POST = 4, B2S_PHASE_OFFSTAGE = 5, B2S_PHASE_DONE = 6,
   B2S_PHASE_SETTLE = 7,            /* Simulator.wait_until_stable after 'done' (push_env.py:723) */
-  B2S_PHASE_IDLE = 8               /* no action in flight: env is frozen by b2s_env_substeps */
+  B2S_PHASE_IDLE = 8,              /* no action in flight: env is frozen by b2s_env_substeps */
+  /* between two episodes of a device-side rollout (b2s_rollout_*): the freshly sampled scene drops
+   * (wait_until_stable with the loose thresholds, push_env.py:443-447), then the final wait (:456-458) */
+  B2S_PHASE_RESET_DROP = 9, B2S_PHASE_RESET_WAIT = 10
 };
 
 /* reward tasks (push_reward.py:283-296) */
@@ -224,7 +227,8 @@ enum {
   B2S_ARR_TABLE_DZ = 12,       /* float [B] */
   B2S_ARR_ERROR_FLAGS = 13,    /* int32 [B] bit0 pair overflow, bit1 manifold overflow, bit2 non-finite state,
                                   bit3 contact overflow, bit4 colour overflow, bit5 collider overflow, bit6 solver invariant,
-                                  bit7 reset found no placement with the MARGIN clearance (re-sample the env) */
+                                  bit7 reset found no placement with the MARGIN clearance (re-sample the env),
+                                  bit8 a rollout's reset found no valid scene in max_reset_retries re-samples (the env stops) */
   B2S_ARR_WAYPOINTS = 14,      /* float [B][2][7] start / end gripper poses */
   B2S_ARR_STATUS = 15,         /* float [B][2][Nmax][4] start/end status: pos3 + yaw (push_env.py:925-937) */
   B2S_ARR_CONTACT_FLAGS = 16,  /* int32 [B] bit0 arm-table, bit1 arm-movable, per last substep */
@@ -236,7 +240,9 @@ enum {
   B2S_ARR_COL_SLOT = 22,       /* int32 [B][max_colliders] body slot of each collider */
   B2S_ARR_COL_HULL = 23,       /* int32 [B][max_colliders] hull id of each collider */
   B2S_ARR_PROF = 24,           /* uint64 [8] stage timing of the substep kernel (ns; tuning builds only) */
-  B2S_ARR_COUNT = 25
+  B2S_ARR_NUM_EPISODES = 25,   /* int32 [B] episodes finished by b2s_rollout_* (RobotEnv.num_episodes, robot_env.py:262) */
+  B2S_ARR_ROLLOUT_STATE = 26,  /* int32 [B][4] rollout: steps of the current episode, episodes of this rollout, re-samples, spare */
+  B2S_ARR_COUNT = 27
 };
 #define B2S_CP_FLOATS 16   /* localA3 localB3 normalB3 dist lambda_n lambda_t1 lambda_t2, then 3 spare words: in point 0 of a
                               manifold they hold the GJK simplex of the pair's last call (int n, (ia | ib << 8) x 4) */
@@ -288,6 +294,42 @@ int b2s_env_substeps(B2SWorld* world, int n_substeps, int* unfinished_host, void
 /* convenience: set_action + env_substeps until every env finished (or max_substeps) */
 int b2s_env_step(B2SWorld* world, int chunk, int max_substeps, void* stream);
 
+/* Episodes on the device: the loops of robovat/io/episode_generation.py:41-61 (`action = policy.action(obs);
+ * obs, reward, done, _ = env.step(action)` until done or num_steps) and :88-112 (episode after episode, `env.reset()`
+ * in between) with HeuristicPushPolicy (robovat/policies/push_policy.py:33-52 over heuristic_push_sampler.py:66-123),
+ * for every env independently and without returning to the host: an env that finishes an action computes its reward
+ * (PushReward), records the transition, draws its next action and starts it inside the same kernel launch; an env
+ * whose episode is over samples its next scene, lets it drop and settle (re-sampling scenes whose bodies fell off the
+ * table) and starts the next episode.  Nobody waits for the slowest env of the batch -- this is what
+ * tools/parallel_run.py's independent worker processes amount to.  All pointers are device pointers owned by the
+ * caller; output pointers may be NULL.  Records of episode ep of env e start at index (e * num_episodes + ep). */
+typedef struct B2SRollout {
+  int32_t num_actions;         /* A: steps per episode at most (config MAX_STEPS) */
+  int32_t max_attempts;        /* HEURISTICS.MAX_ATTEMPS of the rejection sampler (1..65535) */
+  int32_t num_episodes;        /* EP: episodes per env in this rollout; an env goes idle after its last one */
+  int32_t max_reset_retries;   /* re-samples of a scene that came out invalid before the env gives up (error bit8) */
+  uint64_t seed;               /* policy seed: Philox key; counter = (stream 1, step, global env id, RobotEnv.num_episodes, attempt) */
+  uint64_t reset_seed;         /* scene seed of the resets between episodes (as b2s_reset's seed) */
+  float drop_lin_threshold, drop_ang_threshold;   /* 0.1, 0.1  push_env.py:443-447 */
+  int32_t drop_max_steps;      /* 500 */
+  int32_t reserved;
+  const float* first_action;   /* [B][4] action of step 0 of episode 0, or NULL: drawn by the device policy like the others */
+  float* actions;              /* out [B][EP][A][4] */
+  float* rewards;              /* out [B][EP][A] */
+  float* positions;            /* out [B][EP][A+1][Nmax][3] PoseObs 'position' before step 0 and after every step */
+  uint8_t* flags;              /* out [B][EP][A] bit0 is_safe, bit1 is_effective, bit2 termination (reward fn), bit3 unsafe at 'done' */
+  int32_t* substeps;           /* out [B][EP][A] Simulator.num_steps after the step */
+  int32_t* lengths;            /* out [B][EP] steps taken (the episode stops at termination / unsafe-at-done / A) */
+  float* returns;              /* out [B][EP] RobotEnv.episode_reward at the end of the episode */
+} B2SRollout;
+/* starts episode 0 in every env from its current (reset and settled) state */
+int b2s_rollout_begin(B2SWorld* world, const B2SRollout* rollout, void* stream);
+/* advances the rollout by launches of `chunk` substeps queued back to back until every env has finished its last
+ * episode or max_substeps per env were launched (the count of unfinished envs is read back asynchronously two launches
+ * behind, so the queue never drains).  *unfinished_host (may be NULL) receives the final count after synchronising the
+ * stream.  May be called repeatedly: a rollout keeps its state between calls. */
+int b2s_rollout_run(B2SWorld* world, int chunk, int max_substeps, int* unfinished_host, void* stream);
+
 /* robot commands outside the phase machine (sawyer_sim.py:186-308); poses/q are device pointers */
 int b2s_arm_move_to_gripper_pose(B2SWorld* world, const float* pose_dev /*[B][7]*/, const uint8_t* env_mask_dev, void* stream);
 int b2s_arm_move_to_joint_positions(B2SWorld* world, const float* q_dev /*[B][7]*/, const uint8_t* env_mask_dev, void* stream);
@@ -329,7 +371,7 @@ int b2s_allgather_returns(B2SWorld* world, void* nccl_comm, float* out_dev, void
 
 /* inspection: device pointer + byte size of a world-owned array */
 int b2s_array(B2SWorld* world, int which, void** dev_ptr, int64_t* bytes);
-/* sizeof(B2SParams / B2SSceneDesc / B2SBuffers) for which = 0 / 1 / 2: lets a binding check its layout */
+/* sizeof(B2SParams / B2SSceneDesc / B2SBuffers / B2SRollout) for which = 0 / 1 / 2 / 3: lets a binding check its layout */
 int b2s_sizeof(int which);
 /* number of kernels this library has launched on this world since creation */
 int64_t b2s_launch_count(const B2SWorld* world);

@@ -28,6 +28,7 @@ DTYPES = {
     _capi.ARR_STATUS: np.float32, _capi.ARR_CONTACT_FLAGS: np.int32, _capi.ARR_PHASE_STATE: np.int32,
     _capi.ARR_SOLVER_STATS: np.int32, _capi.ARR_CTRL_TIME: np.float64, _capi.ARR_LINK_VEL: np.float32,
     _capi.ARR_NUM_COLLIDERS: np.int32, _capi.ARR_COL_SLOT: np.int32, _capi.ARR_COL_HULL: np.int32,
+    _capi.ARR_NUM_EPISODES: np.int32, _capi.ARR_ROLLOUT_STATE: np.int32,
     100: np.float32, 101: np.float32, 102: np.float32, 103: np.float32, 104: np.int32, 105: np.uint8,
     106: np.float32, 107: np.uint8, 108: np.float32, 109: np.float32, 110: np.uint8, 111: np.uint8,
     112: np.uint8, 113: np.float32,
@@ -127,6 +128,41 @@ class OracleWorld(object):
         u = C.c_int()
         self._chk(self.lib.b2o_env_substeps(self.h, int(n), C.byref(u)))
         return u.value
+
+    # -- episodes without the host (b2s_rollout_*) ----------------------------------------------
+    def rollout_begin(self, num_actions, num_episodes=1, policy_seed=0, reset_seed=0, max_attempts=20000,
+                      first_action=None, positions=True, max_reset_retries=8, drop_thresholds=(0.1, 0.1, 500)):
+        """Returns the record: dict of numpy arrays with the layouts of B2SRollout."""
+        B, N, EP, A = self.B, self.N, int(num_episodes), int(num_actions)
+        rec = {'actions': np.zeros((B, EP, A, 4), self.real), 'rewards': np.zeros((B, EP, A), self.real),
+               'positions': np.zeros((B, EP, A + 1, N, 3), self.real) if positions else None,
+               'flags': np.zeros((B, EP, A), np.uint8), 'substeps': np.zeros((B, EP, A), np.int32),
+               'lengths': np.zeros((B, EP), np.int32), 'returns': np.zeros((B, EP), self.real)}
+        r = _capi.B2SRollout()
+        r.num_actions, r.num_episodes, r.max_attempts = A, EP, int(min(max_attempts, 65535))
+        r.max_reset_retries = int(max_reset_retries)
+        r.seed, r.reset_seed = int(policy_seed), int(reset_seed)
+        r.drop_lin_threshold, r.drop_ang_threshold, r.drop_max_steps = float(drop_thresholds[0]), float(drop_thresholds[1]), int(drop_thresholds[2])
+        for k in ('flags', 'substeps', 'lengths'):
+            setattr(r, k, rec[k].ctypes.data)
+        fa = None if first_action is None else np.ascontiguousarray(first_action, self.real).reshape(B, 4)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._rollout_keepalive = (rec, fa)
+        self._chk(self.lib.b2o_rollout_begin(self.h, C.byref(r), vp(fa), vp(rec['actions']), vp(rec['rewards']),
+                                             vp(rec['positions']), vp(rec['returns'])))
+        return rec
+
+    def rollout_run(self, n):
+        u = C.c_int()
+        self._chk(self.lib.b2o_rollout_run(self.h, int(n), C.byref(u)))
+        return u.value
+
+    def policy_sample(self, seed, action_index, num_episodes, max_attempts=20000):
+        out = np.zeros((self.B, 4), self.real)
+        ne = np.ascontiguousarray(np.broadcast_to(np.asarray(num_episodes, np.int32), (self.B,)))
+        self._chk(self.lib.b2o_policy_sample(self.h, C.c_uint64(int(seed)), int(action_index), ne.ctypes.data_as(C.c_void_p),
+                                             int(min(max_attempts, 65535)), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def move_to_gripper_pose(self, pose, mask=None):
         p = np.ascontiguousarray(pose, self.real)

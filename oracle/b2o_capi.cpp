@@ -50,6 +50,7 @@ int b2o_create(const B2SParams* p, World** out) {
   w->B = p->num_envs; w->Nmax = p->max_movables;
   w->Ns = 0; w->L = 0; w->NB = 0; w->Hmax = p->max_colliders;
   w->cam_per_env = 0; w->substeps_executed = 0;
+  w->substeps_executed_env.assign(p->num_envs, 0);
   *out = w;
   return 0;
 }
@@ -106,6 +107,8 @@ int b2o_load_scene(World* w, const B2SSceneDesc* d) {
   for (int e = 0; e < B; ++e) w->phase_state[(size_t)e * 8] = -1;
   w->ncol.assign(B, 0); w->col_slot.assign((size_t)B * w->Hmax, 0); w->col_hull.assign((size_t)B * w->Hmax, 0);
   w->reset_count.assign(B, 0);
+  memset(&w->ro, 0, sizeof(w->ro));
+  w->ro_state.assign((size_t)B * 4, 0); w->num_episodes.assign(B, 0);
   w->prev_xy.assign((size_t)B * N * 2, 0.0f);
   w->cam.assign((size_t)B * 21, 0.0f);
   return 0;
@@ -117,8 +120,9 @@ int b2o_reset(World* w, const uint8_t* mask, uint64_t seed) {
 }
 
 static void run_env(World* w, int e, int n, int mode, float lin, float ang, int max_steps) {
-  /* mode 0: raw substeps; 1: env substeps (phase machine); 2: settle */
+  /* mode 0: raw substeps; 1: env substeps (phase machine); 2: settle; 3: rollout substeps */
   if (mode == 0) { for (int i = 0; i < n; ++i) substep(*w, e); return; }
+  if (mode == 3) { for (int i = 0; i < n; ++i) { if (w->phase[e] == B2S_PHASE_IDLE) break; rollout_substep(*w, e); } return; }
   if (mode == 1) { for (int i = 0; i < n; ++i) { if (w->phase[e] == B2S_PHASE_IDLE) break; env_substep(*w, e); } return; }
   int steps = 0, stable = 0;
   while (1) {
@@ -139,13 +143,17 @@ static void run_env(World* w, int e, int n, int mode, float lin, float ang, int 
 
 static void run_all(World* w, int n, int mode, float lin, float ang, int max_steps, const uint8_t* mask = nullptr) {
   const int B = w->B;
-  /* substep() bumps w->substeps_executed; under OpenMP that would race, so save and
-   * recompute it from the per-env step counters, which are private to each env. */
+  /* substep() counts per env (no race between the host threads); the total is summed here */
   int64_t base = w->substeps_executed;
-  std::vector<int32_t> before(w->num_steps);
-  parallel_envs(B, [&](int e) { if (!mask || mask[e]) run_env(w, e, n, mode, lin, ang, max_steps); });
+  std::vector<int64_t> added(B, 0);
+  parallel_envs(B, [&](int e) {
+    if (mask && !mask[e]) return;
+    const int64_t before = w->substeps_executed_env[e];
+    run_env(w, e, n, mode, lin, ang, max_steps);
+    added[e] = w->substeps_executed_env[e] - before;
+  });
   int64_t add = 0;
-  for (int e = 0; e < B; ++e) add += (int64_t)(w->num_steps[e] - before[e]);
+  for (int e = 0; e < B; ++e) add += added[e];
   w->substeps_executed = base + add;
 }
 
@@ -162,10 +170,35 @@ int b2o_begin_episode(World* w, const uint8_t* mask) {
     }
   return 0;
 }
-int b2o_set_action(World* w) { for (int e = 0; e < w->B; ++e) set_action(*w, e); return 0; }
+int b2o_set_action(World* w) { w->ro.enabled = 0; for (int e = 0; e < w->B; ++e) set_action(*w, e); return 0; }
 int b2o_env_substeps(World* w, int n, int* unfinished) {
   run_all(w, n, 1, 0, 0, 0);
   if (unfinished) { int u = 0; for (int e = 0; e < w->B; ++e) u += (w->phase[e] != B2S_PHASE_IDLE); *unfinished = u; }
+  return 0;
+}
+/* b2s_rollout_begin / b2s_rollout_run: scalars, flags / substeps / lengths from *r; the real-typed record arrays are
+ * passed separately because they are double in the double-precision build */
+int b2o_rollout_begin(World* w, const B2SRollout* r, const float* first_action, float* actions, float* rewards, float* positions,
+                      float* returns) {
+  if (!r || r->num_actions < 1 || r->num_episodes < 1 || r->max_attempts < 1 || r->max_attempts > 65535) { g_err = "b2o_rollout_begin: bad rollout"; return B2S_E_INVALID; }
+  World::Rollout& ro = w->ro;
+  ro.enabled = 1; ro.num_actions = r->num_actions; ro.max_attempts = r->max_attempts; ro.num_episodes = r->num_episodes;
+  ro.max_reset_retries = r->max_reset_retries; ro.drop_max_steps = r->drop_max_steps;
+  ro.drop_lin = r->drop_lin_threshold; ro.drop_ang = r->drop_ang_threshold;
+  ro.seed = r->seed; ro.reset_seed = r->reset_seed;
+  ro.actions = actions; ro.rewards = rewards; ro.positions = positions; ro.returns = returns;
+  ro.flags = r->flags; ro.substeps = r->substeps; ro.lengths = r->lengths;
+  for (int e = 0; e < w->B; ++e) rollout_begin(*w, e, first_action);
+  return 0;
+}
+int b2o_rollout_run(World* w, int n, int* unfinished) {
+  run_all(w, n, 3, 0, 0, 0);
+  if (unfinished) { int u = 0; for (int e = 0; e < w->B; ++e) u += (w->phase[e] != B2S_PHASE_IDLE); *unfinished = u; }
+  return 0;
+}
+/* the device policy for one observation (testing): positions are read from the world's body state */
+int b2o_policy_sample(World* w, uint64_t seed, int action_index, const int32_t* num_episodes, int max_attempts, float* out /*[B][4]*/) {
+  for (int e = 0; e < w->B; ++e) policy_sample(*w, e, seed, action_index, num_episodes[e], max_attempts, out + (size_t)e * 4);
   return 0;
 }
 int b2o_arm_move_to_gripper_pose(World* w, const float* pose, const uint8_t* mask) {
@@ -292,6 +325,7 @@ int b2o_array(World* w, int which, void** ptr, int64_t* bytes) {
     case B2S_ARR_CONTACT_FLAGS: RET(w->contact_flags) case B2S_ARR_PHASE_STATE: RET(w->phase_state)
     case B2S_ARR_SOLVER_STATS: RET(w->solver_stats)
     case B2S_ARR_CTRL_TIME: RET(w->ctrl_time) case B2S_ARR_LINK_VEL: RET(w->link_vel)
+    case B2S_ARR_NUM_EPISODES: RET(w->num_episodes) case B2S_ARR_ROLLOUT_STATE: RET(w->ro_state)
     case B2S_ARR_NUM_COLLIDERS: RET(w->ncol) case B2S_ARR_COL_SLOT: RET(w->col_slot) case B2S_ARR_COL_HULL: RET(w->col_hull)
     case 100: RET(w->body_state) case 101: RET(w->joint_state) case 102: RET(w->action)
     case 103: RET(w->obs_position) case 104: RET(w->num_movables) case 105: RET(w->body_mask)

@@ -143,6 +143,8 @@ void observe(World& w, int e) {
   }
 }
 
+void reward_env(World& w, int e, const float* s0, const float* s1);
+
 static void movable_status(World& w, int e, int which) {
   /* PushEnv._get_movable_status: positions + yaw (push_env.py:925-937) */
   for (int i = 0; i < w.Nmax; ++i) {
@@ -273,12 +275,19 @@ void env_substep(World& w, int e) {
     if (w.phase[e] == B2S_PHASE_DONE) { w.phase[e] = B2S_PHASE_SETTLE; ps[2] = 0; ps[3] = 0; }
     return;
   }
-  /* Simulator.wait_until_stable(movables) (simulator.py:325-376) */
+  /* Simulator.wait_until_stable(movables) (simulator.py:325-376): after 'done' (SETTLE), or inside a rollout's reset
+   * (RESET_DROP with the loose thresholds of push_env.py:443-447, then RESET_WAIT) */
+  const bool drop = (ph == B2S_PHASE_RESET_DROP);
+  const float slin = drop ? w.ro.drop_lin : P.stable_lin_threshold, sang = drop ? w.ro.drop_ang : P.stable_ang_threshold;
+  const int smax = drop ? w.ro.drop_max_steps : P.stable_max_steps;
   substep(w, e);
   ps[2] += 1;
   if (ps[2] < P.stable_check_after) return;
-  if (all_stable(w, e, P.stable_lin_threshold, P.stable_ang_threshold)) ps[3] += 1;
-  if (ps[3] >= P.stable_min_steps || ps[2] >= P.stable_max_steps) finish_action(w, e);
+  if (all_stable(w, e, slin, sang)) ps[3] += 1;
+  if (!(ps[3] >= P.stable_min_steps || ps[2] >= smax)) return;
+  if (ph == B2S_PHASE_SETTLE) finish_action(w, e);
+  else if (drop) { w.phase[e] = B2S_PHASE_RESET_WAIT; ps[2] = 0; ps[3] = 0; }
+  else w.phase[e] = B2S_PHASE_IDLE;          /* RESET_WAIT over: rollout_substep decides what follows */
 }
 
 /* ------------------------------------------------------------- reward ---- */
@@ -310,10 +319,16 @@ static float clearing_score(const float* xy, int n) {
 }
 
 void reward(World& w, int e, const float* prev_xy, const float* next_xy) {
-  const B2SSceneDesc& d = w.S.d;
   const int N = w.Nmax;
   const float* s0 = prev_xy + (size_t)e * N * 2;
   const float* s1 = next_xy + (size_t)e * N * 2;
+  reward_env(w, e, s0, s1);
+}
+
+/* s0 / s1: xy of the Nmax bodies of env e before / after the action */
+void reward_env(World& w, int e, const float* s0, const float* s1) {
+  const B2SSceneDesc& d = w.S.d;
+  const int N = w.Nmax;
   float r = 0.0f;
   bool term = false;
   const int task = w.P.task;
@@ -347,6 +362,152 @@ void reward(World& w, int e, const float* prev_xy, const float* next_xy) {
   w.reward[e] = r;
   w.termination[e] = (term || goal_reached) ? 1 : 0;
   w.episode_return[e] += r;
+}
+
+/* ----------------------------------------------- episodes without the host ---- */
+/* HeuristicPushSampler._sample (heuristic_push_sampler.py:66-123) with Philox draws: attempt k uses the counter
+ * (stream 1 | action index << 8, global env id, k | num_episodes << 16), blocks 0 and 1. */
+void policy_sample(World& w, int e, uint64_t seed, int action_index, int num_episodes, int max_attempts, float out[4]) {
+  const B2SParams& P = w.P;
+  int nb = w.num_movables[e]; if (nb < 1) nb = 1;
+  const int target = num_episodes % nb;
+  const float a = (float)(num_episodes * 42);                       /* SEED, heuristic_push_sampler.py:13 */
+  const float base_angle = a - floorf(a / (2.0f * B2S_PI)) * (2.0f * B2S_PI);
+  out[0] = out[1] = out[2] = out[3] = 0.0f;
+  for (int att = 0; att < max_attempts; ++att) {
+    const uint32_t c1 = 1u | ((uint32_t)action_index << 8), c2 = (uint32_t)(P.env_id_offset + e);
+    const uint32_t c3 = (uint32_t)att | ((uint32_t)num_episodes << 16);
+    const b2s_u4 r0 = b2s_philox((uint32_t)seed, (uint32_t)(seed >> 32), 0u, c1, c2, c3);
+    const b2s_u4 r1 = b2s_philox((uint32_t)seed, (uint32_t)(seed >> 32), 1u, c1, c2, c3);
+    const float sx = -1.0f + 2.0f * b2s_u01(r0.x), sy = -1.0f + 2.0f * b2s_u01(r0.y);
+    const float angle = base_angle + (-0.25f * B2S_PI + (0.5f * B2S_PI) * b2s_u01(r0.z));
+    float sn, cs;
+    b2s_sincos(angle, &sn, &cs);
+    const float mx = fminf(1.0f, fmaxf(-1.0f, cs + (-0.3f + 0.6f * b2s_u01(r0.w))));
+    const float my = fminf(1.0f, fmaxf(-1.0f, sn + (-0.3f + 0.6f * b2s_u01(r1.x))));
+    const float offx = 0.5f * (P.cspace_high[0] + P.cspace_low[0]), offy = 0.5f * (P.cspace_high[1] + P.cspace_low[1]);
+    const float rngx = 0.5f * (P.cspace_high[0] - P.cspace_low[0]), rngy = 0.5f * (P.cspace_high[1] - P.cspace_low[1]);
+    const float x0 = sx * rngx + offx, y0 = sy * rngy + offy;
+    const float x1 = fminf(P.cspace_high[0], fmaxf(P.cspace_low[0], x0 + mx * P.translation_x));
+    const float y1 = fminf(P.cspace_high[1], fmaxf(P.cspace_low[1], y0 + my * P.translation_y));
+    bool clear = true;                                               /* start_margin 0.05 */
+    for (int i = 0; i < nb; ++i) {
+      const float dx = bs(w, 0, e, i) - x0, dy = bs(w, 1, e, i) - y0;
+      if (!(sqrtf(dx * dx + dy * dy) > 0.05f)) clear = false;
+    }
+    const float tx = bs(w, 0, e, target), ty = bs(w, 1, e, target);
+    const float d0 = sqrtf((tx - x0) * (tx - x0) + (ty - y0) * (ty - y0));
+    const float d1 = sqrtf((tx - x1) * (tx - x1) + (ty - y1) * (ty - y1));
+    const bool touches = !(d0 >= 0.01f && d1 >= 0.01f);             /* motion_margin 0.01 */
+    out[0] = sx; out[1] = sy; out[2] = mx; out[3] = my;
+    if (clear && touches) return;
+  }
+}
+
+static void episode_start(World& w, int e, const float* first_action) {
+  const int N = w.Nmax, A = w.ro.num_actions, EP = w.ro.num_episodes;
+  const int nm = w.num_movables[e];
+  const int ep = w.ro_state[(size_t)e * 4 + 1];
+  float act[4];
+  if (first_action) for (int k = 0; k < 4; ++k) act[k] = first_action[(size_t)e * 4 + k];
+  else policy_sample(w, e, w.ro.seed, 0, w.num_episodes[e], w.ro.max_attempts, act);
+  w.ro_state[(size_t)e * 4 + 0] = 0;
+  w.episode_return[e] = 0.0f; w.reward[e] = 0.0f; w.termination[e] = 0;
+  observe(w, e);
+  for (int i = 0; i < N; ++i) {
+    w.prev_xy[((size_t)e * N + i) * 2] = (i < nm) ? bs(w, 0, e, i) : 0.0f;
+    w.prev_xy[((size_t)e * N + i) * 2 + 1] = (i < nm) ? bs(w, 1, e, i) : 0.0f;
+  }
+  if (ep < EP) {
+    if (w.ro.lengths) w.ro.lengths[(size_t)e * EP + ep] = 0;
+    if (w.ro.positions)
+      for (int i = 0; i < N; ++i)
+        for (int k = 0; k < 3; ++k)
+          w.ro.positions[((((size_t)e * EP + ep) * (A + 1)) * N + i) * 3 + k] = (i < nm) ? bs(w, k, e, i) : 0.0f;
+  }
+  for (int k = 0; k < 4; ++k) w.action[(size_t)e * 4 + k] = act[k];
+  set_action(w, e);
+}
+
+void rollout_begin(World& w, int e, const float* first_action) {
+  w.ro_state[(size_t)e * 4 + 1] = 0; w.ro_state[(size_t)e * 4 + 2] = 0;
+  episode_start(w, e, first_action);
+}
+
+static void rollout_reset(World& w, int e) {
+  reset_env(w, e, w.ro.reset_seed);
+  w.phase[e] = B2S_PHASE_RESET_DROP;
+  w.phase_state[(size_t)e * 8 + 2] = 0; w.phase_state[(size_t)e * 8 + 3] = 0;
+}
+
+/* RobotEnv.step's bookkeeping after an action (robot_env.py:237-273) + generate_episode(s) (episode_generation.py:41-61, 88-112) */
+static void rollout_advance(World& w, int e) {
+  const int N = w.Nmax, nm = w.num_movables[e];
+  const int A = w.ro.num_actions, EP = w.ro.num_episodes;
+  const int t = w.ro_state[(size_t)e * 4 + 0], ep = w.ro_state[(size_t)e * 4 + 1];
+  float* prev = &w.prev_xy[(size_t)e * N * 2];
+  float s0[128] = {0}, s1[128] = {0};
+  for (int i = 0; i < N; ++i) {
+    s0[i * 2] = prev[i * 2]; s0[i * 2 + 1] = prev[i * 2 + 1];
+    s1[i * 2] = (i < nm) ? bs(w, 0, e, i) : 0.0f; s1[i * 2 + 1] = (i < nm) ? bs(w, 1, e, i) : 0.0f;
+  }
+  reward_env(w, e, s0, s1);
+  const float r = w.reward[e];
+  const bool term = w.termination[e] != 0;
+  for (int i = 0; i < N * 2; ++i) prev[i] = s1[i];
+  observe(w, e);
+  const bool env_done = w.phase_state[(size_t)e * 8 + 4] != 0;
+  if (t < A && ep < EP) {
+    const size_t rec = ((size_t)e * EP + ep) * A + t;
+    if (w.ro.actions) for (int k = 0; k < 4; ++k) w.ro.actions[rec * 4 + k] = w.action[(size_t)e * 4 + k];
+    if (w.ro.rewards) w.ro.rewards[rec] = r;
+    if (w.ro.flags) w.ro.flags[rec] = (uint8_t)((w.is_safe[e] ? 1 : 0) | (w.is_effective[e] ? 2 : 0) | (term ? 4 : 0) | (env_done ? 8 : 0));
+    if (w.ro.substeps) w.ro.substeps[rec] = w.num_steps[e];
+    if (w.ro.positions)
+      for (int i = 0; i < N; ++i)
+        for (int k = 0; k < 3; ++k)
+          w.ro.positions[((((size_t)e * EP + ep) * (A + 1) + t + 1) * N + i) * 3 + k] = (i < nm) ? bs(w, k, e, i) : 0.0f;
+  }
+  const bool over = term || env_done || t + 1 >= A;
+  w.ro_state[(size_t)e * 4 + 0] = t + 1;
+  if (over) {
+    if (ep < EP) {
+      if (w.ro.lengths) w.ro.lengths[(size_t)e * EP + ep] = t + 1;
+      if (w.ro.returns) w.ro.returns[(size_t)e * EP + ep] = w.episode_return[e];
+    }
+    w.num_episodes[e] += 1;
+    w.ro_state[(size_t)e * 4 + 1] = ep + 1;
+    if (ep + 1 < EP) { w.ro_state[(size_t)e * 4 + 2] = 0; rollout_reset(w, e); }
+    return;
+  }
+  float act[4];
+  policy_sample(w, e, w.ro.seed, t + 1, w.num_episodes[e], w.ro.max_attempts, act);
+  for (int k = 0; k < 4; ++k) w.action[(size_t)e * 4 + k] = act[k];
+  set_action(w, e);
+}
+
+static void rollout_reset_done(World& w, int e) {
+  float table_z = 0.0f;
+  for (int s = 0; s < w.Ns; ++s) if (w.S.static_flags[s] & B2S_STATIC_IS_TABLE) table_z = w.S.static_pose[s * 7 + 2];
+  const float zmin = table_z + w.table_dz[e];
+  bool bad = false;
+  for (int i = 0; i < w.num_movables[e]; ++i) if (bs(w, 2, e, i) < zmin) bad = true;
+  if (w.error_flags[e] & 128) bad = true;
+  if (bad) {
+    if (w.ro_state[(size_t)e * 4 + 2] < w.ro.max_reset_retries) { w.ro_state[(size_t)e * 4 + 2] += 1; rollout_reset(w, e); }
+    else { w.error_flags[e] |= 256; w.phase[e] = B2S_PHASE_IDLE; }
+    return;
+  }
+  episode_start(w, e, NULL);
+}
+
+void rollout_substep(World& w, int e) {
+  const int ph = w.phase[e];
+  if (ph == B2S_PHASE_IDLE) return;
+  env_substep(w, e);
+  if (w.phase[e] != B2S_PHASE_IDLE) return;
+  if (ph == B2S_PHASE_SETTLE) rollout_advance(w, e);
+  else if (ph == B2S_PHASE_RESET_WAIT) rollout_reset_done(w, e);
 }
 
 }  // namespace b2o

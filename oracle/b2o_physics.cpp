@@ -731,6 +731,7 @@ void substep(World& w, int e) {
   }
   for (int j = 0; j < 7; ++j) w.joint_state[(0 * 7 + j) * B + e] = q[j] + qd[j] * dt;
   w.num_steps[e] += 1;
+  w.substeps_executed_env[e] += 1;
 }
 
 }  // namespace b2o

@@ -20,9 +20,9 @@ CTRL_FLOATS = 40
 OK, E_INVALID, E_CUDA, E_STATE, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 (PHASE_INITIAL, PHASE_PRE, PHASE_START, PHASE_MOTION, PHASE_POST, PHASE_OFFSTAGE,
- PHASE_DONE, PHASE_SETTLE, PHASE_IDLE) = range(9)
+ PHASE_DONE, PHASE_SETTLE, PHASE_IDLE, PHASE_RESET_DROP, PHASE_RESET_WAIT) = range(11)
 PHASE_NAMES = ['initial', 'pre', 'start', 'motion', 'post', 'offstage', 'done',
-               'settle', 'idle']
+               'settle', 'idle', 'reset_drop', 'reset_wait']
 
 TASK_NONE, TASK_CLEARING, TASK_INSERTION, TASK_CROSSING = range(4)
 TASK_IDS = {None: TASK_NONE, 'data_collection': TASK_NONE, 'clearing': TASK_CLEARING,
@@ -34,7 +34,7 @@ STATIC_ON_TABLE, STATIC_IS_TABLE, STATIC_NO_COLLIDE, STATIC_IS_TILE = 1, 2, 4, 8
  ARR_NUM_PAIRS, ARR_PHASE, ARR_NUM_STEPS, ARR_CTRL, ARR_CTRL_FLAGS, ARR_LINK_POSES,
  ARR_MOV_PARAMS, ARR_TABLE_DZ, ARR_ERROR_FLAGS, ARR_WAYPOINTS, ARR_STATUS, ARR_CONTACT_FLAGS,
  ARR_PHASE_STATE, ARR_SOLVER_STATS, ARR_CTRL_TIME, ARR_LINK_VEL, ARR_NUM_COLLIDERS,
- ARR_COL_SLOT, ARR_COL_HULL, ARR_PROF) = range(25)
+ ARR_COL_SLOT, ARR_COL_HULL, ARR_PROF, ARR_NUM_EPISODES, ARR_ROLLOUT_STATE) = range(27)
 
 f32, i32, u32, u8, f64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint8, C.c_double
 P = C.POINTER
@@ -107,6 +107,16 @@ class B2SBuffers(C.Structure):
     ]
 
 
+class B2SRollout(C.Structure):
+    _fields_ = [
+        ('num_actions', i32), ('max_attempts', i32), ('num_episodes', i32), ('max_reset_retries', i32),
+        ('seed', C.c_uint64), ('reset_seed', C.c_uint64),
+        ('drop_lin_threshold', f32), ('drop_ang_threshold', f32), ('drop_max_steps', i32), ('reserved', i32),
+        ('first_action', C.c_void_p), ('actions', C.c_void_p), ('rewards', C.c_void_p), ('positions', C.c_void_p),
+        ('flags', C.c_void_p), ('substeps', C.c_void_p), ('lengths', C.c_void_p), ('returns', C.c_void_p),
+    ]
+
+
 # every symbol include/b2s.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -127,6 +137,8 @@ SYMBOLS = {
     'b2s_set_action': (C.c_int, [_vp, _vp]),
     'b2s_env_substeps': (C.c_int, [_vp, C.c_int, P(C.c_int), _vp]),
     'b2s_env_step': (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    'b2s_rollout_begin': (C.c_int, [_vp, P(B2SRollout), _vp]),
+    'b2s_rollout_run': (C.c_int, [_vp, C.c_int, C.c_int, P(C.c_int), _vp]),
     'b2s_arm_move_to_gripper_pose': (C.c_int, [_vp, _vp, _vp, _vp]),
     'b2s_arm_move_to_joint_positions': (C.c_int, [_vp, _vp, _vp, _vp]),
     'b2s_arm_reset_targets': (C.c_int, [_vp, _vp, _vp]),
@@ -180,7 +192,7 @@ def load(path=None):
         fn = getattr(lib, name)      # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    for which, struct in enumerate((B2SParams, B2SSceneDesc, B2SBuffers)):
+    for which, struct in enumerate((B2SParams, B2SSceneDesc, B2SBuffers, B2SRollout)):
         if lib.b2s_sizeof(which) != C.sizeof(struct):
             raise RuntimeError('ctypes layout of %s (%d bytes) differs from include/b2s.h (%d)' % (
                 struct.__name__, C.sizeof(struct), lib.b2s_sizeof(which)))

@@ -24,7 +24,8 @@ struct B2SWorld {
   int32_t* exp_keys; int32_t* exp_npts; float* exp_pts;
   size_t arr_bytes[B2S_ARR_COUNT];
   void* arr_ptr[B2S_ARR_COUNT];
-  int* unfinished_pinned;
+  int* unfinished_pinned;          // [4] ring of read-backs
+  cudaEvent_t ring_event[4];
 };
 
 static thread_local std::string g_err;
@@ -92,7 +93,8 @@ extern "C" {
 int b2s_version(void) { return B2S_VERSION; }
 const char* b2s_last_error(void) { return g_err.c_str(); }
 int b2s_sizeof(int which) {
-  return which == 0 ? (int)sizeof(B2SParams) : which == 1 ? (int)sizeof(B2SSceneDesc) : which == 2 ? (int)sizeof(B2SBuffers) : -1;
+  return which == 0 ? (int)sizeof(B2SParams) : which == 1 ? (int)sizeof(B2SSceneDesc) : which == 2 ? (int)sizeof(B2SBuffers) :
+         which == 3 ? (int)sizeof(B2SRollout) : -1;
 }
 
 int b2s_default_params(B2SParams* p) {
@@ -144,7 +146,7 @@ int b2s_destroy(B2SWorld* w) {
   if (!w) return 0;
   DeviceGuard device_guard_(w->device);
   for (void* p : w->allocs) cudaFree(p);
-  if (w->unfinished_pinned) cudaFreeHost(w->unfinished_pinned);
+  if (w->unfinished_pinned) { cudaFreeHost(w->unfinished_pinned); for (int i = 0; i < 4; ++i) cudaEventDestroy(w->ring_event[i]); }
   delete w;
   return 0;
 }
@@ -271,6 +273,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   ALLOC(contact_flags, B, 0); ALLOC(phase_state, B * 8, 0); ALLOC(solver_stats, B * 4, 0);
   ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
   ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
+  ALLOC(ro_state, B * 4, 0); ALLOC(num_episodes, B, 0);
   ALLOC(substeps, 1, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16, 0);
   if ((rc = dalloc(w, &w->exp_keys, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_npts, B * M, 0))) return rc;
@@ -282,7 +285,8 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     CU(cudaMemcpy(d.phase, ph.data(), B * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.phase_state, ps.data(), B * 8 * 4, cudaMemcpyHostToDevice));
   }
-  CU(cudaMallocHost((void**)&w->unfinished_pinned, sizeof(int)));
+  CU(cudaMallocHost((void**)&w->unfinished_pinned, 4 * sizeof(int)));
+  for (int i = 0; i < 4; ++i) CU(cudaEventCreateWithFlags(&w->ring_event[i], cudaEventDisableTiming));
   // shared-memory carve-up (see SmemLayout)
   SmemLayout& sm = d.sm;
   int o = 0;
@@ -356,6 +360,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   reg(B2S_ARR_LINK_VEL, d.link_vel, B * d.L * 24); reg(B2S_ARR_NUM_COLLIDERS, d.ncol, B * 4);
   reg(B2S_ARR_COL_SLOT, d.col_slot, B * d.Hmax * 4); reg(B2S_ARR_COL_HULL, d.col_hull, B * d.Hmax * 4);
   reg(B2S_ARR_PROF, d.prof, (8 + 4 * 1024 + 16) * 8);
+  reg(B2S_ARR_NUM_EPISODES, d.num_episodes, B * 4); reg(B2S_ARR_ROLLOUT_STATE, d.ro_state, B * 4 * 4);
   w->scene_loaded = true;
   return 0;
 }
@@ -411,6 +416,7 @@ int b2s_step_staged(B2SWorld* w, int n, void* stream) {
 
 int b2s_set_action(B2SWorld* w, void* stream) {
   NEED_READY(w);
+  w->d.ro.enabled = 0;                       // lock-step path: the host decides what follows an action
   b2s_launch_set_action(w->d, (cudaStream_t)stream);
   return check_launch(w, "set_action");
 }
@@ -442,6 +448,52 @@ int b2s_env_step(B2SWorld* w, int chunk, int max_substeps, void* stream) {
     if (rc) return rc;
     done += chunk;
   }
+  return 0;
+}
+
+int b2s_rollout_begin(B2SWorld* w, const B2SRollout* r, void* stream) {
+  NEED_READY(w);
+  if (!r) return fail(B2S_E_INVALID, "b2s_rollout_begin: rollout is NULL");
+  if (r->num_actions < 1) return fail(B2S_E_INVALID, "b2s_rollout_begin: num_actions < 1");
+  if (r->max_attempts < 1 || r->max_attempts > 65535) return fail(B2S_E_INVALID, "b2s_rollout_begin: max_attempts must be 1..65535");
+  if (w->d.Nmax > 32) return fail(B2S_E_CAPACITY, "b2s_rollout_begin: max_movables > 32");
+  DRollout& ro = w->d.ro;
+  if (r->num_episodes < 1) return fail(B2S_E_INVALID, "b2s_rollout_begin: num_episodes < 1");
+  if (r->max_reset_retries < 0) return fail(B2S_E_INVALID, "b2s_rollout_begin: max_reset_retries < 0");
+  ro.enabled = 1; ro.num_actions = r->num_actions; ro.max_attempts = r->max_attempts; ro.num_episodes = r->num_episodes;
+  ro.max_reset_retries = r->max_reset_retries; ro.drop_max_steps = r->drop_max_steps;
+  ro.drop_lin = r->drop_lin_threshold; ro.drop_ang = r->drop_ang_threshold;
+  ro.seed = r->seed; ro.reset_seed = r->reset_seed;
+  ro.actions = r->actions; ro.rewards = r->rewards; ro.positions = r->positions; ro.flags = r->flags;
+  ro.substeps = r->substeps; ro.lengths = r->lengths; ro.returns = r->returns;
+  b2s_launch_rollout_begin(w->d, r->first_action, (cudaStream_t)stream);
+  return check_launch(w, "rollout_begin");
+}
+
+int b2s_rollout_run(B2SWorld* w, int chunk, int max_substeps, int* unfinished_host, void* stream) {
+  NEED_READY(w);
+  if (chunk < 1) return fail(B2S_E_INVALID, "b2s_rollout_run: chunk < 1");
+  if (!w->d.ro.enabled) return fail(B2S_E_STATE, "b2s_rollout_run: call b2s_rollout_begin first");
+  cudaStream_t s = (cudaStream_t)stream;
+  int launched = 0, i = 0, last = -1;
+  while (launched < max_substeps) {
+    CU(cudaMemsetAsync(w->d.unfinished, 0, sizeof(int), s));
+    const int n = (max_substeps - launched < chunk) ? (max_substeps - launched) : chunk;
+    b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
+    int rc = check_launch(w, "rollout_run", 2);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(w->unfinished_pinned + (i & 3), w->d.unfinished, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(w->ring_event[i & 3], s));
+    launched += n;
+    ++i;
+    if (i >= 3) {                            // look at the launch before the previous one: two launches stay queued
+      CU(cudaEventSynchronize(w->ring_event[(i - 3) & 3]));
+      if (w->unfinished_pinned[(i - 3) & 3] == 0) break;
+    }
+  }
+  CU(cudaStreamSynchronize(s));
+  last = w->unfinished_pinned[(i - 1) & 3];
+  if (unfinished_host) *unfinished_host = last;
   return 0;
 }
 

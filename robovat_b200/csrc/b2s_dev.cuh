@@ -91,6 +91,14 @@ struct DLayout {
   int num_movable_assets, num_target_assets;
 };
 
+// device-side episode driver (b2s_rollout_*, b2s_rollout.cuh)
+struct DRollout {
+  int enabled, num_actions, max_attempts, num_episodes, max_reset_retries, drop_max_steps;
+  float drop_lin, drop_ang;
+  unsigned long long seed, reset_seed;
+  float* actions; float* rewards; float* positions; uint8_t* flags; int32_t* substeps; int32_t* lengths; float* returns;
+};
+
 // Shared memory of a block = E per-environment regions, one scratch region per warp, E meta records.
 // A warp may pick up any environment of its block in any stage, so everything that has to survive from
 // one stage to the next (body table, colliders, pair list, contact list) is per environment; GJK, manifold
@@ -169,6 +177,9 @@ struct DWorld {
   unsigned long long* prof;       // [8] stage timing counters (only written by -DB2S_PROF builds)
   float* pair_stage;              // [blocks][E][max_pairs][68] narrow-phase result of every candidate pair of the substep
   float* row_scratch;             // [blocks][warps][32][68] solver rows of the environment a warp is solving (L1/L2 resident)
+  int32_t* ro_state;              // [B][4] rollout: step of the episode, episode index, re-samples of the current reset, spare
+  int32_t* num_episodes;          // [B] episodes finished by the device-side driver
+  DRollout ro;
   SmemLayout sm;
   int max_ray_planes;    // raster: upper bound of hull face planes / hulls in one environment
   int max_ray_cols;
@@ -196,6 +207,7 @@ static inline void b2s_opt_in_smem(K kernel, size_t smem, size_t* configured /* 
 // host launchers (defined next to their kernels)
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s);
 void b2s_launch_begin_episode(const DWorld& W, const uint8_t* mask, cudaStream_t s);
+void b2s_launch_rollout_begin(const DWorld& W, const float* first_action, cudaStream_t s);
 void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s);
 void b2s_launch_staged(const DWorld& W, int n, cudaStream_t s, int64_t* launches);
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s);

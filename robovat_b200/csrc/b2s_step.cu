@@ -24,6 +24,7 @@
 #include <mutex>
 
 #include "b2s_dev.cuh"
+#include "b2s_rollout.cuh"
 
 #define LD3(p) v3((p)[0], (p)[1], (p)[2])
 #define ST3(p, v) { (p)[0] = (v).x; (p)[1] = (v).y; (p)[2] = (v).z; }
@@ -1890,6 +1891,10 @@ __device__ __noinline__ void finish_action(int e, int lane) {
   __syncwarp();
 }
 
+// between two actions of a device-side episode (b2s_rollout.cuh); out of line: it runs once per ~2000 substeps
+__device__ __noinline__ void rollout_next(int e, int lane) { rollout_advance(g_W, e, lane); }
+__device__ __noinline__ void rollout_after_reset(int e, int lane) { rollout_reset_done(g_W, e, lane); }
+
 // ----------------------------------------------------------- the kernel -----
 
 // Hand-out of environments inside a stage: dynamic (shared counter) when the solver rows live in registers;
@@ -2079,16 +2084,30 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
           }
           }
         } else {
+          // wait_until_stable: after 'done' (SETTLE), or of a rollout's reset (RESET_DROP with the loose thresholds, then RESET_WAIT)
+          const bool drop = (ph == B2S_PHASE_RESET_DROP);
+          const float slin = drop ? W.ro.drop_lin : P.stable_lin_threshold, sang = drop ? W.ro.drop_ang : P.stable_ang_threshold;
+          const int smax = drop ? W.ro.drop_max_steps : P.stable_max_steps;
           int s2 = ps[2] + 1, s3 = ps[3];
           __syncwarp();
           bool fin = false;
           if (s2 >= P.stable_check_after) {
-            if (all_stable(e, lane, P.stable_lin_threshold, P.stable_ang_threshold)) s3 += 1;
-            if (s3 >= P.stable_min_steps || s2 >= P.stable_max_steps) fin = true;
+            if (all_stable(e, lane, slin, sang)) s3 += 1;
+            if (s3 >= P.stable_min_steps || s2 >= smax) fin = true;
           }
           if (lane == 0) { ps[2] = s2; ps[3] = s3; }
           __syncwarp();
-          if (fin) finish_action(e, lane);
+          if (fin) {
+            if (ph == B2S_PHASE_SETTLE) {
+              finish_action(e, lane);
+              if (W.ro.enabled) rollout_next(e, lane);     // reward, record, next action or next episode: the env goes on in this launch
+            } else if (drop) {
+              if (lane == 0) { W.phase[e] = B2S_PHASE_RESET_WAIT; ps[2] = 0; ps[3] = 0; }
+              __syncwarp();
+            } else {
+              rollout_after_reset(e, lane);
+            }
+          }
         }
         nxt = nxt && (W.phase[e] != B2S_PHASE_IDLE);
       } else if (mode == MODE_SETTLE) {   // Simulator.wait_until_stable for this env

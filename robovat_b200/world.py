@@ -33,7 +33,29 @@ _ARR_TYPES = {
     _capi.ARR_CONTACT_FLAGS: '<i4', _capi.ARR_PHASE_STATE: '<i4', _capi.ARR_SOLVER_STATS: '<i4',
     _capi.ARR_CTRL_TIME: '<f8', _capi.ARR_LINK_VEL: '<f4', _capi.ARR_NUM_COLLIDERS: '<i4',
     _capi.ARR_COL_SLOT: '<i4', _capi.ARR_COL_HULL: '<i4', _capi.ARR_PROF: '<i8',
+    _capi.ARR_NUM_EPISODES: '<i4', _capi.ARR_ROLLOUT_STATE: '<i4',
 }
+
+
+class RolloutRecord(object):
+    """Device-resident records of a rollout (layouts of B2SRollout, include/b2s.h)."""
+
+    def __init__(self, B, N, num_episodes, num_actions, device, positions=True):
+        EP, A = int(num_episodes), int(num_actions)
+        f32 = torch.float32
+        self.actions = torch.zeros(B, EP, A, 4, dtype=f32, device=device)
+        self.rewards = torch.zeros(B, EP, A, dtype=f32, device=device)
+        self.positions = torch.zeros(B, EP, A + 1, N, 3, dtype=f32, device=device) if positions else None
+        self.flags = torch.zeros(B, EP, A, dtype=torch.uint8, device=device)
+        self.substeps = torch.zeros(B, EP, A, dtype=torch.int32, device=device)
+        self.lengths = torch.zeros(B, EP, dtype=torch.int32, device=device)
+        self.returns = torch.zeros(B, EP, dtype=f32, device=device)
+
+    def tensors(self):
+        return {k: v for k, v in vars(self).items() if v is not None}
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.tensors().values())
 
 
 class World(object):
@@ -147,6 +169,34 @@ class World(object):
 
     def env_step(self, chunk=200, max_substeps=40000):
         self._chk(self.lib.b2s_env_step(self.h, int(chunk), int(max_substeps), self._stream()))
+
+    # -- episodes on the device -----------------------------------------------------------------
+    def rollout_begin(self, num_actions, num_episodes=1, policy_seed=0, reset_seed=0, max_attempts=20000,
+                      first_action=None, record=None, max_reset_retries=8, drop_thresholds=(0.1, 0.1, 500)):
+        """Start episode 0 of a device-side rollout in every env (from its reset, settled state).  `record` is a
+        RolloutRecord (or None: nothing is recorded).  Returns the record."""
+        r = _capi.B2SRollout()
+        r.num_actions, r.num_episodes, r.max_attempts = int(num_actions), int(num_episodes), int(min(max_attempts, 65535))
+        r.max_reset_retries = int(max_reset_retries)
+        r.seed, r.reset_seed = int(policy_seed), int(reset_seed)
+        r.drop_lin_threshold, r.drop_ang_threshold, r.drop_max_steps = float(drop_thresholds[0]), float(drop_thresholds[1]), int(drop_thresholds[2])
+        fa = None
+        if first_action is not None:
+            fa = torch.as_tensor(first_action, dtype=torch.float32, device=self.device).reshape(self.B, 4).contiguous()
+            r.first_action = fa.data_ptr()
+        if record is not None:
+            for name, t in record.tensors().items():
+                setattr(r, name, t.data_ptr())
+        self._rollout_keepalive = (record, fa)
+        self._chk(self.lib.b2s_rollout_begin(self.h, C.byref(r), self._stream()))
+        return record
+
+    def rollout_run(self, chunk=250, max_substeps=1 << 30):
+        """Advance the rollout until every env finished its last episode or `max_substeps` per env were launched.
+        Returns the number of envs that are still running."""
+        u = C.c_int(-1)
+        self._chk(self.lib.b2s_rollout_run(self.h, int(chunk), int(max_substeps), C.byref(u), self._stream()))
+        return u.value
 
     # -- robot ------------------------------------------------------------------------------
     def move_to_gripper_pose(self, pose, mask=None):
