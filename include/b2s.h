@@ -303,6 +303,7 @@ int b2s_env_step(B2SWorld* world, int chunk, int max_substeps, void* stream);
  * table) and starts the next episode.  Nobody waits for the slowest env of the batch -- this is what
  * tools/parallel_run.py's independent worker processes amount to.  All pointers are device pointers owned by the
  * caller; output pointers may be NULL.  Records of episode ep of env e start at index (e * num_episodes + ep). */
+enum { B2S_POLICY_HEURISTIC = 0, B2S_POLICY_AIMED = 1 };
 typedef struct B2SRollout {
   int32_t num_actions;         /* A: steps per episode at most (config MAX_STEPS) */
   int32_t max_attempts;        /* HEURISTICS.MAX_ATTEMPS of the rejection sampler (1..65535) */
@@ -312,7 +313,8 @@ typedef struct B2SRollout {
   uint64_t reset_seed;         /* scene seed of the resets between episodes (as b2s_reset's seed) */
   float drop_lin_threshold, drop_ang_threshold;   /* 0.1, 0.1  push_env.py:443-447 */
   int32_t drop_max_steps;      /* 500 */
-  int32_t reserved;
+  int32_t policy_kind;         /* B2S_POLICY_HEURISTIC (HeuristicPushSampler), B2S_POLICY_AIMED (synthetic workloads: start
+                                  8 cm behind a random body in a random direction and push through it; always a contact) */
   const float* first_action;   /* [B][4] action of step 0 of episode 0, or NULL: drawn by the device policy like the others */
   float* actions;              /* out [B][EP][A][4] */
   float* rewards;              /* out [B][EP][A] */
@@ -329,6 +331,19 @@ int b2s_rollout_begin(B2SWorld* world, const B2SRollout* rollout, void* stream);
  * behind, so the queue never drains).  *unfinished_host (may be NULL) receives the final count after synchronising the
  * stream.  May be called repeatedly: a rollout keeps its state between calls. */
 int b2s_rollout_run(B2SWorld* world, int chunk, int max_substeps, int* unfinished_host, void* stream);
+
+/* Asynchronous stepping with the policy on the host (the other way to never wait for the slowest env: what
+ * tools/parallel_run.py's workers do, each at its own pace, with `policy.action(obs)` / `env.step(action)` /
+ * `env.reset()` of episode_generation.py:41-61 issued per env).  command_dev uint8 [B] (NULL = all 0), looked at only
+ * for envs that are ready (idle): 1 = start the action in buffers.action[e] (PushEnv._execute_action), 2 = re-sample
+ * the env's scene with reset_seed, let it drop and settle on the device (push_env.py:331-471; invalid scenes are
+ * re-sampled up to 8 times).  Then every busy env advances by up to n_substeps.  An env whose action finishes computes
+ * its reward (buffers.reward / termination / episode_return / is_safe / is_effective, PoseObs row) and waits; an env
+ * whose reset finishes publishes its first observation and waits.  status_dev uint8 [B] (may be NULL): bit0 ready
+ * for a command, bit1 an action finished during this call, bit2 a reset finished during this call, bit3 the env ended
+ * its last action unsafe at 'done' (RobotEnv._done, push_env.py:719-721). */
+int b2s_env_async_step(B2SWorld* world, const uint8_t* command_dev, int n_substeps, uint64_t reset_seed, uint8_t* status_dev,
+                       void* stream);
 
 /* robot commands outside the phase machine (sawyer_sim.py:186-308); poses/q are device pointers */
 int b2s_arm_move_to_gripper_pose(B2SWorld* world, const float* pose_dev /*[B][7]*/, const uint8_t* env_mask_dev, void* stream);

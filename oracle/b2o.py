@@ -131,20 +131,25 @@ class OracleWorld(object):
 
     # -- episodes without the host (b2s_rollout_*) ----------------------------------------------
     def rollout_begin(self, num_actions, num_episodes=1, policy_seed=0, reset_seed=0, max_attempts=20000,
-                      first_action=None, positions=True, max_reset_retries=8, drop_thresholds=(0.1, 0.1, 500)):
+                      first_action=None, positions=True, record=True, max_reset_retries=8, drop_thresholds=(0.1, 0.1, 500), policy_kind=0):
         """Returns the record: dict of numpy arrays with the layouts of B2SRollout."""
         B, N, EP, A = self.B, self.N, int(num_episodes), int(num_actions)
-        rec = {'actions': np.zeros((B, EP, A, 4), self.real), 'rewards': np.zeros((B, EP, A), self.real),
-               'positions': np.zeros((B, EP, A + 1, N, 3), self.real) if positions else None,
-               'flags': np.zeros((B, EP, A), np.uint8), 'substeps': np.zeros((B, EP, A), np.int32),
-               'lengths': np.zeros((B, EP), np.int32), 'returns': np.zeros((B, EP), self.real)}
+        if record:
+            rec = {'actions': np.zeros((B, EP, A, 4), self.real), 'rewards': np.zeros((B, EP, A), self.real),
+                   'positions': np.zeros((B, EP, A + 1, N, 3), self.real) if positions else None,
+                   'flags': np.zeros((B, EP, A), np.uint8), 'substeps': np.zeros((B, EP, A), np.int32),
+                   'lengths': np.zeros((B, EP), np.int32), 'returns': np.zeros((B, EP), self.real)}
+        else:                                   # nothing is recorded (throughput runs over many episodes)
+            rec = dict.fromkeys(('actions', 'rewards', 'positions', 'flags', 'substeps', 'lengths', 'returns'))
         r = _capi.B2SRollout()
         r.num_actions, r.num_episodes, r.max_attempts = A, EP, int(min(max_attempts, 65535))
         r.max_reset_retries = int(max_reset_retries)
+        r.policy_kind = int(policy_kind)
         r.seed, r.reset_seed = int(policy_seed), int(reset_seed)
         r.drop_lin_threshold, r.drop_ang_threshold, r.drop_max_steps = float(drop_thresholds[0]), float(drop_thresholds[1]), int(drop_thresholds[2])
         for k in ('flags', 'substeps', 'lengths'):
-            setattr(r, k, rec[k].ctypes.data)
+            if rec[k] is not None:
+                setattr(r, k, rec[k].ctypes.data)
         fa = None if first_action is None else np.ascontiguousarray(first_action, self.real).reshape(B, 4)
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         self._rollout_keepalive = (rec, fa)
@@ -156,6 +161,13 @@ class OracleWorld(object):
         u = C.c_int()
         self._chk(self.lib.b2o_rollout_run(self.h, int(n), C.byref(u)))
         return u.value
+
+    def env_async_step(self, command, n, reset_seed=0):
+        cmd = None if command is None else np.ascontiguousarray(command, np.uint8)
+        status = np.zeros(self.B, np.uint8)
+        self._chk(self.lib.b2o_env_async_step(self.h, None if cmd is None else cmd.ctypes.data_as(C.c_void_p), int(n),
+                                              C.c_uint64(int(reset_seed)), status.ctypes.data_as(C.c_void_p)))
+        return status
 
     def policy_sample(self, seed, action_index, num_episodes, max_attempts=20000):
         out = np.zeros((self.B, 4), self.real)

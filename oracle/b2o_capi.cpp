@@ -108,7 +108,7 @@ int b2o_load_scene(World* w, const B2SSceneDesc* d) {
   w->ncol.assign(B, 0); w->col_slot.assign((size_t)B * w->Hmax, 0); w->col_hull.assign((size_t)B * w->Hmax, 0);
   w->reset_count.assign(B, 0);
   memset(&w->ro, 0, sizeof(w->ro));
-  w->ro_state.assign((size_t)B * 4, 0); w->num_episodes.assign(B, 0);
+  w->ro_state.assign((size_t)B * 4, 0); w->num_episodes.assign(B, 0); w->async_events.assign(B, 0);
   w->prev_xy.assign((size_t)B * N * 2, 0.0f);
   w->cam.assign((size_t)B * 21, 0.0f);
   return 0;
@@ -120,9 +120,10 @@ int b2o_reset(World* w, const uint8_t* mask, uint64_t seed) {
 }
 
 static void run_env(World* w, int e, int n, int mode, float lin, float ang, int max_steps) {
-  /* mode 0: raw substeps; 1: env substeps (phase machine); 2: settle; 3: rollout substeps */
+  /* mode 0: raw substeps; 1: env substeps (phase machine); 2: settle; 3: rollout substeps; 4: async substeps */
   if (mode == 0) { for (int i = 0; i < n; ++i) substep(*w, e); return; }
   if (mode == 3) { for (int i = 0; i < n; ++i) { if (w->phase[e] == B2S_PHASE_IDLE) break; rollout_substep(*w, e); } return; }
+  if (mode == 4) { for (int i = 0; i < n; ++i) { if (w->phase[e] == B2S_PHASE_IDLE) break; async_substep(*w, e); } return; }
   if (mode == 1) { for (int i = 0; i < n; ++i) { if (w->phase[e] == B2S_PHASE_IDLE) break; env_substep(*w, e); } return; }
   int steps = 0, stable = 0;
   while (1) {
@@ -183,7 +184,7 @@ int b2o_rollout_begin(World* w, const B2SRollout* r, const float* first_action, 
   if (!r || r->num_actions < 1 || r->num_episodes < 1 || r->max_attempts < 1 || r->max_attempts > 65535) { g_err = "b2o_rollout_begin: bad rollout"; return B2S_E_INVALID; }
   World::Rollout& ro = w->ro;
   ro.enabled = 1; ro.num_actions = r->num_actions; ro.max_attempts = r->max_attempts; ro.num_episodes = r->num_episodes;
-  ro.max_reset_retries = r->max_reset_retries; ro.drop_max_steps = r->drop_max_steps;
+  ro.max_reset_retries = r->max_reset_retries; ro.drop_max_steps = r->drop_max_steps; ro.policy_kind = r->policy_kind;
   ro.drop_lin = r->drop_lin_threshold; ro.drop_ang = r->drop_ang_threshold;
   ro.seed = r->seed; ro.reset_seed = r->reset_seed;
   ro.actions = actions; ro.rewards = rewards; ro.positions = positions; ro.returns = returns;
@@ -194,6 +195,17 @@ int b2o_rollout_begin(World* w, const B2SRollout* r, const float* first_action, 
 int b2o_rollout_run(World* w, int n, int* unfinished) {
   run_all(w, n, 3, 0, 0, 0);
   if (unfinished) { int u = 0; for (int e = 0; e < w->B; ++e) u += (w->phase[e] != B2S_PHASE_IDLE); *unfinished = u; }
+  return 0;
+}
+int b2o_env_async_step(World* w, const uint8_t* command, int n, uint64_t reset_seed, uint8_t* status) {
+  World::Rollout& ro = w->ro;
+  if (ro.enabled != 2) { memset(&ro, 0, sizeof(ro)); ro.enabled = 2; ro.max_reset_retries = 8; ro.drop_lin = 0.1f; ro.drop_ang = 0.1f; ro.drop_max_steps = 500; }
+  ro.reset_seed = reset_seed;
+  for (int e = 0; e < w->B; ++e) async_command(*w, e, command ? command[e] : 0);
+  if (n > 0) run_all(w, n, 4, 0, 0, 0);
+  if (status)
+    for (int e = 0; e < w->B; ++e)
+      status[e] = (uint8_t)((w->phase[e] == B2S_PHASE_IDLE ? 1 : 0) | (w->async_events[e] & 6) | (w->phase_state[(size_t)e * 8 + 4] ? 8 : 0));
   return 0;
 }
 /* the device policy for one observation (testing): positions are read from the world's body state */

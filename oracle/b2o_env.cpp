@@ -404,13 +404,35 @@ void policy_sample(World& w, int e, uint64_t seed, int action_index, int num_epi
   }
 }
 
+/* B2S_POLICY_AIMED: a random body, a random direction, start 8 cm behind it, push through (synthetic workloads) */
+void policy_aimed(World& w, int e, uint64_t seed, int action_index, int num_episodes, float out[4]) {
+  const B2SParams& P = w.P;
+  int nb = w.num_movables[e]; if (nb < 1) nb = 1;
+  const b2s_u4 r = b2s_philox((uint32_t)seed, (uint32_t)(seed >> 32), 0u, 2u | ((uint32_t)action_index << 8), (uint32_t)(P.env_id_offset + e), (uint32_t)num_episodes);
+  int body = (int)(b2s_u01(r.x) * (float)nb); if (body > nb - 1) body = nb - 1;
+  const float angle = -B2S_PI + (2.0f * B2S_PI) * b2s_u01(r.y);
+  float sn, cs;
+  b2s_sincos(angle, &sn, &cs);
+  const float offx = 0.5f * (P.cspace_high[0] + P.cspace_low[0]), offy = 0.5f * (P.cspace_high[1] + P.cspace_low[1]);
+  const float rngx = 0.5f * (P.cspace_high[0] - P.cspace_low[0]), rngy = 0.5f * (P.cspace_high[1] - P.cspace_low[1]);
+  const float tx = bs(w, 0, e, body) - 0.08f * cs, ty = bs(w, 1, e, body) - 0.08f * sn;
+  out[0] = fminf(1.0f, fmaxf(-1.0f, (tx - offx) / rngx));
+  out[1] = fminf(1.0f, fmaxf(-1.0f, (ty - offy) / rngy));
+  out[2] = cs; out[3] = sn;
+}
+
+static void rollout_policy(World& w, int e, int action_index, float out[4]) {
+  if (w.ro.policy_kind == B2S_POLICY_AIMED) policy_aimed(w, e, w.ro.seed, action_index, w.num_episodes[e], out);
+  else policy_sample(w, e, w.ro.seed, action_index, w.num_episodes[e], w.ro.max_attempts, out);
+}
+
 static void episode_start(World& w, int e, const float* first_action) {
   const int N = w.Nmax, A = w.ro.num_actions, EP = w.ro.num_episodes;
   const int nm = w.num_movables[e];
   const int ep = w.ro_state[(size_t)e * 4 + 1];
   float act[4];
   if (first_action) for (int k = 0; k < 4; ++k) act[k] = first_action[(size_t)e * 4 + k];
-  else policy_sample(w, e, w.ro.seed, 0, w.num_episodes[e], w.ro.max_attempts, act);
+  else rollout_policy(w, e, 0, act);
   w.ro_state[(size_t)e * 4 + 0] = 0;
   w.episode_return[e] = 0.0f; w.reward[e] = 0.0f; w.termination[e] = 0;
   observe(w, e);
@@ -481,12 +503,13 @@ static void rollout_advance(World& w, int e) {
     return;
   }
   float act[4];
-  policy_sample(w, e, w.ro.seed, t + 1, w.num_episodes[e], w.ro.max_attempts, act);
+  rollout_policy(w, e, t + 1, act);
   for (int k = 0; k < 4; ++k) w.action[(size_t)e * 4 + k] = act[k];
   set_action(w, e);
 }
 
-static void rollout_reset_done(World& w, int e) {
+/* 0: scene valid (env IDLE, the caller starts the episode), 1: re-sampled, 2: gave up */
+static int rollout_reset_check(World& w, int e) {
   float table_z = 0.0f;
   for (int s = 0; s < w.Ns; ++s) if (w.S.static_flags[s] & B2S_STATIC_IS_TABLE) table_z = w.S.static_pose[s * 7 + 2];
   const float zmin = table_z + w.table_dz[e];
@@ -494,11 +517,12 @@ static void rollout_reset_done(World& w, int e) {
   for (int i = 0; i < w.num_movables[e]; ++i) if (bs(w, 2, e, i) < zmin) bad = true;
   if (w.error_flags[e] & 128) bad = true;
   if (bad) {
-    if (w.ro_state[(size_t)e * 4 + 2] < w.ro.max_reset_retries) { w.ro_state[(size_t)e * 4 + 2] += 1; rollout_reset(w, e); }
-    else { w.error_flags[e] |= 256; w.phase[e] = B2S_PHASE_IDLE; }
-    return;
+    if (w.ro_state[(size_t)e * 4 + 2] < w.ro.max_reset_retries) { w.ro_state[(size_t)e * 4 + 2] += 1; rollout_reset(w, e); return 1; }
+    w.error_flags[e] |= 256; w.phase[e] = B2S_PHASE_IDLE;
+    return 2;
   }
-  episode_start(w, e, NULL);
+  w.phase[e] = B2S_PHASE_IDLE;
+  return 0;
 }
 
 void rollout_substep(World& w, int e) {
@@ -507,7 +531,44 @@ void rollout_substep(World& w, int e) {
   env_substep(w, e);
   if (w.phase[e] != B2S_PHASE_IDLE) return;
   if (ph == B2S_PHASE_SETTLE) rollout_advance(w, e);
-  else if (ph == B2S_PHASE_RESET_WAIT) rollout_reset_done(w, e);
+  else if (ph == B2S_PHASE_RESET_WAIT) { if (rollout_reset_check(w, e) == 0) episode_start(w, e, NULL); }
+}
+
+/* ---- asynchronous stepping with the policy on the host (b2s_env_async_step) ---- */
+void async_command(World& w, int e, int cmd) {
+  w.async_events[e] = 0;
+  if (w.phase[e] != B2S_PHASE_IDLE) return;
+  if (cmd == 1) set_action(w, e);
+  else if (cmd == 2) { w.ro_state[(size_t)e * 4 + 2] = 0; rollout_reset(w, e); }
+}
+
+void async_substep(World& w, int e) {
+  const int ph = w.phase[e];
+  if (ph == B2S_PHASE_IDLE) return;
+  env_substep(w, e);
+  if (w.phase[e] != B2S_PHASE_IDLE) return;
+  const int N = w.Nmax, nm = w.num_movables[e];
+  if (ph == B2S_PHASE_SETTLE) {
+    float* prev = &w.prev_xy[(size_t)e * N * 2];
+    float s0[128] = {0}, s1[128] = {0};
+    for (int i = 0; i < N; ++i) {
+      s0[i * 2] = prev[i * 2]; s0[i * 2 + 1] = prev[i * 2 + 1];
+      s1[i * 2] = (i < nm) ? bs(w, 0, e, i) : 0.0f; s1[i * 2 + 1] = (i < nm) ? bs(w, 1, e, i) : 0.0f;
+    }
+    reward_env(w, e, s0, s1);
+    for (int i = 0; i < N * 2; ++i) prev[i] = s1[i];
+    observe(w, e);
+    w.async_events[e] |= 2;
+  } else if (ph == B2S_PHASE_RESET_WAIT) {
+    if (rollout_reset_check(w, e) != 0) return;
+    for (int i = 0; i < N; ++i) {
+      w.prev_xy[((size_t)e * N + i) * 2] = (i < nm) ? bs(w, 0, e, i) : 0.0f;
+      w.prev_xy[((size_t)e * N + i) * 2 + 1] = (i < nm) ? bs(w, 1, e, i) : 0.0f;
+    }
+    w.episode_return[e] = 0.0f; w.reward[e] = 0.0f; w.termination[e] = 0;
+    observe(w, e);
+    w.async_events[e] |= 4;
+  }
 }
 
 }  // namespace b2o

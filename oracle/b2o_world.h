@@ -123,12 +123,12 @@ struct World {
   /* device-side episode driver (b2s_rollout_*): settings, per-env state [B][4] (step, episode, re-samples, spare),
    * RobotEnv.num_episodes [B]; record pointers are caller-owned host arrays */
   struct Rollout {
-    int enabled, num_actions, max_attempts, num_episodes, max_reset_retries, drop_max_steps;
+    int enabled, num_actions, max_attempts, num_episodes, max_reset_retries, drop_max_steps, policy_kind;
     float drop_lin, drop_ang;
     uint64_t seed, reset_seed;
     float* actions; float* rewards; float* positions; uint8_t* flags; int32_t* substeps; int32_t* lengths; float* returns;
   } ro;
-  std::vector<int32_t> ro_state, num_episodes;
+  std::vector<int32_t> ro_state, num_episodes, async_events;
   std::vector<float> prev_xy;      /* [B][Nmax][2] */
   std::vector<float> cam;          /* [B][21] K9 R9 t3 */
   int cam_per_env;
@@ -163,8 +163,11 @@ void env_substep(World& w, int e);         /* one substep + phase logic for an i
 void observe(World& w, int e);
 void reward(World& w, int e, const float* prev_xy, const float* next_xy);
 void policy_sample(World& w, int e, uint64_t seed, int action_index, int num_episodes, int max_attempts, float out[4]);
+void policy_aimed(World& w, int e, uint64_t seed, int action_index, int num_episodes, float out[4]);
 void rollout_begin(World& w, int e, const float* first_action);
 void rollout_substep(World& w, int e);     /* env_substep + what follows an action / an episode / a reset */
+void async_command(World& w, int e, int cmd);
+void async_substep(World& w, int e);
 void render(World& w, int e);
 void point_cloud(World& w, int e, uint64_t seed);
 

@@ -273,7 +273,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   ALLOC(contact_flags, B, 0); ALLOC(phase_state, B * 8, 0); ALLOC(solver_stats, B * 4, 0);
   ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
   ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
-  ALLOC(ro_state, B * 4, 0); ALLOC(num_episodes, B, 0);
+  ALLOC(ro_state, B * 4, 0); ALLOC(num_episodes, B, 0); ALLOC(async_events, B, 0);
   ALLOC(substeps, 1, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16, 0);
   if ((rc = dalloc(w, &w->exp_keys, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_npts, B * M, 0))) return rc;
@@ -416,7 +416,7 @@ int b2s_step_staged(B2SWorld* w, int n, void* stream) {
 
 int b2s_set_action(B2SWorld* w, void* stream) {
   NEED_READY(w);
-  w->d.ro.enabled = 0;                       // lock-step path: the host decides what follows an action
+  w->d.ro.enabled = RO_OFF;                  // lock-step path: the host decides what follows an action
   b2s_launch_set_action(w->d, (cudaStream_t)stream);
   return check_launch(w, "set_action");
 }
@@ -458,10 +458,11 @@ int b2s_rollout_begin(B2SWorld* w, const B2SRollout* r, void* stream) {
   if (r->max_attempts < 1 || r->max_attempts > 65535) return fail(B2S_E_INVALID, "b2s_rollout_begin: max_attempts must be 1..65535");
   if (w->d.Nmax > 32) return fail(B2S_E_CAPACITY, "b2s_rollout_begin: max_movables > 32");
   DRollout& ro = w->d.ro;
+  if (r->policy_kind != B2S_POLICY_HEURISTIC && r->policy_kind != B2S_POLICY_AIMED) return fail(B2S_E_INVALID, "b2s_rollout_begin: unknown policy_kind");
   if (r->num_episodes < 1) return fail(B2S_E_INVALID, "b2s_rollout_begin: num_episodes < 1");
   if (r->max_reset_retries < 0) return fail(B2S_E_INVALID, "b2s_rollout_begin: max_reset_retries < 0");
-  ro.enabled = 1; ro.num_actions = r->num_actions; ro.max_attempts = r->max_attempts; ro.num_episodes = r->num_episodes;
-  ro.max_reset_retries = r->max_reset_retries; ro.drop_max_steps = r->drop_max_steps;
+  ro.enabled = RO_EPISODES; ro.num_actions = r->num_actions; ro.max_attempts = r->max_attempts; ro.num_episodes = r->num_episodes;
+  ro.max_reset_retries = r->max_reset_retries; ro.drop_max_steps = r->drop_max_steps; ro.policy_kind = r->policy_kind; ro.pad = 0;
   ro.drop_lin = r->drop_lin_threshold; ro.drop_ang = r->drop_ang_threshold;
   ro.seed = r->seed; ro.reset_seed = r->reset_seed;
   ro.actions = r->actions; ro.rewards = r->rewards; ro.positions = r->positions; ro.flags = r->flags;
@@ -473,7 +474,7 @@ int b2s_rollout_begin(B2SWorld* w, const B2SRollout* r, void* stream) {
 int b2s_rollout_run(B2SWorld* w, int chunk, int max_substeps, int* unfinished_host, void* stream) {
   NEED_READY(w);
   if (chunk < 1) return fail(B2S_E_INVALID, "b2s_rollout_run: chunk < 1");
-  if (!w->d.ro.enabled) return fail(B2S_E_STATE, "b2s_rollout_run: call b2s_rollout_begin first");
+  if (w->d.ro.enabled != RO_EPISODES) return fail(B2S_E_STATE, "b2s_rollout_run: call b2s_rollout_begin first");
   cudaStream_t s = (cudaStream_t)stream;
   int launched = 0, i = 0, last = -1;
   while (launched < max_substeps) {
@@ -494,6 +495,31 @@ int b2s_rollout_run(B2SWorld* w, int chunk, int max_substeps, int* unfinished_ho
   CU(cudaStreamSynchronize(s));
   last = w->unfinished_pinned[(i - 1) & 3];
   if (unfinished_host) *unfinished_host = last;
+  return 0;
+}
+
+int b2s_env_async_step(B2SWorld* w, const uint8_t* command, int n, uint64_t reset_seed, uint8_t* status, void* stream) {
+  NEED_READY(w);
+  if (n < 0) return fail(B2S_E_INVALID, "b2s_env_async_step: n_substeps < 0");
+  if (w->d.Nmax > 32) return fail(B2S_E_CAPACITY, "b2s_env_async_step: max_movables > 32");
+  cudaStream_t s = (cudaStream_t)stream;
+  DRollout& ro = w->d.ro;
+  if (ro.enabled != RO_ASYNC) {
+    memset(&ro, 0, sizeof(ro));
+    ro.enabled = RO_ASYNC; ro.max_reset_retries = 8; ro.drop_lin = 0.1f; ro.drop_ang = 0.1f; ro.drop_max_steps = 500;
+  }
+  ro.reset_seed = reset_seed;
+  b2s_launch_async_commands(w->d, command, s);
+  int rc = check_launch(w, "async_commands");
+  if (rc) return rc;
+  if (n > 0) {
+    b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
+    if ((rc = check_launch(w, "env_async_step", 2))) return rc;
+  }
+  if (status) {
+    b2s_launch_async_status(w->d, status, s);
+    if ((rc = check_launch(w, "async_status"))) return rc;
+  }
   return 0;
 }
 

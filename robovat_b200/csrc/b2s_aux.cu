@@ -72,6 +72,23 @@ __global__ void k_rollout_begin(const __grid_constant__ DWorld W, const float* f
   episode_start(W, e, lane, first_action);
 }
 
+// b2s_env_async_step, before the substeps: start the host's action in the envs it addressed (1) or re-sample their scene (2)
+__global__ void k_async_commands(const __grid_constant__ DWorld W, const uint8_t* command) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= W.B) return;
+  W.async_events[e] = 0;
+  const int cmd = command ? command[e] : 0;
+  if (W.phase[e] != B2S_PHASE_IDLE) return;            // a busy env ignores commands
+  if (cmd == 1) begin_action(W, e);
+  else if (cmd == 2) { RO_RETRY(W, e) = 0; rollout_reset(W, e); }
+}
+// ... and after them: bit0 ready for a command, bit1/bit2 the events, bit3 unsafe at 'done' (RobotEnv._done, push_env.py:719-721)
+__global__ void k_async_status(const __grid_constant__ DWorld W, uint8_t* status) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= W.B) return;
+  status[e] = (uint8_t)((W.phase[e] == B2S_PHASE_IDLE ? 1 : 0) | (W.async_events[e] & 6) | (W.phase_state[(size_t)e * 8 + 4] ? 8 : 0));
+}
+
 // ---- robot commands (sawyer_sim.py:186-308) ----
 // cmd 0: move_to_gripper_pose, 1: move_to_joint_positions, 2: reset_targets, 3: is_limb_ready,
 // 4: latch motor targets (data = q [B][7], out reinterpreted as qd [B][7] or NULL)
@@ -342,6 +359,8 @@ void b2s_launch_begin_episode(const DWorld& W, const uint8_t* mask, cudaStream_t
 void b2s_launch_rollout_begin(const DWorld& W, const float* first_action, cudaStream_t s) {
   k_rollout_begin<<<blocks_for(W.B * 32, 128), 128, 0, s>>>(W, first_action);
 }
+void b2s_launch_async_commands(const DWorld& W, const uint8_t* c, cudaStream_t s) { k_async_commands<<<blocks_for(W.B, 128), 128, 0, s>>>(W, c); }
+void b2s_launch_async_status(const DWorld& W, uint8_t* st, cudaStream_t s) { k_async_status<<<blocks_for(W.B, 128), 128, 0, s>>>(W, st); }
 void b2s_launch_observe(const DWorld& W, cudaStream_t s) { k_observe<<<blocks_for(W.B, 128), 128, 0, s>>>(W); }
 void b2s_launch_reward(const DWorld& W, const float* p, const float* n, cudaStream_t s) { k_reward<<<blocks_for(W.B, 128), 128, 0, s>>>(W, p, n); }
 void b2s_launch_arm_cmd(const DWorld& W, int cmd, const float* data, const uint8_t* mask, uint8_t* out, cudaStream_t s) {

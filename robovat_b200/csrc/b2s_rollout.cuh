@@ -330,8 +330,27 @@ __device__ __forceinline__ void policy_candidate(const DWorld& W, int e, uint64_
   *accept = clear && touches;
 }
 
+// B2S_POLICY_AIMED (synthetic workloads, bench.py): a random body, a random direction, start 8 cm behind the body, push
+// through it.  One Philox block: counter (stream 2 | action index << 8, global env id, num_episodes).
+__device__ inline void policy_aimed(const DWorld& W, int e, uint64_t seed, int action_index, int num_episodes, float out[4]) {
+  const B2SParams& P = W.P;
+  const int nb = max(1, W.buf.num_movables[e]);
+  const b2s_u4 r = b2s_philox((uint32_t)seed, (uint32_t)(seed >> 32), 0u, 2u | ((uint32_t)action_index << 8), (uint32_t)(P.env_id_offset + e), (uint32_t)num_episodes);
+  int body = (int)(b2s_u01(r.x) * (float)nb); if (body > nb - 1) body = nb - 1;
+  const float angle = -B2S_PI + (2.0f * B2S_PI) * b2s_u01(r.y);
+  float sn, cs;
+  b2s_sincos(angle, &sn, &cs);
+  const float offx = 0.5f * (P.cspace_high[0] + P.cspace_low[0]), offy = 0.5f * (P.cspace_high[1] + P.cspace_low[1]);
+  const float rngx = 0.5f * (P.cspace_high[0] - P.cspace_low[0]), rngy = 0.5f * (P.cspace_high[1] - P.cspace_low[1]);
+  const float tx = RO_BS(W, 0, e, body) - 0.08f * cs, ty = RO_BS(W, 1, e, body) - 0.08f * sn;
+  out[0] = fminf(1.0f, fmaxf(-1.0f, (tx - offx) / rngx));
+  out[1] = fminf(1.0f, fmaxf(-1.0f, (ty - offy) / rngy));
+  out[2] = cs; out[3] = sn;
+}
+
 // every lane returns the same action in out[4]
 __device__ inline void policy_sample(const DWorld& W, int e, int lane, uint64_t seed, int action_index, int num_episodes, float out[4]) {
+  if (W.ro.policy_kind == B2S_POLICY_AIMED) { policy_aimed(W, e, seed, action_index, num_episodes, out); return; }
   const int nb = max(1, W.buf.num_movables[e]);
   const int target = num_episodes % nb;
   const float a = (float)(num_episodes * RO_ANGLE_SEED);
@@ -460,8 +479,9 @@ __device__ inline void rollout_advance(const DWorld& W, int e, int lane) {
 }
 
 // The final wait of a reset has ended: re-sample scenes whose bodies fell off the table or that found no placement
-// (push_env.py:460-468; Simulator.reset_scene's retry loop), else start the episode.
-__device__ inline void rollout_reset_done(const DWorld& W, int e, int lane) {
+// (push_env.py:460-468; Simulator.reset_scene's retry loop).  Returns 0 when the scene is valid (the env is IDLE and
+// the caller starts the episode), 1 when it was re-sampled, 2 when the env gave up (error bit8, IDLE).
+__device__ inline int rollout_reset_check(const DWorld& W, int e, int lane) {
   int bad = 0;
   __syncwarp();
   if (lane == 0) {
@@ -477,6 +497,36 @@ __device__ inline void rollout_reset_done(const DWorld& W, int e, int lane) {
       W.phase[e] = B2S_PHASE_IDLE;
     }
   }
-  bad = __shfl_sync(0xffffffffu, bad, 0);
-  if (bad == 0) episode_start(W, e, lane, nullptr);
+  return __shfl_sync(0xffffffffu, bad, 0);
+}
+
+// ---- asynchronous stepping with the policy on the host (b2s_env_async_step) -----------------------------------
+// W.async_events[e]: bit1 an action finished since the last call (reward / flags / PoseObs row are fresh), bit2 a
+// reset finished (PoseObs row = first observation of the episode).  One thread.
+#define B2S_ASYNC_ACTION_DONE 2
+#define B2S_ASYNC_RESET_DONE 4
+__device__ inline void async_action_done(const DWorld& W, int e) {
+  const int N = W.Nmax, nm = W.buf.num_movables[e];
+  float* prev = W.prev_xy + (size_t)e * N * 2;
+  float s0[64], s1[64];
+  for (int i = 0; i < N; ++i) {
+    s0[i * 2] = prev[i * 2]; s0[i * 2 + 1] = prev[i * 2 + 1];
+    s1[i * 2] = (i < nm) ? RO_BS(W, 0, e, i) : 0.0f; s1[i * 2 + 1] = (i < nm) ? RO_BS(W, 1, e, i) : 0.0f;
+  }
+  bool term = false;
+  const float r = reward_eval(W, s0, s1, &term);
+  W.buf.reward[e] = r; W.buf.termination[e] = term ? 1 : 0; W.buf.episode_return[e] += r;
+  for (int i = 0; i < N * 2; ++i) prev[i] = s1[i];
+  observe_env(W, e);
+  W.async_events[e] |= B2S_ASYNC_ACTION_DONE;
+}
+__device__ inline void async_reset_done(const DWorld& W, int e) {
+  const int N = W.Nmax, nm = W.buf.num_movables[e];
+  for (int i = 0; i < N; ++i) {
+    W.prev_xy[((size_t)e * N + i) * 2] = (i < nm) ? RO_BS(W, 0, e, i) : 0.0f;
+    W.prev_xy[((size_t)e * N + i) * 2 + 1] = (i < nm) ? RO_BS(W, 1, e, i) : 0.0f;
+  }
+  W.buf.episode_return[e] = 0.0f; W.buf.reward[e] = 0.0f; W.buf.termination[e] = 0;
+  observe_env(W, e);
+  W.async_events[e] |= B2S_ASYNC_RESET_DONE;
 }

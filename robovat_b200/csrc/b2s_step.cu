@@ -1893,7 +1893,12 @@ __device__ __noinline__ void finish_action(int e, int lane) {
 
 // between two actions of a device-side episode (b2s_rollout.cuh); out of line: it runs once per ~2000 substeps
 __device__ __noinline__ void rollout_next(int e, int lane) { rollout_advance(g_W, e, lane); }
-__device__ __noinline__ void rollout_after_reset(int e, int lane) { rollout_reset_done(g_W, e, lane); }
+__device__ __noinline__ void rollout_after_reset(int e, int lane) {
+  if (rollout_reset_check(g_W, e, lane) != 0) return;
+  if (g_W.ro.enabled == RO_ASYNC) { if (lane == 0) async_reset_done(g_W, e); __syncwarp(); }
+  else episode_start(g_W, e, lane, nullptr);
+}
+__device__ __noinline__ void async_after_action(int e, int lane) { if (lane == 0) async_action_done(g_W, e); __syncwarp(); }
 
 // ----------------------------------------------------------- the kernel -----
 
@@ -2100,7 +2105,8 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
           if (fin) {
             if (ph == B2S_PHASE_SETTLE) {
               finish_action(e, lane);
-              if (W.ro.enabled) rollout_next(e, lane);     // reward, record, next action or next episode: the env goes on in this launch
+              if (W.ro.enabled == RO_EPISODES) rollout_next(e, lane);   // reward, record, next action or next episode: the env goes on in this launch
+              else if (W.ro.enabled == RO_ASYNC) async_after_action(e, lane);   // reward + observation, then the env waits for the host
             } else if (drop) {
               if (lane == 0) { W.phase[e] = B2S_PHASE_RESET_WAIT; ps[2] = 0; ps[3] = 0; }
               __syncwarp();

@@ -159,6 +159,7 @@ class PushEnv(object):
             fn.initialize(self)
         self._action_space = Box(-np.ones(4, np.float32), np.ones(4, np.float32))
         self._reset_count = 0
+        self._async = None
 
     # -- reference properties ---------------------------------------------------------------
     simulator = property(lambda self: self._simulator)
@@ -237,6 +238,7 @@ class PushEnv(object):
         if self._config.MAX_STEPS is not None and self._config.MAX_STEPS == 0:
             self._done[m] = True
         self._simulator.reset_scene(seed=self.seed, mask=None if mask is None else m)
+        self._async = None
         self._refresh_attributes()
         self._obs_data = self._prev_obs_data = None
         return self.get_observation(force=True)
@@ -301,6 +303,97 @@ class PushEnv(object):
         self.num_unsafe += int((~safe & active).sum())
         self.num_ineffective += int((~eff & active).sum())
         self.num_useful += int((safe & eff & active).sum())
+
+    # -- asynchronous stepping: nobody waits for the slowest env -------------------------------------
+    def step_async(self, action, substeps=None):
+        """One slice of asynchronous stepping with the policy on the host.
+
+        The reference collects data with one process per env (tools/parallel_run.py), each alternating
+        `policy.action(obs)` / `env.step(action)` / `env.reset()` at its own pace.  Here every call
+          * starts `action[e]` in every env that is ready (idle) and whose episode is not over; the rows of busy
+            envs are ignored,
+          * re-samples the scene of every ready env whose episode is over (auto-reset: drop + settle on the device),
+          * advances every busy env by up to `substeps` substeps (default SUBSTEP_CHUNK),
+        and returns `(obs, reward, done, info)`: `info['finished']` marks the envs whose action completed in this
+        call (reward / done / is_safe / is_effective rows are those of that transition, as `step` would return
+        them), `info['reset']` those whose reset completed (the row of `obs` is the episode's first observation),
+        `info['ready']` those that will take an action (or, if done, be reset) in the next call.  Rows of other envs
+        keep their last values.  Call `reset()` once before the first slice."""
+        B = self.num_envs
+        if self._async is None:
+            dev = self.world.device
+            self._async = {
+                'cmd_host': torch.zeros(B, dtype=torch.uint8).pin_memory(), 'cmd': torch.zeros(B, dtype=torch.uint8, device=dev),
+                'status': torch.zeros(B, dtype=torch.uint8, device=dev), 'status_host': torch.zeros(B, dtype=torch.uint8).pin_memory(),
+                'reward_host': torch.zeros(B, dtype=torch.float32).pin_memory(), 'term_host': torch.zeros(B, dtype=torch.uint8).pin_memory(),
+                'safe_host': torch.zeros(B, dtype=torch.uint8).pin_memory(), 'eff_host': torch.zeros(B, dtype=torch.uint8).pin_memory(),
+                'pos_host': torch.zeros(B, self.world.N, 3, dtype=torch.float32).pin_memory(),
+                'mask_host': torch.zeros(B, self.world.N, dtype=torch.uint8).pin_memory(),
+                'ready': np.ones(B, bool), 'calls': 0,
+            }
+            self._async['pos_host'].copy_(self.world.obs_position)
+            self._async['mask_host'].copy_(self.world.body_mask)
+        st = self._async
+        w = self.world
+        a = np.asarray(action, dtype=np.float32).reshape(-1, 4)
+        if a.shape[0] != B:
+            raise ValueError('action must have shape [%d, 4]' % B)
+        ready = st['ready']
+        start = ready & ~self._done
+        cmd = np.where(start, 1, np.where(ready & self._done, 2, 0)).astype(np.uint8)
+        st['cmd_host'].copy_(torch.from_numpy(cmd))
+        self._pinned_action.copy_(torch.from_numpy(a))
+        w.action.copy_(self._pinned_action, non_blocking=True)
+        st['cmd'].copy_(st['cmd_host'], non_blocking=True)
+        st['calls'] += 1
+        # counters as of the start of the action, for the envs that start one (robot_env.py:245-246)
+        started_steps = self._num_steps.copy()
+        w.env_async_step(st['cmd'], int(substeps or self.substep_chunk), reset_seed=self.seed * 1000003 + 7919, status=st['status'])
+        st['status_host'].copy_(st['status'], non_blocking=True)
+        st['reward_host'].copy_(w.reward_buf, non_blocking=True)
+        st['term_host'].copy_(w.termination, non_blocking=True)
+        st['safe_host'].copy_(w.is_safe, non_blocking=True)
+        st['eff_host'].copy_(w.is_effective, non_blocking=True)
+        st['pos_host'].copy_(w.obs_position, non_blocking=True)
+        st['mask_host'].copy_(w.body_mask, non_blocking=True)
+        torch.cuda.current_stream(w.device).synchronize()
+        status = st['status_host'].numpy()
+        finished = (status & 2) != 0
+        was_reset = (status & 4) != 0
+        reward = np.where(finished, st['reward_host'].numpy().astype(np.float64), 0.0)
+        termination = st['term_host'].numpy().astype(bool)
+        env_done = (status & 8) != 0
+        self._num_steps[finished] += 1
+        self._episode_reward += reward
+        done_now = finished & (termination | env_done)
+        if self._config.MAX_STEPS is not None:
+            done_now |= finished & (self._num_steps >= self._config.MAX_STEPS)
+        self._done |= done_now
+        self._num_episodes[done_now] += 1
+        self._total_reward[done_now] += self._episode_reward[done_now]
+        self._num_steps[was_reset] = 0
+        self._episode_reward[was_reset] = 0.0
+        self._done[was_reset] = False
+        safe = st['safe_host'].numpy().astype(bool)
+        eff = st['eff_host'].numpy().astype(bool)
+        self.num_total_steps += int(finished.sum())
+        self.num_unsafe += int((~safe & finished).sum())
+        self.num_ineffective += int((~eff & finished).sum())
+        self.num_useful += int((safe & eff & finished).sum())
+        st['ready'] = (status & 1) != 0
+        obs = collections.OrderedDict()
+        obs['num_episodes'] = self._num_episodes.copy()
+        obs['num_steps'] = self._num_steps.copy()
+        obs['layout_id'] = np.full(B, self.layout_id if self.layout_id is not None else 0, np.int64)
+        obs['body_mask'] = st['mask_host'].numpy().astype(np.float32)
+        obs['position'] = st['pos_host'].numpy().copy()
+        obs['is_safe'] = safe.astype(np.int64)
+        obs['is_effective'] = eff.astype(np.int64)
+        info = {'finished': finished, 'reset': was_reset, 'ready': st['ready'].copy(), 'started_num_steps': started_steps}
+        return obs, reward.astype(np.float32), self._done.copy(), info
+
+    async_h2d_bytes = property(lambda self: self.num_envs * (4 * 4 + 1))
+    async_d2h_bytes = property(lambda self: self.num_envs * (1 + 4 + 1 + 1 + 1 + self.world.N * 13))
 
     # -- helpers kept from the reference --------------------------------------------------------
     def _compute_waypoints(self, action):

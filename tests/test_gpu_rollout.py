@@ -68,13 +68,13 @@ def test_rollout_matches_oracle_rollout(task):
 
 def test_rollout_budget_stops_mid_episode_and_resumes():
     """A substep budget cuts the rollout anywhere (mid action, mid reset); the state then equals the oracle's after the
-    same number of substeps per env, and a second run call finishes the episodes."""
+    same number of substeps per env, and a second run call finishes the episodes.  Uses the aimed policy (bench.py)."""
     A, EP, B = 2, 2, 16
     cfg, gpu, cpu = helpers.make_pair(B, params={'export_debug': 0})
     _prepare(gpu, cpu, seed=8)
     rec = RolloutRecord(B, gpu.N, EP, A, gpu.device)
-    gpu.rollout_begin(A, EP, policy_seed=1, reset_seed=2, max_attempts=2000, record=rec)
-    ref = cpu.rollout_begin(A, EP, policy_seed=1, reset_seed=2, max_attempts=2000)
+    gpu.rollout_begin(A, EP, policy_seed=1, reset_seed=2, record=rec, policy_kind=_capi.POLICY_AIMED)
+    ref = cpu.rollout_begin(A, EP, policy_seed=1, reset_seed=2, policy_kind=_capi.POLICY_AIMED)
     left = gpu.rollout_run(chunk=300, max_substeps=3000)
     assert left > 0
     cpu.rollout_run(3000)
@@ -115,3 +115,89 @@ def test_rollout_with_given_first_action_and_lockstep_api_afterwards():
     helpers.assert_bits_equal(gpu.body_state.cpu().numpy(), cpu.body_state, 'lock-step action after the rollout')
     gpu.close()
     cpu.close()
+
+
+def test_async_step_matches_oracle_and_push_env_step_async():
+    """b2s_env_async_step against the oracle twin under the same command stream (actions for ready envs, a reset after
+    every third action), slice by slice: status bytes, rewards, PoseObs rows and the body state are bit-identical."""
+    B = 40
+    cfg, gpu, cpu = helpers.make_pair(B, params={'export_debug': 0}, TASK_NAME='clearing', LAYOUT_ID=0)
+    _prepare(gpu, cpu, seed=5)
+    rs = np.random.RandomState(1)
+    dev = gpu.device
+    status_g = torch.zeros(B, dtype=torch.uint8, device=dev)
+    ready = np.ones(B, bool)
+    since_reset = np.zeros(B, int)
+    need_reset = np.zeros(B, bool)
+    finished_total = resets_total = 0
+    for it in range(60):
+        cmd = np.zeros(B, np.uint8)
+        act = rs.uniform(-1, 1, (B, 4)).astype(np.float32)
+        for e in range(B):
+            if ready[e]:
+                if need_reset[e]:
+                    cmd[e], need_reset[e], since_reset[e] = 2, False, 0
+                else:
+                    cmd[e] = 1
+                    since_reset[e] += 1
+        gpu.action.copy_(torch.from_numpy(act))
+        cpu.array('action')[:] = act.ravel()
+        gpu.env_async_step(torch.from_numpy(cmd).to(dev), 400, reset_seed=31, status=status_g)
+        status_c = cpu.env_async_step(cmd, 400, reset_seed=31)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(status_g.cpu().numpy(), status_c, err_msg='status, slice %d' % it)
+        fin = (status_c & 2) != 0
+        helpers.assert_bits_equal(gpu.reward_buf.cpu().numpy()[fin], cpu.array('reward')[fin], 'reward, slice %d' % it)
+        np.testing.assert_array_equal(gpu.termination.cpu().numpy()[fin], cpu.array('termination')[fin])
+        np.testing.assert_array_equal(gpu.is_effective.cpu().numpy()[fin], cpu.array('is_effective')[fin])
+        helpers.assert_bits_equal(gpu.obs_position.cpu().numpy(), cpu.array('obs_position').reshape(B, -1, 3), 'PoseObs, slice %d' % it)
+        need_reset |= fin & (since_reset >= 3)
+        finished_total += int(fin.sum())
+        resets_total += int(((status_c & 4) != 0).sum())
+        ready = (status_c & 1) != 0
+    helpers.assert_bits_equal(gpu.body_state.cpu().numpy(), cpu.body_state, 'body_state')
+    helpers.assert_bits_equal(gpu.episode_return.cpu().numpy(), cpu.array('episode_return'), 'episode_return')
+    assert finished_total > 2 * B and resets_total > B // 2
+    gpu.close()
+    cpu.close()
+
+
+def test_push_env_step_async_bookkeeping():
+    """PushEnv.step_async: host counters follow the events (num_steps, done at MAX_STEPS, auto-reset), every finished
+    transition equals what the lock-step `step` returns for the same env and action."""
+    from robovat_b200 import config as config_lib
+    from robovat_b200.envs import PushEnv
+    cfg = config_lib.default_push_env_config()
+    cfg.MAX_STEPS = 2
+    B = 24
+    rs = np.random.RandomState(2)
+    script = rs.uniform(-1, 1, (B, 2, 4)).astype(np.float32)
+    env = PushEnv(config=cfg, num_envs=B, seed=11)
+    obs0 = env.reset()
+    taken = np.zeros(B, int)
+    got = {}
+    first_obs_after_reset = {}
+    act = script[:, 0].copy()
+    for it in range(400):
+        obs, reward, done, info = env.step_async(act, substeps=500)
+        for e in np.nonzero(info['finished'])[0]:
+            got[(e, taken[e])] = (float(reward[e]), obs['position'][e].copy(), bool(done[e]), int(obs['num_steps'][e]))
+            taken[e] += 1
+        for e in np.nonzero(info['reset'])[0]:
+            first_obs_after_reset.setdefault(e, obs['position'][e].copy())
+            assert obs['num_steps'][e] == 0 and not done[e]
+        act = np.stack([script[e, min(taken[e], 1)] for e in range(B)])
+        if (taken >= 2).all() and len(first_obs_after_reset) == B:
+            break
+    assert (taken >= 2).all() and len(first_obs_after_reset) == B
+    env2 = PushEnv(config=cfg, num_envs=B, seed=11)
+    env2.reset()
+    for k in range(2):
+        obs, reward, done, _ = env2.step(script[:, k])
+        for e in range(B):
+            r, pos, d, ns = got[(e, k)]
+            assert r == float(reward[e]) and d == bool(done[e]) and ns == k + 1
+            helpers.assert_bits_equal(pos, obs['position'][e], 'position of env %d after action %d' % (e, k))
+    assert done.all()
+    env.close()
+    env2.close()

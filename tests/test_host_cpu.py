@@ -229,7 +229,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--cpu-seconds', '1']
+    cmd = [sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--envs', '256', '--substeps', '500']
     env = dict(os.environ, RANK='0', WORLD_SIZE='1', LOCAL_RANK='0')
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -238,6 +238,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['higher_is_better'] is True and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1 and line['cpu_baseline']['value'] == line['value']
     assert line['e2e'] == {'value': line['value'], 'unit': 'substeps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert line['config']['workload'].startswith('PushEnv 4096 batched envs') and line['config']['policy'] == 'B2S_POLICY_AIMED'
+    assert line['ms_per_step'] > 0 and line['cpu_baseline']['reference_cpu'].startswith('pybullet ')
     env['RANK'] = '1'
     env['WORLD_SIZE'] = '2'
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=env, cwd=root)

@@ -173,3 +173,92 @@ def test_policy_accepts_what_the_reference_sampler_accepts():
     # the start points are uniform over the square
     assert abs(one[:, :2].mean()) < 0.2 and one[:, :2].std() > 0.4
     w.close()
+
+
+def test_async_stepping_equals_lockstep_per_env():
+    """b2s_env_async_step's semantics on the oracle: envs take scripted actions whenever they are ready, are reset after
+    three actions, and advance in slices of 300 substeps.  Per env the sequence of finished transitions (reward, PoseObs
+    row, flags) and the final state equal the lock-step calls applied to that env alone -- waiting for a slice boundary
+    changes nothing."""
+    B, K = 5, 5
+    rs = np.random.RandomState(3)
+    script = rs.uniform(-1, 1, (B, K, 4)).astype(np.float32)
+    cfg, w = _settled_oracle(B, seed=6, **TASK)
+    w.begin_episode()
+    taken = np.zeros(B, int)           # actions started
+    since_reset = np.zeros(B, int)
+    need_reset = np.zeros(B, bool)
+    ready = np.ones(B, bool)
+    log = [[] for _ in range(B)]
+    for it in range(2000):
+        if (taken >= K).all() and ready.all():
+            break
+        cmd = np.zeros(B, np.uint8)
+        act = np.zeros((B, 4), np.float32)
+        for e in range(B):
+            if not ready[e]:
+                continue
+            if need_reset[e]:
+                cmd[e] = 2
+                need_reset[e] = False
+                since_reset[e] = 0
+            elif taken[e] < K:
+                cmd[e] = 1
+                act[e] = script[e, taken[e]]
+                taken[e] += 1
+                since_reset[e] += 1
+        w.array('action')[:] = act.ravel()
+        status = w.env_async_step(cmd, 300, reset_seed=12)
+        for e in range(B):
+            if status[e] & 2:
+                log[e].append(('action', float(w.array('reward')[e]), w.array('obs_position').reshape(B, -1, 3)[e].copy(),
+                               int(w.array('is_safe')[e]), int(w.array('is_effective')[e]), int(w.array('termination')[e])))
+                if since_reset[e] == 3:
+                    need_reset[e] = True
+            if status[e] & 4:
+                log[e].append(('reset', w.array('obs_position').reshape(B, -1, 3)[e].copy()))
+        ready = (status & 1) != 0
+    assert (taken == K).all()
+    final = w.body_state.copy()
+
+    cfg2, w2 = _settled_oracle(B, seed=6, **TASK)
+    w2.begin_episode()
+    table_z = [s['pose'][2] for s in w2.scene.statics if s['flags'] & _capi.STATIC_IS_TABLE][-1]
+    for e in range(B):
+        only = np.zeros(B, np.uint8)
+        only[e] = 1
+        others = np.arange(B) != e
+        expect = []
+        for k in range(K):
+            if k == 3:
+                for attempt in range(9):
+                    w2.reset(seed=12, mask=only)
+                    w2.settle(0.1, 0.1, 500, mask=only)
+                    w2.settle(mask=only)
+                    nm = int(w2.num_movables[e])
+                    bad = bool((w2.body_state[2, e, :nm] < np.float32(table_z) + w2.array(_capi.ARR_TABLE_DZ)[e]).any()) or bool(w2.array(_capi.ARR_ERROR_FLAGS)[e] & 128)
+                    if not bad:
+                        break
+                w2.begin_episode(mask=only)
+                expect.append(('reset', w2.observe()[e].copy()))
+            a = w2.array('action').reshape(B, 4).copy()
+            a[e] = script[e, k]
+            ph = w2.array(_capi.ARR_PHASE).copy()
+            w2.set_action(a)
+            w2.array(_capi.ARR_PHASE)[others] = ph[others]
+            while w2.array(_capi.ARR_PHASE)[e] != _capi.PHASE_IDLE:
+                w2.env_substeps(500)
+            pos = w2.observe()[e].copy()
+            r, term = w2.reward()
+            expect.append(('action', float(r[e]), pos, int(w2.array('is_safe')[e]), int(w2.array('is_effective')[e]), int(term[e])))
+        assert len(expect) == len(log[e]), (e, len(expect), len(log[e]))
+        for got, want in zip(log[e], expect):
+            assert got[0] == want[0]
+            if got[0] == 'action':
+                assert got[1] == want[1] and got[3:] == want[3:], (e, got, want)
+                helpers.assert_bits_equal(got[2], want[2], 'PoseObs row of env %d' % e)
+            else:
+                helpers.assert_bits_equal(got[1], want[1], 'first observation of env %d' % e)
+    helpers.assert_bits_equal(final, w2.body_state, 'final body_state')
+    w.close()
+    w2.close()
