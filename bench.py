@@ -226,6 +226,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--exact-schedule', action='store_true', help='every launch advances every env by exactly 250 substeps (default: free-running launches)')
     ap.add_argument('--no-extras', action='store_true', help='skip lockstep / pose_tolerance / other_configs')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -295,7 +296,7 @@ def main():
 
     # ---- device-resident leg: the rollout runs entirely on the device ---------------------------
     w.rollout_begin(cfg.MAX_STEPS, num_episodes=1 << 20, policy_seed=POLICY_SEED, reset_seed=RESET_SEED, record=None,
-                    policy_kind=_capi.POLICY_AIMED)
+                    policy_kind=_capi.POLICY_AIMED, free_running=not args.exact_schedule)
     kernel_events = []
 
     def device_step(timed, last=False):
@@ -348,7 +349,7 @@ def main():
         def e2e_step(obs, last=False):
             for _ in range(slices):
                 act = heuristic_actions_np(obs['position'], obs['body_mask'], cfg, rs)       # host policy on the host observation
-                obs, rew, done, info = env2.step_async(act, substeps=CHUNK)
+                obs, rew, done, info = env2.step_async(act, substeps=CHUNK, free_running=not args.exact_schedule)
             gather_returns(w2, last)
             return obs
         for _ in range(args.warmup):
@@ -464,7 +465,8 @@ def extras(args, cfg, env, device, threads):
         env3 = PushEnv(config=cfg3, num_envs=B, seed=args.seed, device=device)
         env3.reset()
         w3 = env3.world
-        w3.rollout_begin(cfg3.MAX_STEPS, num_episodes=1 << 20, policy_seed=POLICY_SEED, reset_seed=RESET_SEED, record=None, policy_kind=_capi.POLICY_AIMED)
+        w3.rollout_begin(cfg3.MAX_STEPS, num_episodes=1 << 20, policy_seed=POLICY_SEED, reset_seed=RESET_SEED, record=None, policy_kind=_capi.POLICY_AIMED,
+                         free_running=not args.exact_schedule)
         w3.rollout_run(chunk=CHUNK, max_substeps=500)
         torch.cuda.synchronize()
         s0 = w3.substeps_executed()

@@ -315,6 +315,12 @@ typedef struct B2SRollout {
   int32_t drop_max_steps;      /* 500 */
   int32_t policy_kind;         /* B2S_POLICY_HEURISTIC (HeuristicPushSampler), B2S_POLICY_AIMED (synthetic workloads: start
                                   8 cm behind a random body in a random direction and push through it; always a contact) */
+  int32_t free_running;        /* 0: every launch advances every env by exactly `chunk` substeps.  1: a launch ends when it has
+                                  executed chunk x (running envs) substeps IN TOTAL, all thread blocks stopping together -- envs
+                                  that are cheap to step get ahead of expensive ones and no SM waits for the slowest block.
+                                  What an env computes is unchanged (its episodes do not depend on the schedule); only how far
+                                  each env has got when a call returns is. */
+  int32_t reserved;
   const float* first_action;   /* [B][4] action of step 0 of episode 0, or NULL: drawn by the device policy like the others */
   float* actions;              /* out [B][EP][A][4] */
   float* rewards;              /* out [B][EP][A] */
@@ -344,6 +350,10 @@ int b2s_rollout_run(B2SWorld* world, int chunk, int max_substeps, int* unfinishe
  * its last action unsafe at 'done' (RobotEnv._done, push_env.py:719-721). */
 int b2s_env_async_step(B2SWorld* world, const uint8_t* command_dev, int n_substeps, uint64_t reset_seed, uint8_t* status_dev,
                        void* stream);
+/* the same with a free-running launch (see B2SRollout.free_running): n_substeps x (busy envs) substeps in total, at most
+ * 2 n_substeps for one env */
+int b2s_env_async_step_free(B2SWorld* world, const uint8_t* command_dev, int n_substeps, uint64_t reset_seed, uint8_t* status_dev,
+                            void* stream);
 
 /* robot commands outside the phase machine (sawyer_sim.py:186-308); poses/q are device pointers */
 int b2s_arm_move_to_gripper_pose(B2SWorld* world, const float* pose_dev /*[B][7]*/, const uint8_t* env_mask_dev, void* stream);

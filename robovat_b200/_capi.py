@@ -112,7 +112,7 @@ class B2SRollout(C.Structure):
     _fields_ = [
         ('num_actions', i32), ('max_attempts', i32), ('num_episodes', i32), ('max_reset_retries', i32),
         ('seed', C.c_uint64), ('reset_seed', C.c_uint64),
-        ('drop_lin_threshold', f32), ('drop_ang_threshold', f32), ('drop_max_steps', i32), ('policy_kind', i32),
+        ('drop_lin_threshold', f32), ('drop_ang_threshold', f32), ('drop_max_steps', i32), ('policy_kind', i32), ('free_running', i32), ('reserved', i32),
         ('first_action', C.c_void_p), ('actions', C.c_void_p), ('rewards', C.c_void_p), ('positions', C.c_void_p),
         ('flags', C.c_void_p), ('substeps', C.c_void_p), ('lengths', C.c_void_p), ('returns', C.c_void_p),
     ]
@@ -141,6 +141,7 @@ SYMBOLS = {
     'b2s_rollout_begin': (C.c_int, [_vp, P(B2SRollout), _vp]),
     'b2s_rollout_run': (C.c_int, [_vp, C.c_int, C.c_int, P(C.c_int), _vp]),
     'b2s_env_async_step': (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, _vp, _vp]),
+    'b2s_env_async_step_free': (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, _vp, _vp]),
     'b2s_arm_move_to_gripper_pose': (C.c_int, [_vp, _vp, _vp, _vp]),
     'b2s_arm_move_to_joint_positions': (C.c_int, [_vp, _vp, _vp, _vp]),
     'b2s_arm_reset_targets': (C.c_int, [_vp, _vp, _vp]),

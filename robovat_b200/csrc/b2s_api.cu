@@ -274,7 +274,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
   ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
   ALLOC(ro_state, B * 4, 0); ALLOC(num_episodes, B, 0); ALLOC(async_events, B, 0);
-  ALLOC(substeps, 1, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16, 0);
+  ALLOC(substeps, 1, 0); ALLOC(free_target, 1, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16, 0);
   if ((rc = dalloc(w, &w->exp_keys, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_npts, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_pts, B * M * 4 * B2S_CP_FLOATS, 0))) return rc;
@@ -462,7 +462,7 @@ int b2s_rollout_begin(B2SWorld* w, const B2SRollout* r, void* stream) {
   if (r->num_episodes < 1) return fail(B2S_E_INVALID, "b2s_rollout_begin: num_episodes < 1");
   if (r->max_reset_retries < 0) return fail(B2S_E_INVALID, "b2s_rollout_begin: max_reset_retries < 0");
   ro.enabled = RO_EPISODES; ro.num_actions = r->num_actions; ro.max_attempts = r->max_attempts; ro.num_episodes = r->num_episodes;
-  ro.max_reset_retries = r->max_reset_retries; ro.drop_max_steps = r->drop_max_steps; ro.policy_kind = r->policy_kind; ro.pad = 0;
+  ro.max_reset_retries = r->max_reset_retries; ro.drop_max_steps = r->drop_max_steps; ro.policy_kind = r->policy_kind; ro.free_running = r->free_running ? 1 : 0;
   ro.drop_lin = r->drop_lin_threshold; ro.drop_ang = r->drop_ang_threshold;
   ro.seed = r->seed; ro.reset_seed = r->reset_seed;
   ro.actions = r->actions; ro.rewards = r->rewards; ro.positions = r->positions; ro.flags = r->flags;
@@ -480,7 +480,8 @@ int b2s_rollout_run(B2SWorld* w, int chunk, int max_substeps, int* unfinished_ho
   while (launched < max_substeps) {
     CU(cudaMemsetAsync(w->d.unfinished, 0, sizeof(int), s));
     const int n = (max_substeps - launched < chunk) ? (max_substeps - launched) : chunk;
-    b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
+    if (w->d.ro.free_running) b2s_launch_substeps(w->d, 2 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
+    else b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
     int rc = check_launch(w, "rollout_run", 2);
     if (rc) return rc;
     CU(cudaMemcpyAsync(w->unfinished_pinned + (i & 3), w->d.unfinished, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -498,7 +499,14 @@ int b2s_rollout_run(B2SWorld* w, int chunk, int max_substeps, int* unfinished_ho
   return 0;
 }
 
+static int async_step(B2SWorld* w, const uint8_t* command, int n, uint64_t reset_seed, uint8_t* status, void* stream, bool free_running);
 int b2s_env_async_step(B2SWorld* w, const uint8_t* command, int n, uint64_t reset_seed, uint8_t* status, void* stream) {
+  return async_step(w, command, n, reset_seed, status, stream, false);
+}
+int b2s_env_async_step_free(B2SWorld* w, const uint8_t* command, int n, uint64_t reset_seed, uint8_t* status, void* stream) {
+  return async_step(w, command, n, reset_seed, status, stream, true);
+}
+static int async_step(B2SWorld* w, const uint8_t* command, int n, uint64_t reset_seed, uint8_t* status, void* stream, bool free_running) {
   NEED_READY(w);
   if (n < 0) return fail(B2S_E_INVALID, "b2s_env_async_step: n_substeps < 0");
   if (w->d.Nmax > 32) return fail(B2S_E_CAPACITY, "b2s_env_async_step: max_movables > 32");
@@ -513,7 +521,8 @@ int b2s_env_async_step(B2SWorld* w, const uint8_t* command, int n, uint64_t rese
   int rc = check_launch(w, "async_commands");
   if (rc) return rc;
   if (n > 0) {
-    b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
+    if (free_running) b2s_launch_substeps(w->d, 2 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
+    else b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
     if ((rc = check_launch(w, "env_async_step", 2))) return rc;
   }
   if (status) {

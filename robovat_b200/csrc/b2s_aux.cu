@@ -178,7 +178,7 @@ __global__ void k_rebuild_colliders(const __grid_constant__ DWorld W) {
 // warm start), which no deal can predict.
 #define HEAVY_KEY 60       // iterations x colours of the last substep from which an environment counts as expensive (a resting
                            // scene has none: then the deal is a plain round-robin, which is the best for uniform work)
-__global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DWorld W, int mode, int nblocks) {
+__global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DWorld W, int mode, int nblocks, int free_chunk) {
   __shared__ int hist[256];
   __shared__ int base[256];
   __shared__ int s_heavy;
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
   // (only when the stepping environments need more than one wave per block anyway: a sparse launch -- the tail of
   // a batched PushEnv.step -- is fastest with the environments spread one per block)
   const int stepping = W.B - hist[255];
+  if (threadIdx.x == 0 && free_chunk > 0) *W.free_target = *W.substeps + (unsigned long long)stepping * (unsigned long long)free_chunk;
   // B2S_HW expensive environments per block of that class (default: one per warp), topped up with B2S_LF of the
   // cheapest ones (default: none)
 #ifndef B2S_HW
@@ -350,8 +351,8 @@ __global__ void k_se3(int op, const float* a, const float* b, float* out, int n)
 
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
-void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s) {
-  k_assign_envs<<<1, 1024, 0, s>>>(W, mode, W.num_blocks);
+void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk) {
+  k_assign_envs<<<1, 1024, 0, s>>>(W, mode, W.num_blocks, free_chunk);
 }
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s) { k_reset<<<blocks_for(W.B, 64), 64, 0, s>>>(W, mask, seed); }
 void b2s_launch_set_action(const DWorld& W, cudaStream_t s) { k_set_action<<<blocks_for(W.B, 128), 128, 0, s>>>(W); }

@@ -94,7 +94,7 @@ struct DLayout {
 // device-side episode driver (b2s_rollout_*, b2s_env_async_step; b2s_rollout.cuh)
 enum { RO_OFF = 0, RO_EPISODES = 1, RO_ASYNC = 2 };    // DRollout.enabled
 struct DRollout {
-  int enabled, num_actions, max_attempts, num_episodes, max_reset_retries, drop_max_steps, policy_kind, pad;
+  int enabled, num_actions, max_attempts, num_episodes, max_reset_retries, drop_max_steps, policy_kind, free_running;
   float drop_lin, drop_ang;
   unsigned long long seed, reset_seed;
   float* actions; float* rewards; float* positions; uint8_t* flags; int32_t* substeps; int32_t* lengths; float* returns;
@@ -180,6 +180,7 @@ struct DWorld {
   float* row_scratch;             // [blocks][warps][32][68] solver rows of the environment a warp is solving (L1/L2 resident)
   int32_t* ro_state;              // [B][4] rollout: step of the episode, episode index, re-samples of the current reset, spare
   int32_t* num_episodes;          // [B] episodes finished by the device-side driver
+  unsigned long long* free_target;   // [1] value of *substeps at which a free-running launch stops (set by k_assign_envs)
   int32_t* async_events;          // [B] b2s_env_async_step: what happened to the env since the last call (B2S_ASYNC_*)
   DRollout ro;
   SmemLayout sm;
@@ -207,12 +208,15 @@ static inline void b2s_opt_in_smem(K kernel, size_t smem, size_t* configured /* 
 }
 
 // host launchers (defined next to their kernels)
-void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s);
+// free_chunk > 0 (MODE_ENV only): a free-running launch -- the blocks stop together once the launch has executed
+// free_chunk substeps per stepping environment IN TOTAL (n then only caps what one environment may take)
+void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s,
+                         int free_chunk = 0);
 void b2s_launch_begin_episode(const DWorld& W, const uint8_t* mask, cudaStream_t s);
 void b2s_launch_rollout_begin(const DWorld& W, const float* first_action, cudaStream_t s);
 void b2s_launch_async_commands(const DWorld& W, const uint8_t* command, cudaStream_t s);
 void b2s_launch_async_status(const DWorld& W, uint8_t* status, cudaStream_t s);
-void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s);
+void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk = 0);
 void b2s_launch_staged(const DWorld& W, int n, cudaStream_t s, int64_t* launches);
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s);
 void b2s_launch_set_action(const DWorld& W, cudaStream_t s);

@@ -1986,8 +1986,9 @@ __device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_o
 // (2.0x slower: 16 warps in 16 code regions), warps leaving the barrier protocol during long solves
 // (1.15-1.25x slower: persistent stragglers become the tail of the launch), two 8-warp blocks per SM (1.2x).
 __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps,
-                                                                                 const uint8_t* __restrict__ env_mask) {
+                                                                                 const uint8_t* __restrict__ env_mask, int free_run) {
   __shared__ int s_cnt[4];    // hand-out counters of the three stages, candidate pairs of the block in this round
+  __shared__ int s_stop;      // free-running launch: the launch has done its total of substeps, every block stops after its round
 #ifdef B2S_PROF
   __shared__ int s_maxc;
   if (threadIdx.x == 0) s_maxc = 0;
@@ -2000,7 +2001,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
   const B2SParams& P = W.P;
   for (int slot = wib; slot < E; slot += Wn)
     if (lane < META_WORDS) env_meta(slot)[lane] = 0;
-  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; }
+  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; s_stop = 0; }
   __syncthreads();
   int done_steps = 0;
   int any_next = 0;
@@ -2020,7 +2021,18 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       }
     }
     any_next = 0;
+    // Free-running launch (environments of a rollout are independent: nobody has to wait for anybody).  Every warp
+    // publishes the substeps it has done to the global counter once per round; when the launch has executed its total,
+    // all blocks stop within one round of each other, whatever their environments cost -- no SM idles at the end of a
+    // launch behind the slowest block.  Which environment got how many substeps depends on the schedule; what an
+    // environment computes does not.
+    if (free_run && s > 0) {
+      if (lane == 0 && done_steps) { atomicAdd(W.substeps, (unsigned long long)done_steps); }
+      done_steps = 0;
+      if (threadIdx.x == 0) s_stop = (*(volatile unsigned long long*)W.substeps >= *(volatile unsigned long long*)W.free_target) ? 1 : 0;
+    }
     if (!__syncthreads_or(any)) break;
+    if (free_run && s_stop) break;
     if (threadIdx.x == 0) s_cnt[2] = 0;
 #ifdef B2S_PROF
     long long pstart_ = prof_now();
@@ -2161,7 +2173,8 @@ static DevLaunch g_launch[B2S_MAX_DEVICES];
 static size_t g_smem_configured[B2S_MAX_DEVICES];
 static std::mutex g_launch_mutex;
 
-void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s) {
+void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s,
+                         int free_chunk) {
   std::lock_guard<std::mutex> lock(g_launch_mutex);
   const int wpb = W.P.warps_per_block;
   const int blocks = W.num_blocks;
@@ -2171,9 +2184,10 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
   cudaGetDevice(&dev);
   DevLaunch* L = (dev >= 0 && dev < B2S_MAX_DEVICES) ? &g_launch[dev] : nullptr;
   if (L && L->have && L->stream != s) cudaStreamWaitEvent(s, L->done, 0);
-  b2s_launch_assign_envs(W, mode, s);
+  if (mode != MODE_ENV) free_chunk = 0;
+  b2s_launch_assign_envs(W, mode, s, free_chunk);
   cudaMemcpyToSymbolAsync(g_W, &W, sizeof(DWorld), 0, cudaMemcpyHostToDevice, s);
-  k_substeps<<<blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask);
+  k_substeps<<<blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, free_chunk > 0 ? 1 : 0);
   if (L) {
     if (!L->have) { if (cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming) == cudaSuccess) L->have = true; }
     if (L->have) { cudaEventRecord(L->done, s); L->stream = s; }

@@ -305,7 +305,7 @@ class PushEnv(object):
         self.num_useful += int((safe & eff & active).sum())
 
     # -- asynchronous stepping: nobody waits for the slowest env -------------------------------------
-    def step_async(self, action, substeps=None):
+    def step_async(self, action, substeps=None, free_running=True):
         """One slice of asynchronous stepping with the policy on the host.
 
         The reference collects data with one process per env (tools/parallel_run.py), each alternating
@@ -313,7 +313,9 @@ class PushEnv(object):
           * starts `action[e]` in every env that is ready (idle) and whose episode is not over; the rows of busy
             envs are ignored,
           * re-samples the scene of every ready env whose episode is over (auto-reset: drop + settle on the device),
-          * advances every busy env by up to `substeps` substeps (default SUBSTEP_CHUNK),
+          * advances every busy env by up to `substeps` substeps (default SUBSTEP_CHUNK); with `free_running` the slice
+            is `substeps` x (busy envs) substeps in total and cheap envs get further than expensive ones
+            (b2s_env_async_step_free),
         and returns `(obs, reward, done, info)`: `info['finished']` marks the envs whose action completed in this
         call (reward / done / is_safe / is_effective rows are those of that transition, as `step` would return
         them), `info['reset']` those whose reset completed (the row of `obs` is the episode's first observation),
@@ -348,7 +350,8 @@ class PushEnv(object):
         st['calls'] += 1
         # counters as of the start of the action, for the envs that start one (robot_env.py:245-246)
         started_steps = self._num_steps.copy()
-        w.env_async_step(st['cmd'], int(substeps or self.substep_chunk), reset_seed=self.seed * 1000003 + 7919, status=st['status'])
+        w.env_async_step(st['cmd'], int(substeps or self.substep_chunk), reset_seed=self.seed * 1000003 + 7919, status=st['status'],
+                         free_running=free_running)
         st['status_host'].copy_(st['status'], non_blocking=True)
         st['reward_host'].copy_(w.reward_buf, non_blocking=True)
         st['term_host'].copy_(w.termination, non_blocking=True)

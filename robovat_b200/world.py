@@ -172,13 +172,14 @@ class World(object):
 
     # -- episodes on the device -----------------------------------------------------------------
     def rollout_begin(self, num_actions, num_episodes=1, policy_seed=0, reset_seed=0, max_attempts=20000,
-                      first_action=None, record=None, max_reset_retries=8, drop_thresholds=(0.1, 0.1, 500), policy_kind=0):
+                      first_action=None, record=None, max_reset_retries=8, drop_thresholds=(0.1, 0.1, 500), policy_kind=0, free_running=False):
         """Start episode 0 of a device-side rollout in every env (from its reset, settled state).  `record` is a
         RolloutRecord (or None: nothing is recorded).  Returns the record."""
         r = _capi.B2SRollout()
         r.num_actions, r.num_episodes, r.max_attempts = int(num_actions), int(num_episodes), int(min(max_attempts, 65535))
         r.max_reset_retries = int(max_reset_retries)
         r.policy_kind = int(policy_kind)
+        r.free_running = int(bool(free_running))
         r.seed, r.reset_seed = int(policy_seed), int(reset_seed)
         r.drop_lin_threshold, r.drop_ang_threshold, r.drop_max_steps = float(drop_thresholds[0]), float(drop_thresholds[1]), int(drop_thresholds[2])
         fa = None
@@ -199,9 +200,10 @@ class World(object):
         self._chk(self.lib.b2s_rollout_run(self.h, int(chunk), int(max_substeps), C.byref(u), self._stream()))
         return u.value
 
-    def env_async_step(self, command, n, reset_seed=0, status=None):
-        """b2s_env_async_step: `command` uint8 [B] device tensor (or None), `status` uint8 [B] device tensor out."""
-        self._chk(self.lib.b2s_env_async_step(self.h, self._ptr(command), int(n), C.c_uint64(int(reset_seed)),
+    def env_async_step(self, command, n, reset_seed=0, status=None, free_running=False):
+        """b2s_env_async_step(_free): `command` uint8 [B] device tensor (or None), `status` uint8 [B] device tensor out."""
+        fn = self.lib.b2s_env_async_step_free if free_running else self.lib.b2s_env_async_step
+        self._chk(fn(self.h, self._ptr(command), int(n), C.c_uint64(int(reset_seed)),
                                               self._ptr(status), self._stream()))
         return status
 

@@ -36,16 +36,17 @@ def _compare_records(rec, ref, A):
     helpers.assert_bits_equal(g['returns'], ref['returns'], 'returns')
 
 
-@pytest.mark.parametrize('task', [None, 'clearing'])
-def test_rollout_matches_oracle_rollout(task):
+@pytest.mark.parametrize('task,free_running', [(None, False), ('clearing', False), (None, True), ('clearing', True)])
+def test_rollout_matches_oracle_rollout(task, free_running):
     """48 envs, three episodes of up to three actions each with scene resets in between; runs of 250 substeps on the
-    GPU against runs of 1000 on the CPU (the chunking must not matter)."""
+    GPU against runs of 1000 on the CPU (the chunking must not matter).  free_running: the launches stop on a total of
+    substeps instead of a count per env -- envs advance unevenly, their episodes must not change."""
     A, EP, B = 3, 3, 48
     bind = {} if task is None else dict(TASK_NAME=task, LAYOUT_ID=0)
     cfg, gpu, cpu = helpers.make_pair(B, params={'export_debug': 0}, **bind)
     _prepare(gpu, cpu, seed=4)
     rec = RolloutRecord(B, gpu.N, EP, A, gpu.device)
-    gpu.rollout_begin(A, EP, policy_seed=13, reset_seed=6, max_attempts=2000, record=rec)
+    gpu.rollout_begin(A, EP, policy_seed=13, reset_seed=6, max_attempts=2000, record=rec, free_running=free_running)
     ref = cpu.rollout_begin(A, EP, policy_seed=13, reset_seed=6, max_attempts=2000)
     assert gpu.rollout_run(chunk=250, max_substeps=400000) == 0
     launched = 0
@@ -142,7 +143,7 @@ def test_async_step_matches_oracle_and_push_env_step_async():
                     since_reset[e] += 1
         gpu.action.copy_(torch.from_numpy(act))
         cpu.array('action')[:] = act.ravel()
-        gpu.env_async_step(torch.from_numpy(cmd).to(dev), 400, reset_seed=31, status=status_g)
+        gpu.env_async_step(torch.from_numpy(cmd).to(dev), 400, reset_seed=31, status=status_g, free_running=False)
         status_c = cpu.env_async_step(cmd, 400, reset_seed=31)
         torch.cuda.synchronize()
         np.testing.assert_array_equal(status_g.cpu().numpy(), status_c, err_msg='status, slice %d' % it)
@@ -179,7 +180,7 @@ def test_push_env_step_async_bookkeeping():
     first_obs_after_reset = {}
     act = script[:, 0].copy()
     for it in range(400):
-        obs, reward, done, info = env.step_async(act, substeps=500)
+        obs, reward, done, info = env.step_async(act, substeps=500, free_running=(it % 2 == 0))
         for e in np.nonzero(info['finished'])[0]:
             got[(e, taken[e])] = (float(reward[e]), obs['position'][e].copy(), bool(done[e]), int(obs['num_steps'][e]))
             taken[e] += 1

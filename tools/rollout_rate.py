@@ -1,6 +1,6 @@
 """Throughput of the device-side rollout: B envs, every launch advances every env by `chunk` substeps.
 
-usage: python tools/rollout_rate.py [envs] [chunk] [launches] [num_actions]
+usage: python tools/rollout_rate.py [envs] [chunk] [launches] [num_actions] [free_running] [policy_kind]
 """
 import os
 import sys
@@ -14,11 +14,13 @@ envs = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 250
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 A = int(sys.argv[4]) if len(sys.argv) > 4 else 8
+free = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+kind = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 cfg = bench.bench_config(envs)
 env = PushEnv(config=cfg, num_envs=envs, seed=0)
 env.reset()
 w = env.world
-w.rollout_begin(A, num_episodes=1 << 20, policy_seed=1, reset_seed=2, max_attempts=2000)
+w.rollout_begin(A, num_episodes=1 << 20, policy_seed=1, reset_seed=2, max_attempts=2000, free_running=bool(free), policy_kind=kind)
 torch.cuda.synchronize()
 rates = []
 for i in range(launches):
