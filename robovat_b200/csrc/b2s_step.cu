@@ -1505,57 +1505,21 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   float* lam = S.con + SOLVE_LAM;
   int sA = 0, sB = 0, mk = 0;
   bool dA = false, dB = false;
+  // the three rows of this lane's contact (row r: dir, angA = rA x dir, iangA = I_A^-1 angA, 1/d, d, k1 = dir . vB,
+  // k2 = angB . wB) and its scalars
+  V3 rdir[3], rangA[3], riangA[3];
+  float rinvd[3], rd[3], rk1[3], rk2[3], rl[3];
+  float imA = 0.0f, imB = 0.0f, bias0 = 0.0f, mu = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { rdir[r] = rangA[r] = riangA[r] = v3(0, 0, 0); rinvd[r] = rd[r] = rk1[r] = rk2[r] = rl[r] = 0.0f; }
   __syncwarp();
   if (act) {
     mk = S.cmk[lane];
-    const int m = mk >> 2, k = mk & 3;
-    const int key = W.man_keys[nbase + m];
+    const int key = W.man_keys[nbase + (mk >> 2)];
     const int a = key >> 16, b = key & 0xffff;
     sA = __float_as_int(S.col[a * COL_STRIDE + CO_SLOT]); sB = __float_as_int(S.col[b * COL_STRIDE + CO_SLOT]);
-    const float* bA = S.body + sA * BODY_STRIDE;
-    const float* bB = S.body + sB * BODY_STRIDE;
-    const float* p = W.man_pts + ((nbase + m) * 4 + k) * B2S_CP_FLOATS;
-    V3 posA = LD3(bA + BO_POS), posB = LD3(bB + BO_POS);
-    V3 wA = posA + mmul(ldm3(bA + BO_R), v3(p[0], p[1], p[2]));
-    V3 wB = posB + mmul(ldm3(bB + BO_R), v3(p[3], p[4], p[5]));
-    V3 n = v3(p[6], p[7], p[8]);
-    V3 rA = wA - posA, rB = wB - posB;
-    V3 t1, t2;
-    plane_space(n, &t1, &t2);
-    const V3 velB = LD3(bB + BO_VEL), angvB = LD3(bB + BO_ANG);
-    if (P.friction_dirs == 1) {
-      V3 rel = (LD3(bA + BO_VEL) + cross(LD3(bA + BO_ANG), rA)) - (velB + cross(angvB, rB));
-      V3 lat = rel - n * dot(rel, n);
-      float l2 = len2(lat);
-      if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
-    }
-    const float imA = bA[BO_INVM], imB = bB[BO_INVM];
-    dA = __float_as_int(bA[BO_TYPE]) == B2S_TYPE_DYNAMIC; dB = __float_as_int(bB[BO_TYPE]) == B2S_TYPE_DYNAMIC;
-    const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
-    float4* rec = (float4*)(rr + lane * RR_WORDS);
-    float* recb = rr + lane * RR_WORDS + RR_B;
-    const float pen = p[9] + P.linear_slop;
-    const float bias0 = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
-    const float mu = bA[BO_FRIC] * bB[BO_FRIC];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
-      const V3 angA = cross(rA, dir), angB = cross(rB, dir);
-      const V3 iangA = mmul(iA, angA), iangB = mmul(iB, angB);
-      const float d = ((imA + imB) + dot(iangA, angA)) + dot(iangB, angB);
-      const float inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
-      float l0 = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
-      if (r >= nrows) l0 = 0.0f;
-      lam[r * 32 + lane] = l0;
-      rec[r * 4 + 0] = make_float4(dir.x, dir.y, dir.z, angA.x);
-      rec[r * 4 + 1] = make_float4(angA.y, angA.z, iangA.x, iangA.y);
-      rec[r * 4 + 2] = make_float4(iangA.z, inv_d, d, dot(dir, velB));
-      rec[r * 4 + 3] = make_float4(dot(angB, angvB), imA, (r == 0) ? bias0 : mu, imB);
-      if (dB) {
-        recb[r * 6 + 0] = angB.x; recb[r * 6 + 1] = angB.y; recb[r * 6 + 2] = angB.z;
-        recb[r * 6 + 3] = iangB.x; recb[r * 6 + 4] = iangB.y; recb[r * 6 + 5] = iangB.z;
-      }
-    }
+    dA = __float_as_int(S.body[sA * BODY_STRIDE + BO_TYPE]) == B2S_TYPE_DYNAMIC;
+    dB = __float_as_int(S.body[sB * BODY_STRIDE + BO_TYPE]) == B2S_TYPE_DYNAMIC;
   }
   PROF_SEC(0)
   // greedy colouring in contact order; lane s keeps the colour mask of body slot s
@@ -1586,11 +1550,179 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   unsigned long long coupled = 0ull;
   for (int k = 0; k < ncolours; ++k)
     if (__any_sync(FULL, act && mycol == k && dA && dB)) coupled |= 1ull << k;
+  if (act && dB && !dA) W.error_flags[e] |= 64;   // cannot happen: movable colliders are numbered last
   __syncwarp();
-  // ---- sweeps: lane = body slot
-  const float* myb = S.body + (lane < W.NB ? lane : 0) * BODY_STRIDE;
-  const bool dyn = lane < W.NB && __float_as_int(myb[BO_TYPE]) == B2S_TYPE_DYNAMIC;
-  V3 vel = LD3(myb + BO_VEL), ang = LD3(myb + BO_ANG);
+  // rows of this lane's contact (after the colouring, which only needs the body slots: fewer live registers there)
+  if (act) {
+    const int m = mk >> 2, k = mk & 3;
+    const float* bA = S.body + sA * BODY_STRIDE;
+    const float* bB = S.body + sB * BODY_STRIDE;
+    const float* p = W.man_pts + ((nbase + m) * 4 + k) * B2S_CP_FLOATS;
+    V3 posA = LD3(bA + BO_POS), posB = LD3(bB + BO_POS);
+    V3 wA = posA + mmul(ldm3(bA + BO_R), v3(p[0], p[1], p[2]));
+    V3 wB = posB + mmul(ldm3(bB + BO_R), v3(p[3], p[4], p[5]));
+    V3 n = v3(p[6], p[7], p[8]);
+    V3 rA = wA - posA, rB = wB - posB;
+    V3 t1, t2;
+    plane_space(n, &t1, &t2);
+    const V3 velB = LD3(bB + BO_VEL), angvB = LD3(bB + BO_ANG);
+    if (P.friction_dirs == 1) {
+      V3 rel = (LD3(bA + BO_VEL) + cross(LD3(bA + BO_ANG), rA)) - (velB + cross(angvB, rB));
+      V3 lat = rel - n * dot(rel, n);
+      float l2 = len2(lat);
+      if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
+    }
+    imA = bA[BO_INVM]; imB = bB[BO_INVM];
+    const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
+    const float pen = p[9] + P.linear_slop;
+    bias0 = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
+    mu = bA[BO_FRIC] * bB[BO_FRIC];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const V3 dir = (r == 0) ? n : (r == 1 ? t1 : t2);
+      const V3 angA = cross(rA, dir), angB = cross(rB, dir);
+      const V3 iangA = mmul(iA, angA), iangB = mmul(iB, angB);
+      const float d = ((imA + imB) + dot(iangA, angA)) + dot(iangB, angB);
+      const float inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
+      float l0 = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
+      if (r >= nrows) l0 = 0.0f;
+      rdir[r] = dir; rangA[r] = angA; riangA[r] = iangA; rinvd[r] = inv_d; rd[r] = d;
+      rk1[r] = dot(dir, velB); rk2[r] = dot(angB, angvB); rl[r] = l0;
+      if (coupled != 0ull && dB) {
+        float* recb = rr + lane * RR_WORDS + RR_B;
+        recb[r * 6 + 0] = angB.x; recb[r * 6 + 1] = angB.y; recb[r * 6 + 2] = angB.z;
+        recb[r * 6 + 3] = iangB.x; recb[r * 6 + 4] = iangB.y; recb[r * 6 + 5] = iangB.z;
+      }
+    }
+  }
+  __syncwarp();     // the contact lanes rejoin the others here: the sweeps below are warp-synchronous (shuffles in every
+                    // colour step), and a warp that enters them split pays the divergent-shuffle path on every one
+  PROF_SEC(1)
+  float maxres = 0.0f;
+  int iters = 0;
+  if (coupled == 0ull) {
+    // ---- the rule: no contact joins two dynamic bodies.  The sweeps stay on the CONTACT lanes: the rows never leave
+    // the registers they were built in, and every lane carries a copy of the velocity of its (dynamic) body A.  In
+    // colour step k the lanes whose contact has colour k update their rows -- at most one contact per body, that is
+    // what a colour is -- and then every lane takes the velocity of its body from the lane that just changed it
+    // (T[k][body]: one byte load and six shuffles).  Per body the row updates happen in colour order with the
+    // oracle's IEEE operations on the same operands as before, so the results are bit-identical; per row there is no
+    // load, no address arithmetic and no table walk left, which is what the latency of a 50-iteration solve -- the
+    // thing a block's solve stage waits for -- was made of.
+    const bool mine = act && dA && mycol >= 0;
+    const float* myb = S.body + sA * BODY_STRIDE;
+    V3 vel = LD3(myb + BO_VEL), ang = LD3(myb + BO_ANG);
+    const unsigned char* Tm = T + sA;
+    // Every colour step is branch-free: all lanes compute the update of "their" row, the lanes whose contact is not of
+    // colour k discard it with selects (a divergent branch per step cost more than the arithmetic it skipped), and the
+    // byte of T that names the exchange partner is loaded before the arithmetic, so its latency hides behind it.
+#define XCHG_SRC(k) const unsigned t_ = (act && dA) ? (unsigned)Tm[(k) * 32] : 0xffu; const int src_ = (t_ != 0xffu) ? (int)(t_ & 31u) : lane;
+#define XCHG()                                                                                                    \
+    {                                                                                                             \
+      vel.x = __shfl_sync(FULL, vel.x, src_); vel.y = __shfl_sync(FULL, vel.y, src_); vel.z = __shfl_sync(FULL, vel.z, src_); \
+      ang.x = __shfl_sync(FULL, ang.x, src_); ang.y = __shfl_sync(FULL, ang.y, src_); ang.z = __shfl_sync(FULL, ang.z, src_); \
+    }
+#define KEEP(on, nv, na) { vel.x = (on) ? (nv).x : vel.x; vel.y = (on) ? (nv).y : vel.y; vel.z = (on) ? (nv).z : vel.z; \
+                           ang.x = (on) ? (na).x : ang.x; ang.y = (on) ? (na).y : ang.y; ang.z = (on) ? (na).z : ang.z; }
+    // one row update on (v, w) -> (v, w), lambda and the residual in temporaries
+#define ROW(r, BIAS, LO, HI, v, w, lnew, res2)                                                                    \
+      {                                                                                                           \
+        const float jv = ((dot(rdir[r], v) + dot(rangA[r], w)) - rk1[r]) - rk2[r];                                \
+        float dl = ((BIAS) - jv) * rinvd[r];                                                                      \
+        float nl = rl[r] + dl;                                                                                    \
+        nl = fminf((HI), fmaxf((LO), nl));                                                                        \
+        dl = nl - rl[r];                                                                                          \
+        lnew = nl;                                                                                                \
+        const float res = dl * rd[r];                                                                             \
+        res2 = res * res;                                                                                         \
+        v = vmad(v, rdir[r], imA * dl); w = vmad(w, riangA[r], dl);                                               \
+      }
+    // warm start
+#pragma unroll 1
+    for (int k = 0; k < ncolours; ++k) {
+      XCHG_SRC(k)
+      const bool on = mine && mycol == k;
+      V3 v = vel, w = ang;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        if (r < nrows) { v = vmad(v, rdir[r], imA * rl[r]); w = vmad(w, riangA[r], rl[r]); }
+      KEEP(on, v, w)
+      XCHG()
+    }
+    for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
+      maxres = 0.0f;
+#pragma unroll 1
+      for (int k = 0; k < ncolours; ++k) {                 // normal rows
+        XCHG_SRC(k)
+        const bool on = mine && mycol == k;
+        V3 v = vel, w = ang;
+        float l0n, r0;
+        {
+          const float jv = ((dot(rdir[0], v) + dot(rangA[0], w)) - rk1[0]) - rk2[0];
+          float dl = (bias0 - jv) * rinvd[0];
+          float nl = rl[0] + dl;
+          nl = fmaxf(0.0f, nl);
+          dl = nl - rl[0];
+          l0n = nl;
+          const float res = dl * rd[0];
+          r0 = res * res;
+          v = vmad(v, rdir[0], imA * dl); w = vmad(w, riangA[0], dl);
+        }
+        rl[0] = on ? l0n : rl[0];
+        maxres = on ? fmaxf(maxres, r0) : maxres;
+        KEEP(on, v, w)
+        XCHG()
+      }
+#pragma unroll 1
+      for (int k = 0; k < ncolours; ++k) {                 // friction rows
+        XCHG_SRC(k)
+        const bool on = mine && mycol == k;
+        const float lim = mu * rl[0];
+        V3 v = vel, w = ang;
+        float l1n, r1, l2n = rl[2], r2 = 0.0f;
+        ROW(1, 0.0f, -lim, lim, v, w, l1n, r1)
+        if (nrows > 2) ROW(2, 0.0f, -lim, lim, v, w, l2n, r2)
+        rl[1] = on ? l1n : rl[1]; rl[2] = on ? l2n : rl[2];
+        maxres = on ? fmaxf(fmaxf(maxres, r1), r2) : maxres;
+        KEEP(on, v, w)
+        XCHG()
+      }
+      iters = it + 1;
+      unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
+      if (__uint_as_float(mx) <= P.residual_threshold) break;
+    }
+#undef KEEP
+#undef XCHG_SRC
+#undef ROW
+#undef XCHG
+    PROF_SEC(2)
+    if (act && dA) {
+      float* wb = S.body + sA * BODY_STRIDE;           // every lane of a body holds the same final velocity
+      ST3(wb + BO_VEL, vel); ST3(wb + BO_ANG, ang);
+    }
+    __syncwarp();
+    if (act) {
+      float* p = W.man_pts + ((nbase + (mk >> 2)) * 4 + (mk & 3)) * B2S_CP_FLOATS;
+      p[10] = rl[0]; p[11] = rl[1]; p[12] = rl[2];
+    }
+  } else {
+    // ---- general case (movables touching each other): rows parked in the per-warp record array, sweeps one BODY
+    // per lane, coupled colours exchange velocities between the two lanes of a contact
+    if (act) {
+      float4* rec = (float4*)(rr + lane * RR_WORDS);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        lam[r * 32 + lane] = rl[r];
+        rec[r * 4 + 0] = make_float4(rdir[r].x, rdir[r].y, rdir[r].z, rangA[r].x);
+        rec[r * 4 + 1] = make_float4(rangA[r].y, rangA[r].z, riangA[r].x, riangA[r].y);
+        rec[r * 4 + 2] = make_float4(riangA[r].z, rinvd[r], rd[r], rk1[r]);
+        rec[r * 4 + 3] = make_float4(rk2[r], imA, (r == 0) ? bias0 : mu, imB);
+      }
+    }
+    __syncwarp();
+    const float* myb = S.body + (lane < W.NB ? lane : 0) * BODY_STRIDE;
+    const bool dyn = lane < W.NB && __float_as_int(myb[BO_TYPE]) == B2S_TYPE_DYNAMIC;
+    V3 vel = LD3(myb + BO_VEL), ang = LD3(myb + BO_ANG);
   // one row update of the contact this lane meets in colour k; pass 0: warm start, 1: normal row, 2: friction rows.
   // STEP_FAST: no contact of the colour joins two dynamic bodies (warp uniform) -- every lane is the A side.
 #define STEP_FAST(PASS)                                                                                           \
@@ -1626,7 +1758,6 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   if (act) {
     lam[192 + lane] = __int_as_float(sA); lam[224 + lane] = __int_as_float(sB);
     lam[96 + lane] = lam[lane]; lam[128 + lane] = lam[32 + lane]; lam[160 + lane] = lam[64 + lane];
-    if (dB && !dA) W.error_flags[e] |= 64;   // cannot happen: movable colliders are numbered last
   }
   __syncwarp();
   // STEP_SLOW: the colour holds a contact between two dynamic bodies (rare: movables touching each other).  Its
@@ -1688,9 +1819,6 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   // Two instances of the sweep: environments without a coupled colour (the rule) run loops that contain the
   // fast step only -- ~200 instructions that stay in the L0 instruction cache for up to 50 iterations -- the
   // others run the general loops.
-  PROF_SEC(1)
-  float maxres = 0.0f;
-  int iters = 0;
 #define SWEEP(GENERAL)                                                                                            \
   {                                                                                                               \
     _Pragma("unroll 1")                                                                                           \
@@ -1709,19 +1837,20 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       if (__uint_as_float(mx) <= P.residual_threshold) break;                                                     \
     }                                                                                                             \
   }
-  if (coupled == 0ull) SWEEP(false) else SWEEP(true)
-  PROF_SEC(2)
+    SWEEP(true)
+    PROF_SEC(2)
 #undef SWEEP
 #undef STEP_FAST
 #undef STEP_SLOW
-  if (dyn) {
-    float* wb = S.body + lane * BODY_STRIDE;
-    ST3(wb + BO_VEL, vel); ST3(wb + BO_ANG, ang);
-  }
-  __syncwarp();
-  if (act) {
-    float* p = W.man_pts + ((nbase + (mk >> 2)) * 4 + (mk & 3)) * B2S_CP_FLOATS;
-    p[10] = lam[lane]; p[11] = lam[32 + lane]; p[12] = lam[64 + lane];
+    if (dyn) {
+      float* wb = S.body + lane * BODY_STRIDE;
+      ST3(wb + BO_VEL, vel); ST3(wb + BO_ANG, ang);
+    }
+    __syncwarp();
+    if (act) {
+      float* p = W.man_pts + ((nbase + (mk >> 2)) * 4 + (mk & 3)) * B2S_CP_FLOATS;
+      p[10] = lam[lane]; p[11] = lam[32 + lane]; p[12] = lam[64 + lane];
+    }
   }
   if (lane == 0) {
     int32_t* st = W.solver_stats + (size_t)e * 4;
