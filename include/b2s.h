@@ -98,7 +98,10 @@ typedef struct B2SParams {
   int32_t envs_per_block;          /* environment slots per block of the substep kernel; 0 = derived from num_envs and the SM count */
   int32_t export_debug;            /* 1: every substep also writes the inspection arrays (B2S_ARR_PAIR_KEYS, LINK_POSES, LINK_VEL);
                                       0 (product default): they are only refreshed by the calls that need them */
-  int32_t reserved_i[2];
+  int32_t num_goal_steps;          /* NUM_GOAL_STEPS (push_env.py:259-262, 803-806): 0 = None: one (start, motion) pair per action;
+                                      G >= 1: an action is [G][4] and the arm goes post -> pre G times before it leaves */
+  int32_t use_crop;                /* 1: SegmentedPointCloudObs keeps only points inside [crop_min, crop_max] (OBS.CROP_MIN/MAX,
+                                      camera_obs.py:187-193) */
 
   double time_step;                /* dt; reference default 1e-3 (simulator.py:26) */
   float gravity[3];                /* (0,0,-9.8) simulator.py:27 */
@@ -130,7 +133,8 @@ typedef struct B2SParams {
   float table_workspace_low[2], table_workspace_high[2];   /* push_env.py:85-90 */
   /* camera (bullet_camera.py:17-19) */
   float cam_near, cam_far;
-  float reserved_f[8];
+  float crop_min[3], crop_max[3];  /* world frame, metres */
+  float reserved_f[2];
 } B2SParams;
 
 /* Scene description: host pointers, copied to the device by b2s_load_scene.
@@ -195,7 +199,7 @@ typedef struct B2SSceneDesc {
 typedef struct B2SBuffers {
   float* body_state;       /* [13][B][Nmax]  px py pz qx qy qz qw vx vy vz wx wy wz of the movables */
   float* joint_state;      /* [2][7][B]      q, qdot of the limb */
-  float* action;           /* [B][4]         PushEnv action in [-1,1] */
+  float* action;           /* [B][G][4]      PushEnv action in [-1,1] (G = max(1, params.num_goal_steps)) */
   float* obs_position;     /* [B][Nmax][3]   PoseObs 'position' (pose_obs.py:53-73), zero padded */
   int32_t* num_movables;   /* [B] */
   uint8_t* body_mask;      /* [B][Nmax]      movable_body_mask (push_env.py:363-365) */
@@ -229,7 +233,7 @@ enum {
                                   bit3 contact overflow, bit4 colour overflow, bit5 collider overflow, bit6 solver invariant,
                                   bit7 reset found no placement with the MARGIN clearance (re-sample the env),
                                   bit8 a rollout's reset found no valid scene in max_reset_retries re-samples (the env stops) */
-  B2S_ARR_WAYPOINTS = 14,      /* float [B][2][7] start / end gripper poses */
+  B2S_ARR_WAYPOINTS = 14,      /* float [B][G][2][7] start / end gripper poses of every goal step */
   B2S_ARR_STATUS = 15,         /* float [B][2][Nmax][4] start/end status: pos3 + yaw (push_env.py:925-937) */
   B2S_ARR_CONTACT_FLAGS = 16,  /* int32 [B] bit0 arm-table, bit1 arm-movable, per last substep */
   B2S_ARR_PHASE_STATE = 17,    /* int32 [B][8] max_phase_steps, num_waypoints, settle_steps, stable_steps, ... */

@@ -85,7 +85,8 @@ int b2o_load_scene(World* w, const B2SSceneDesc* d) {
   const B2SParams& P = w->P;
   w->body_state.assign((size_t)13 * B * N, 0.0f);
   w->joint_state.assign((size_t)2 * 7 * B, 0.0f);
-  w->action.assign((size_t)B * 4, 0.0f);
+  const int G = P.num_goal_steps > 0 ? P.num_goal_steps : 1;
+  w->action.assign((size_t)B * G * 4, 0.0f);
   w->obs_position.assign((size_t)B * N * 3, 0.0f);
   w->num_movables.assign(B, 0); w->body_mask.assign((size_t)B * N, 0);
   w->depth.assign((size_t)B * P.cam_height * P.cam_width, 0.0f);
@@ -102,7 +103,7 @@ int b2o_load_scene(World* w, const B2SSceneDesc* d) {
   w->link_poses.assign((size_t)B * (w->L + 1) * 7, 0.0f); w->link_vel.assign((size_t)B * w->L * 6, 0.0f);
   w->mov_params.assign((size_t)4 * B * N, 0.0f);
   w->table_dz.assign(B, 0.0f); w->error_flags.assign(B, 0);
-  w->waypoints.assign((size_t)B * 14, 0.0f); w->status.assign((size_t)B * 2 * N * 4, 0.0f);
+  w->waypoints.assign((size_t)B * G * 14, 0.0f); w->status.assign((size_t)B * 2 * N * 4, 0.0f);
   w->contact_flags.assign(B, 0); w->phase_state.assign((size_t)B * 8, 0); w->solver_stats.assign((size_t)B * 4, 0);
   for (int e = 0; e < B; ++e) w->phase_state[(size_t)e * 8] = -1;
   w->ncol.assign(B, 0); w->col_slot.assign((size_t)B * w->Hmax, 0); w->col_hull.assign((size_t)B * w->Hmax, 0);

@@ -158,18 +158,21 @@ static void movable_status(World& w, int e, int which) {
 
 void set_action(World& w, int e) {
   const B2SParams& P = w.P;
-  const float* a = &w.action[(size_t)e * 4];
+  const int G = P.num_goal_steps > 0 ? P.num_goal_steps : 1;
   float off[3], rng[3];
   for (int k = 0; k < 3; ++k) { off[k] = 0.5f * (P.cspace_high[k] + P.cspace_low[k]); rng[k] = 0.5f * (P.cspace_high[k] - P.cspace_low[k]); }
-  /* PushEnv._compute_waypoints (push_env.py:752-786) */
-  float x = a[0] * rng[0] + off[0], y = a[1] * rng[1] + off[1];
-  float z = P.finger_tip_offset + off[2];
-  float x2 = fminf(P.cspace_high[0], fmaxf(P.cspace_low[0], x + a[2] * P.translation_x));
-  float y2 = fminf(P.cspace_high[1], fmaxf(P.cspace_low[1], y + a[3] * P.translation_y));
-  Q4 down = q_from_euler(B2S_PI, 0.0f, 0.0f);
-  float* wp = &w.waypoints[(size_t)e * 14];
-  wp[0] = x; wp[1] = y; wp[2] = z; wp[3] = down.x; wp[4] = down.y; wp[5] = down.z; wp[6] = down.w;
-  wp[7] = x2; wp[8] = y2; wp[9] = z; wp[10] = down.x; wp[11] = down.y; wp[12] = down.z; wp[13] = down.w;
+  const Q4 down = q_from_euler(B2S_PI, 0.0f, 0.0f);
+  for (int g = 0; g < G; ++g) {
+    /* PushEnv._compute_all_waypoints / _compute_waypoints (push_env.py:735-786) */
+    const float* a = &w.action[((size_t)e * G + g) * 4];
+    float x = a[0] * rng[0] + off[0], y = a[1] * rng[1] + off[1];
+    float z = P.finger_tip_offset + off[2];
+    float x2 = fminf(P.cspace_high[0], fmaxf(P.cspace_low[0], x + a[2] * P.translation_x));
+    float y2 = fminf(P.cspace_high[1], fmaxf(P.cspace_low[1], y + a[3] * P.translation_y));
+    float* wp = &w.waypoints[((size_t)e * G + g) * 14];
+    wp[0] = x; wp[1] = y; wp[2] = z; wp[3] = down.x; wp[4] = down.y; wp[5] = down.z; wp[6] = down.w;
+    wp[7] = x2; wp[8] = y2; wp[9] = z; wp[10] = down.x; wp[11] = down.y; wp[12] = down.z; wp[13] = down.w;
+  }
   w.is_safe[e] = 1; w.is_effective[e] = 1;
   w.phase[e] = B2S_PHASE_INITIAL;
   int32_t* ps = &w.phase_state[(size_t)e * 8];
@@ -198,11 +201,13 @@ static void phase_logic(World& w, int e) {
     memcpy(ee, lp + w.L * 7, sizeof(float) * 7);
   }
   if (ready) {
-    /* _get_next_phase (push_env.py:788-810), NUM_GOAL_STEPS = None */
+    /* _get_next_phase (push_env.py:788-810) */
     if (interrupt && ph != B2S_PHASE_POST && ph != B2S_PHASE_OFFSTAGE && ph != B2S_PHASE_DONE) ph = B2S_PHASE_POST;
+    else if (ph == B2S_PHASE_POST && P.num_goal_steps > 0 && ps[1] < P.num_goal_steps) ph = B2S_PHASE_PRE;
     else ph = ph + 1;
     ps[0] = nsteps + (ph == B2S_PHASE_MOTION ? P.max_motion_steps : ph == B2S_PHASE_OFFSTAGE ? P.max_offstage_steps : P.max_phase_steps);
-    const float* wp = &w.waypoints[(size_t)e * 14];
+    const int G = P.num_goal_steps > 0 ? P.num_goal_steps : 1;
+    const float* wp = &w.waypoints[((size_t)e * G + (ps[1] < G - 1 ? ps[1] : G - 1)) * 14];    /* waypoints[num_waypoints] */
     float pose[7];
     if (ph == B2S_PHASE_PRE) { memcpy(pose, wp, sizeof(float) * 7); pose[2] = P.gripper_safe_height; arm_reset_targets(w, e); arm_set_link_target(w, e, pose); }
     else if (ph == B2S_PHASE_START) { arm_reset_targets(w, e); arm_set_link_target(w, e, wp); }

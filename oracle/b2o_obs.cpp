@@ -137,7 +137,19 @@ void point_cloud(World& w, int e, uint64_t seed) {
     if (i >= w.num_movables[e]) continue;
     const int uid = body_uid(w, e, w.Ns + w.L + i) & 255;
     std::vector<int> idx;
-    for (int k = 0; k < H * Wd; ++k) if (seg[k] == uid) idx.push_back(k);
+    for (int k = 0; k < H * Wd; ++k) {
+      if (seg[k] != uid) continue;
+      if (P.use_crop) {                                /* OBS.CROP_MIN / CROP_MAX on the world-frame cloud (camera_obs.py:187-193) */
+        const int v = k / Wd, u = k % Wd;
+        const float z = depth[k];
+        const float dy = ((float)v - cy) / fy;
+        const float dx = (((float)u - cx) - sk * dy) / fx;
+        const V3 x = mtmul(R, v3(dx * z, dy * z, z) - t);
+        if (!(x.x >= P.crop_min[0] && x.y >= P.crop_min[1] && x.z >= P.crop_min[2] &&
+              x.x <= P.crop_max[0] && x.y <= P.crop_max[1] && x.z <= P.crop_max[2])) continue;
+      }
+      idx.push_back(k);
+    }
     const int n = (int)idx.size();
     if (n == 0) continue;
     /* np.random.choice(n, P, replace = n < P) (perception/point_cloud_utils.py:23-39): Philox stream 3 */

@@ -149,6 +149,31 @@ def gen_camera(rs):
     }
 
 
+def gen_calibration():
+    """ArmEnv._reset_camera (arm_env.py:109-152) of the unmodified reference with a recording camera stub."""
+    from robovat.envs import arm_env
+
+    class Cam(object):
+        def set_calibration(self, intrinsics, translation, rotation):
+            self.got = (intrinsics, translation, rotation)
+
+    class Self(object):
+        is_simulation = True
+    out = []
+    K = [365.0, 0, 256.0, 0, 365.0, 212.0, 0, 0, 1]
+    for seed, (kn, tn, rn) in enumerate([(None, None, None), ([2.0, 0, 2.0, 0, 2.0, 2.0, 0, 0, 0], [0.01, 0.02, 0.03], [0.05, 0.05, 0.1]),
+                                         (None, [0.02, 0.02, 0.02], None), ([1.0] * 9, None, [0.01, 0.0, 0.02])]):
+        np.random.seed(100 + seed)
+        cam = Cam()
+        arm_env.ArmEnv._reset_camera(Self(), cam, np.array(K).reshape(3, 3), [0.6, 0.0, 1.2], [np.pi, 0, 0],
+                                     None if kn is None else np.array(kn).reshape(3, 3), tn, rn)
+        out.append({'seed': 100 + seed, 'intrinsics': K, 'translation': [0.6, 0.0, 1.2], 'rotation': [float(np.pi), 0, 0],
+                    'intrinsics_noise': kn, 'translation_noise': tn, 'rotation_noise': rn,
+                    'got_intrinsics': _tolist(np.asarray(cam.got[0], np.float64)), 'got_translation': _tolist(np.asarray(cam.got[1], np.float64)),
+                    'got_rotation': _tolist(np.asarray(cam.got[2], np.float64))})
+    return out
+
+
 def gen_cosim(cfg_bindings, seed, action_fn, name):
     """Reference-driven PushEnv.step on our backend; returns the arrays of one trace."""
     from oracle import ref_cosim
@@ -176,7 +201,7 @@ def gen_cosim(cfg_bindings, seed, action_fn, name):
         log.append((int(env.simulator.num_steps), env.phase_list.index(ph)))
         return ph
     env._get_next_phase = logged_next
-    waypoints = env._compute_waypoints(action)
+    waypoints = env._compute_waypoints(action if np.ndim(action) == 1 else action[0])     # of the first goal step
     obs2, reward, done, _ = env.step(action)
     final = snapshot(world)
     out = {'action': np.asarray(action, np.float32), 'phase_log': np.asarray(log, np.int32),
@@ -196,6 +221,13 @@ def gen_cosim(cfg_bindings, seed, action_fn, name):
         name, int(final['arr%d' % _capi.ARR_NUM_STEPS][0] - start['arr%d' % _capi.ARR_NUM_STEPS][0]),
         [p for _, p in log], out['is_safe'], out['is_effective']))
     return out
+
+
+def push_twice(first, second):
+    """NUM_GOAL_STEPS = 2: action [2, 4], both pushes aimed at body 0's position at the start of the action."""
+    def fn(position, cfg):
+        return np.stack([first(position, cfg), second(position, cfg)])
+    return fn
 
 
 def push_body0(dx, dy):
@@ -369,7 +401,8 @@ def main():
     for name, bindings, seed, fn in (
             ('push_x', {}, 3, push_body0(1.0, 0.0)),
             ('push_diag', {}, 5, push_body0(-0.7, 0.7)),
-            ('push_240hz', {'SIM_TIME_STEP': 1.0 / 240.0}, 7, push_body0(0.0, -1.0))):
+            ('push_240hz', {'SIM_TIME_STEP': 1.0 / 240.0}, 7, push_body0(0.0, -1.0)),
+            ('push_two_goals', {'NUM_GOAL_STEPS': 2}, 11, push_twice(push_body0(1.0, 0.0), push_body0(0.0, 1.0)))):
         b = dict(bindings)
         if 'SIM_TIME_STEP' in b:
             from robovat_b200 import config
@@ -382,6 +415,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'push_step_trace.npz'), **traces)
     print('wrote push_step_trace.npz (%d arrays)' % len(traces))
     dump('camera.json', gen_camera(rs))
+    dump('calibration.json', gen_calibration())
 
 
 if __name__ == '__main__':

@@ -51,7 +51,7 @@ class B2SParams(C.Structure):
         ('stable_check_after', i32), ('stable_min_steps', i32), ('stable_max_steps', i32),
         ('clamp_joint_velocity', i32), ('cam_height', i32), ('cam_width', i32),
         ('num_points', i32), ('task', i32), ('max_contacts', i32), ('max_colliders', i32),
-        ('warps_per_block', i32), ('envs_per_block', i32), ('export_debug', i32), ('reserved_i', i32 * 2),
+        ('warps_per_block', i32), ('envs_per_block', i32), ('export_debug', i32), ('num_goal_steps', i32), ('use_crop', i32),
         ('time_step', f64), ('gravity', f32 * 3), ('erp2', f32), ('linear_slop', f32),
         ('warmstart', f32), ('residual_threshold', f32), ('linear_damping', f32),
         ('angular_damping', f32), ('breaking_factor', f32), ('ik_damping', f32),
@@ -63,7 +63,7 @@ class B2SParams(C.Structure):
         ('gripper_safe_height', f32), ('offstage_positions', f32 * NUM_JOINTS),
         ('min_delta_position', f32), ('min_delta_angle', f32),
         ('table_workspace_low', f32 * 2), ('table_workspace_high', f32 * 2),
-        ('cam_near', f32), ('cam_far', f32), ('reserved_f', f32 * 8),
+        ('cam_near', f32), ('cam_far', f32), ('crop_min', f32 * 3), ('crop_max', f32 * 3), ('reserved_f', f32 * 2),
     ]
 
 

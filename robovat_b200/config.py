@@ -97,7 +97,9 @@ DEFAULT_PUSH_ENV = {
         # URDF origin of the table at its top surface (tiles sit at table.z + 0.001 - 0.025, push_env.py:349)
         'GROUND': {'POSE': [[0, 0, -0.9], [0, 0, 0]]},
         'TABLE': {'POSE': [[0.6, 0.0, 0.0], [0, 0, 0]], 'THICKNESS': 0.05, 'FRICTION': 1.0},
-        'WALL': {'USE': False},
+        # the reference loads SIM.WALL.PATH (a URDF of its data package, which is not in the repository): here the wall is
+        # a static box given by POSE (centre) and SIZE (full extents), or a URDF from the asset pipeline in PATH
+        'WALL': {'USE': False, 'POSE': [[1.1, 0.0, 0.25], [0, 0, 0]], 'SIZE': [0.05, 1.6, 1.4], 'PATH': None, 'FRICTION': 1.0},
         'TILE': {'HEIGHT': 0.05, 'COLLIDE': True},
         'STEPS_CHECK': 20, 'MAX_PHASE_STEPS': 3000, 'MAX_MOTION_STEPS': 4000, 'MAX_OFFSTAGE_STEPS': 4000,
     },
@@ -175,6 +177,18 @@ def build_scene(config):
                                                           (0, 0, -0.5 * th))], center_on_com=False)
     statics.append({'name': 'table', 'asset': tab, 'pose': [tx, ty, tz, 0, 0, 0, 1.0], 'friction': float(table.FRICTION),
                     'flags': _capi.STATIC_ON_TABLE | _capi.STATIC_IS_TABLE})
+    if cfg.SIM.WALL.get('USE', False):                         # ArmEnv._reset_scene (arm_env.py:93-98): third static body
+        wall = cfg.SIM.WALL
+        if wall.get('PATH'):
+            path = wall.PATH if os.path.isabs(wall.PATH) else os.path.join(assets_lib.DATA_DIR, wall.PATH)
+            hulls, _ = mesh_io.urdf_asset(path)
+            wid = lib.add_asset('wall', hulls, center_on_com=False)
+        else:
+            sx, sy, sz = [0.5 * float(v) for v in wall.SIZE]
+            wid = lib.add_asset('wall', [assets_lib.box_vertices(sx, sy, sz)], center_on_com=False)
+        wq = assets_lib.quat_from_euler(*[float(v) for v in wall.POSE[1]])
+        statics.append({'name': 'wall', 'asset': wid, 'pose': [float(v) for v in wall.POSE[0]] + [float(v) for v in wq],
+                        'friction': float(wall.get('FRICTION', 1.0)), 'flags': 0})
     layout = {}
     task = cfg.TASK_NAME
     if task not in (None, 'data_collection'):
@@ -246,6 +260,7 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     p.max_pairs = max(64, 2 * p.max_manifolds)
     p.envs_per_block = int(os.environ.get('B2S_EPB', 0))     # 0 = library default
     p.export_debug = int(os.environ.get('B2S_EXPORT_DEBUG', 0))
+    p.num_goal_steps = int(cfg.NUM_GOAL_STEPS or 0)               # push_env.py:259-262
     # <= 32 contact points keeps the solver's Jacobian rows in registers (one contact per lane)
     p.max_contacts = max(32, 8 * movable_hulls)
     p.solver_iterations, p.friction_dirs = int(phys.SOLVER_ITERATIONS), int(phys.FRICTION_DIRS)
@@ -258,6 +273,10 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     p.clamp_joint_velocity = 1 if cfg.ROBOT.CLAMP_JOINT_VELOCITY else 0
     p.cam_height, p.cam_width = int(cfg.KINECT2.DEPTH.HEIGHT), int(cfg.KINECT2.DEPTH.WIDTH)
     p.num_points = int(cfg.OBS.NUM_POINTS)
+    if cfg.OBS.CROP_MIN is not None and cfg.OBS.CROP_MAX is not None:        # camera_obs.py:143-150, 187-193
+        p.use_crop = 1
+        p.crop_min[:] = [float(x) for x in cfg.OBS.CROP_MIN]
+        p.crop_max[:] = [float(x) for x in cfg.OBS.CROP_MAX]
     p.task = _capi.TASK_IDS[cfg.TASK_NAME]
     if os.environ.get('B2S_WARPS'):
         p.warps_per_block = int(os.environ['B2S_WARPS'])           # default: what the library was built for

@@ -135,6 +135,7 @@ int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
   w->d.P = *p;
   if (w->d.P.warps_per_block == 0) w->d.P.warps_per_block = B2S_BLOCK_THREADS / 32;
   w->d.B = p->num_envs; w->d.Nmax = p->max_movables; w->d.Hmax = p->max_colliders;
+  w->d.G = p->num_goal_steps > 0 ? p->num_goal_steps : 1;
   w->device = device; w->scene_loaded = false; w->buffers_bound = false; w->launches = 0;
   w->exp_keys = nullptr; w->exp_npts = nullptr; w->exp_pts = nullptr; w->unfinished_pinned = nullptr;
   memset(w->arr_bytes, 0, sizeof(w->arr_bytes)); memset(w->arr_ptr, 0, sizeof(w->arr_ptr));
@@ -269,7 +270,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   ALLOC(ctrl, B * B2S_CTRL_FLOATS, 0); ALLOC(ctrl_flags, B * 4, 0); ALLOC(ctrl_time, B * 5, 0);
   ALLOC(link_poses, B * (d.L + 1) * 7, 0); ALLOC(link_vel, B * d.L * 6, 0);
   ALLOC(mov_params, 4 * B * N, 0); ALLOC(table_dz, B, 0); ALLOC(error_flags, B, 0);
-  ALLOC(waypoints, B * 14, 0); ALLOC(status, B * 2 * N * 4, 0);
+  ALLOC(waypoints, B * d.G * 14, 0); ALLOC(status, B * 2 * N * 4, 0);
   ALLOC(contact_flags, B, 0); ALLOC(phase_state, B * 8, 0); ALLOC(solver_stats, B * 4, 0);
   ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
   ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
@@ -354,7 +355,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   reg(B2S_ARR_CTRL, d.ctrl, B * B2S_CTRL_FLOATS * 4); reg(B2S_ARR_CTRL_FLAGS, d.ctrl_flags, B * 16);
   reg(B2S_ARR_LINK_POSES, d.link_poses, B * (d.L + 1) * 28); reg(B2S_ARR_MOV_PARAMS, d.mov_params, 4 * B * N * 4);
   reg(B2S_ARR_TABLE_DZ, d.table_dz, B * 4); reg(B2S_ARR_ERROR_FLAGS, d.error_flags, B * 4);
-  reg(B2S_ARR_WAYPOINTS, d.waypoints, B * 56); reg(B2S_ARR_STATUS, d.status, B * 2 * N * 16);
+  reg(B2S_ARR_WAYPOINTS, d.waypoints, B * d.G * 56); reg(B2S_ARR_STATUS, d.status, B * 2 * N * 16);
   reg(B2S_ARR_CONTACT_FLAGS, d.contact_flags, B * 4); reg(B2S_ARR_PHASE_STATE, d.phase_state, B * 32);
   reg(B2S_ARR_SOLVER_STATS, d.solver_stats, B * 16); reg(B2S_ARR_CTRL_TIME, d.ctrl_time, B * 40);
   reg(B2S_ARR_LINK_VEL, d.link_vel, B * d.L * 24); reg(B2S_ARR_NUM_COLLIDERS, d.ncol, B * 4);
@@ -459,6 +460,7 @@ int b2s_rollout_begin(B2SWorld* w, const B2SRollout* r, void* stream) {
   if (w->d.Nmax > 32) return fail(B2S_E_CAPACITY, "b2s_rollout_begin: max_movables > 32");
   DRollout& ro = w->d.ro;
   if (r->policy_kind != B2S_POLICY_HEURISTIC && r->policy_kind != B2S_POLICY_AIMED) return fail(B2S_E_INVALID, "b2s_rollout_begin: unknown policy_kind");
+  if (w->d.G > 1) return fail(B2S_E_UNSUPPORTED, "b2s_rollout_begin: the device policies draw one (start, motion) pair per action; NUM_GOAL_STEPS > 1 needs the host policy (b2s_env_async_step)");
   if (r->num_episodes < 1) return fail(B2S_E_INVALID, "b2s_rollout_begin: num_episodes < 1");
   if (r->max_reset_retries < 0) return fail(B2S_E_INVALID, "b2s_rollout_begin: max_reset_retries < 0");
   ro.enabled = RO_EPISODES; ro.num_actions = r->num_actions; ro.max_attempts = r->max_attempts; ro.num_episodes = r->num_episodes;

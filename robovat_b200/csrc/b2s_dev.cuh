@@ -127,6 +127,7 @@ struct SmemLayout {
 struct DWorld {
   B2SParams P;
   int B, Nmax, Ns, L, NB, Hmax;
+  int G;                 // goal steps per action: max(1, P.num_goal_steps)
   // scene (device, read-only)
   const float4* verts;
   const DHull* hulls;

@@ -154,11 +154,32 @@ __global__ void k_point_cloud(const __grid_constant__ DWorld W, uint64_t seed) {
   const uint8_t* seg = W.buf.segmask + (size_t)e * npix;
   const float* depth = W.buf.depth + (size_t)e * npix;
   int* prefix = pc_smem;                      // [nchunk + 1] exclusive prefix of matches per 32-pixel chunk
+  const float* cam = W.cam + (size_t)e * 21;
+  const float fx = cam[0], sk = cam[1], cx = cam[2], fy = cam[4], cy = cam[5];
+  M3 R; R.r0 = v3(cam[9], cam[10], cam[11]); R.r1 = v3(cam[12], cam[13], cam[14]); R.r2 = v3(cam[15], cam[16], cam[17]);
+  const V3 t = v3(cam[18], cam[19], cam[20]);
+  // Camera.deproject_depth_image for one pixel (camera.py:213-244)
+  auto deproject = [&](int pix) {
+    const int v = pix / Wd, u = pix % Wd;
+    const float z = depth[pix];
+    const float dy = ((float)v - cy) / fy;
+    const float dx = (((float)u - cx) - sk * dy) / fx;
+    return mtmul(R, v3(dx * z, dy * z, z) - t);
+  };
+  // a pixel belongs to body i if the segmentation says so and, with OBS.CROP_MIN/MAX, its point lies inside the crop box
+  // (the reference crops the whole cloud before it groups by label, camera_obs.py:187-201)
+  const bool crop = P.use_crop != 0;
+  auto match = [&](int pix) {
+    if (pix >= npix || seg[pix] != uid) return false;
+    if (!crop) return true;
+    const V3 x = deproject(pix);
+    return x.x >= P.crop_min[0] && x.y >= P.crop_min[1] && x.z >= P.crop_min[2] &&
+           x.x <= P.crop_max[0] && x.y <= P.crop_max[1] && x.z <= P.crop_max[2];
+  };
   // pass 1: chunk counts via ballot, running total kept by all lanes
   int total = 0;
   for (int c = 0; c < nchunk; ++c) {
-    int pix = c * 32 + lane;
-    bool m = pix < npix && seg[pix] == uid;
+    const bool m = match(c * 32 + lane);
     unsigned b = __ballot_sync(FULL, m);
     if (lane == 0) prefix[c] = total;
     total += __popc(b);
@@ -167,10 +188,6 @@ __global__ void k_point_cloud(const __grid_constant__ DWorld W, uint64_t seed) {
   __syncwarp();
   const int n = total;
   if (n == 0) return;
-  const float* cam = W.cam + (size_t)e * 21;
-  const float fx = cam[0], sk = cam[1], cx = cam[2], fy = cam[4], cy = cam[5];
-  M3 R; R.r0 = v3(cam[9], cam[10], cam[11]); R.r1 = v3(cam[12], cam[13], cam[14]); R.r2 = v3(cam[15], cam[16], cam[17]);
-  const V3 t = v3(cam[18], cam[19], cam[20]);
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), env = (uint32_t)(P.env_id_offset + e);
   const float u0 = b2s_u01(b2s_philox(k0, k1, 0u, 3u + 16u * (uint32_t)i, env, 0u).x);
   for (int j = lane; j < NP; j += 32) {
@@ -188,13 +205,9 @@ __global__ void k_point_cloud(const __grid_constant__ DWorld W, uint64_t seed) {
     int rem = k - prefix[lo], pix = lo * 32;
     for (int q = 0; q < 32; ++q) {
       int pp = lo * 32 + q;
-      if (pp < npix && seg[pp] == uid) { if (rem == 0) { pix = pp; break; } --rem; }
+      if (match(pp)) { if (rem == 0) { pix = pp; break; } --rem; }
     }
-    const int v = pix / Wd, u = pix % Wd;
-    const float z = depth[pix];
-    const float dy = ((float)v - cy) / fy;
-    const float dx = (((float)u - cx) - sk * dy) / fx;
-    V3 xw = mtmul(R, v3(dx * z, dy * z, z) - t);
+    const V3 xw = deproject(pix);
     o[j * 3] = xw.x; o[j * 3 + 1] = xw.y; o[j * 3 + 2] = xw.z;
   }
 }

@@ -266,17 +266,19 @@ __device__ inline float reward_eval(const DWorld& W, const float* s0, const floa
 // ---- start of an action (one thread) --------------------------------------------------------------------------
 __device__ inline void begin_action(const DWorld& W, int e) {
   const B2SParams& P = W.P;
-  const float* a = W.buf.action + (size_t)e * 4;
   float off[3], rng[3];
   for (int k = 0; k < 3; ++k) { off[k] = 0.5f * (P.cspace_high[k] + P.cspace_low[k]); rng[k] = 0.5f * (P.cspace_high[k] - P.cspace_low[k]); }
-  float x = a[0] * rng[0] + off[0], y = a[1] * rng[1] + off[1];
-  float z = P.finger_tip_offset + off[2];
-  float x2 = fminf(P.cspace_high[0], fmaxf(P.cspace_low[0], x + a[2] * P.translation_x));
-  float y2 = fminf(P.cspace_high[1], fmaxf(P.cspace_low[1], y + a[3] * P.translation_y));
-  Q4 down = q_from_euler(B2S_PI, 0.0f, 0.0f);
-  float* wp = W.waypoints + (size_t)e * 14;
-  wp[0] = x; wp[1] = y; wp[2] = z; wp[3] = down.x; wp[4] = down.y; wp[5] = down.z; wp[6] = down.w;
-  wp[7] = x2; wp[8] = y2; wp[9] = z; wp[10] = down.x; wp[11] = down.y; wp[12] = down.z; wp[13] = down.w;
+  const Q4 down = q_from_euler(B2S_PI, 0.0f, 0.0f);
+  for (int g = 0; g < W.G; ++g) {                       // _compute_all_waypoints (push_env.py:735-750)
+    const float* a = W.buf.action + ((size_t)e * W.G + g) * 4;
+    float x = a[0] * rng[0] + off[0], y = a[1] * rng[1] + off[1];
+    float z = P.finger_tip_offset + off[2];
+    float x2 = fminf(P.cspace_high[0], fmaxf(P.cspace_low[0], x + a[2] * P.translation_x));
+    float y2 = fminf(P.cspace_high[1], fmaxf(P.cspace_low[1], y + a[3] * P.translation_y));
+    float* wp = W.waypoints + ((size_t)e * W.G + g) * 14;
+    wp[0] = x; wp[1] = y; wp[2] = z; wp[3] = down.x; wp[4] = down.y; wp[5] = down.z; wp[6] = down.w;
+    wp[7] = x2; wp[8] = y2; wp[9] = z; wp[10] = down.x; wp[11] = down.y; wp[12] = down.z; wp[13] = down.w;
+  }
   W.buf.is_safe[e] = 1; W.buf.is_effective[e] = 1;
   W.phase[e] = B2S_PHASE_INITIAL;
   int32_t* ps = W.phase_state + (size_t)e * 8;

@@ -1928,9 +1928,12 @@ __device__ __noinline__ void phase_logic(int e, int lane, int wib) {
   int new_ps0 = ps0;
   if (ready) {
     if (interrupt && ph != B2S_PHASE_POST && ph != B2S_PHASE_OFFSTAGE && ph != B2S_PHASE_DONE) ph = B2S_PHASE_POST;
+    else if (ph == B2S_PHASE_POST && P.num_goal_steps > 0 && ps1 < P.num_goal_steps) ph = B2S_PHASE_PRE;   // next goal step (push_env.py:803-806)
     else ph = ph + 1;
     new_ps0 = nsteps + (ph == B2S_PHASE_MOTION ? P.max_motion_steps : ph == B2S_PHASE_OFFSTAGE ? P.max_offstage_steps : P.max_phase_steps);
-    const float* wp = W.waypoints + (size_t)e * 14;
+    // waypoints[num_waypoints]; an interrupt can take the arm to 'post' once more after the last goal step, and the
+    // reference would then index past its list in 'pre' -- which it never reaches (post -> offstage), as here
+    const float* wp = W.waypoints + ((size_t)e * W.G + min(ps1, W.G - 1)) * 14;
     float pose[7];
     if (ph == B2S_PHASE_PRE) {
 #pragma unroll

@@ -110,9 +110,8 @@ class PushEnv(object):
             from robovat_b200 import layouts
             self.layouts = layouts.TASK_NAME_TO_LAYOUTS[self.task_name]
             self.num_layouts = len(self.layouts)
-        self.num_goal_steps = cfg.NUM_GOAL_STEPS
-        if self.num_goal_steps is not None:
-            raise NotImplementedError('NUM_GOAL_STEPS (multi-waypoint actions) is not on the path yet')
+        self.num_goal_steps = cfg.NUM_GOAL_STEPS           # None: action [4]; G: action [G, 4], post -> pre G times
+        self._action_floats = 4 * max(1, int(self.num_goal_steps or 0))
         self.cspace = Box(cfg.ACTION.CSPACE.LOW, cfg.ACTION.CSPACE.HIGH)
         start_low = np.array(cfg.ACTION.CSPACE.LOW, dtype=np.float32)
         start_high = np.array(cfg.ACTION.CSPACE.HIGH, dtype=np.float32)
@@ -150,15 +149,17 @@ class PushEnv(object):
         self._obs_data = self._prev_obs_data = None
         self.substep_chunk = int(cfg.get('SUBSTEP_CHUNK', 250))
         self.max_action_substeps = int(cfg.get('MAX_ACTION_SUBSTEPS', 60000))
-        self._pinned_action = torch.zeros(B, 4, dtype=torch.float32).pin_memory()
+        self._pinned_action = torch.zeros(B, self._action_floats, dtype=torch.float32).pin_memory()
         self._observations = self._create_observations()
         for obs in self._observations:
             obs.initialize(self)
         self._reward_fns = [PushReward('reward', self.task_name, self.layout_id)]
         for fn in self._reward_fns:
             fn.initialize(self)
-        self._action_space = Box(-np.ones(4, np.float32), np.ones(4, np.float32))
+        shape = [4] if self.num_goal_steps is None else [int(self.num_goal_steps), 4]      # push_env.py:253-262
+        self._action_space = Box(-np.ones(shape, np.float32), np.ones(shape, np.float32))
         self._reset_count = 0
+        self._calibration = None
         self._async = None
 
     # -- reference properties ---------------------------------------------------------------
@@ -227,6 +228,33 @@ class PushEnv(object):
             'is_effective': w.is_effective.cpu().numpy().astype(bool),
         }
 
+    def _reset_camera(self, mask=None):
+        """ArmEnv._reset_camera (arm_env.py:109-152) for the envs being reset: calibration = configured values plus
+        uniform noise in [-NOISE, NOISE], drawn in the reference's order (intrinsics, translation, rotation).  One env
+        draws from the global numpy generator exactly like the reference; a batch draws per env from a generator
+        seeded by (seed, reset count, global env id)."""
+        from robovat_b200.simulation.camera import draw_calibration
+        cam_cfg = self._config.KINECT2.DEPTH
+        B = self.num_envs
+        noises = (cam_cfg.get('INTRINSICS_NOISE'), cam_cfg.get('TRANSLATION_NOISE'), cam_cfg.get('ROTATION_NOISE'))
+        if all(n is None for n in noises):
+            return
+        K0 = np.array(cam_cfg.INTRINSICS, np.float32).reshape(3, 3)
+        if noises[0] is not None:
+            noises = (np.array(noises[0], np.float64).reshape(3, 3),) + noises[1:]
+        if self._calibration is None:
+            self._calibration = [np.tile(K0, (B, 1, 1)), np.tile(np.array(cam_cfg.TRANSLATION, np.float32), (B, 1)),
+                                 np.tile(np.array(cam_cfg.ROTATION, np.float32).reshape(1, -1), (B, 1))]
+        m = np.ones(B, bool) if mask is None else np.asarray(mask, bool)
+        offset = int(self.world.params.env_id_offset)
+        for e in np.nonzero(m)[0]:
+            rs = np.random if B == 1 else np.random.RandomState((self.seed * 1000003 + self._reset_count * 7919 + offset + int(e)) % (1 << 32))
+            vals = draw_calibration(K0, cam_cfg.TRANSLATION, cam_cfg.ROTATION, noises[0], noises[1], noises[2], rs=rs)
+            for dst, v in zip(self._calibration, vals):
+                dst[e] = v
+        K, t, r = self._calibration
+        self.camera.set_calibration(K if B > 1 else K[0], t if B > 1 else t[0], r if B > 1 else r[0])
+
     # -- gym API (robot_env.py:202-310) -------------------------------------------------------
     def reset(self, mask=None):
         """Reset every env (or the envs in `mask`): new scene, movables dropped and settled."""
@@ -238,6 +266,9 @@ class PushEnv(object):
         if self._config.MAX_STEPS is not None and self._config.MAX_STEPS == 0:
             self._done[m] = True
         self._simulator.reset_scene(seed=self.seed, mask=None if mask is None else m)
+        self._reset_count += 1
+        if self.camera is not None:
+            self._reset_camera(None if mask is None else m)
         self._async = None
         self._refresh_attributes()
         self._obs_data = self._prev_obs_data = None
@@ -281,9 +312,10 @@ class PushEnv(object):
 
     def _execute_action(self, action):
         """push_env.py:631-733: the whole loop runs on the device."""
-        a = np.asarray(action, dtype=np.float32).reshape(-1, 4)
+        a = np.asarray(action, dtype=np.float32).reshape(-1, self._action_floats)
         if a.shape[0] != self.num_envs:
-            raise ValueError('action must have shape [%d, 4] (or [4] / [1, 4] for one env)' % self.num_envs)
+            raise ValueError('action must have shape [%d%s, 4] (or without the batch axis for one env)' % (
+                self.num_envs, '' if self.num_goal_steps is None else ', %d' % self.num_goal_steps))
         self._pinned_action.copy_(torch.from_numpy(a))
         self.world.action.copy_(self._pinned_action, non_blocking=True)
         self.world.set_action()
@@ -337,9 +369,9 @@ class PushEnv(object):
             self._async['mask_host'].copy_(self.world.body_mask)
         st = self._async
         w = self.world
-        a = np.asarray(action, dtype=np.float32).reshape(-1, 4)
+        a = np.asarray(action, dtype=np.float32).reshape(-1, self._action_floats)
         if a.shape[0] != B:
-            raise ValueError('action must have shape [%d, 4]' % B)
+            raise ValueError('action must have shape [%d, %d]' % (B, self._action_floats))
         ready = st['ready']
         start = ready & ~self._done
         cmd = np.where(start, 1, np.where(ready & self._done, 2, 0)).astype(np.uint8)

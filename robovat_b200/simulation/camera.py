@@ -26,6 +26,23 @@ def _rotation_matrix(rotation):
     return quat_to_matrix(quat_from_euler(*r))
 
 
+def draw_calibration(intrinsics, translation, rotation, intrinsics_noise=None, translation_noise=None, rotation_noise=None,
+                     rs=np.random):
+    """The calibration ArmEnv._reset_camera hands to camera.set_calibration in simulation (arm_env.py:109-152): float32
+    copies of the configured values plus uniform noise in [-noise, noise], drawn from `rs` in the reference's order
+    (intrinsics, translation, rotation)."""
+    intrinsics = np.copy(intrinsics).astype(np.float32)
+    translation = np.copy(translation).astype(np.float32)
+    rotation = np.copy(rotation).astype(np.float32)
+    if intrinsics_noise is not None:
+        intrinsics += rs.uniform(-np.array(intrinsics_noise), np.array(intrinsics_noise))
+    if translation_noise is not None:
+        translation += rs.uniform(-np.array(translation_noise), np.array(translation_noise))
+    if rotation_noise is not None:
+        rotation += rs.uniform(-np.array(rotation_noise), np.array(rotation_noise))
+    return intrinsics, translation, rotation
+
+
 class CudaCamera(object):
     def __init__(self, simulator, height=DEPTH_HEIGHT, width=DEPTH_WIDTH, intrinsics=None, translation=None,
                  rotation=None, crop=None, near=NEAR_PLANE, far=FAR_PLANE, distance=1.0, upside_down=True):

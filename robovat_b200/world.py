@@ -69,6 +69,7 @@ class World(object):
         self.scene = scene
         self.device = torch.device('cuda', device)
         self.B, self.N = params.num_envs, params.max_movables
+        self.G = max(1, int(params.num_goal_steps))        # goal steps per action (NUM_GOAL_STEPS)
         self.h = C.c_void_p()
         self._chk(self.lib.b2s_create(C.byref(params), int(device), C.byref(self.h)))
         self._chk(self.lib.b2s_load_scene(self.h, C.byref(scene.desc)))
@@ -76,7 +77,7 @@ class World(object):
         f32, u8, i32 = torch.float32, torch.uint8, torch.int32
         self.body_state = torch.zeros(13, B, N, dtype=f32, device=dev)
         self.joint_state = torch.zeros(2, 7, B, dtype=f32, device=dev)
-        self.action = torch.zeros(B, 4, dtype=f32, device=dev)
+        self.action = torch.zeros(B, self.G * 4, dtype=f32, device=dev)      # [B][G][4]
         self.obs_position = torch.zeros(B, N, 3, dtype=f32, device=dev)
         self.num_movables = torch.zeros(B, dtype=i32, device=dev)
         self.body_mask = torch.zeros(B, N, dtype=u8, device=dev)
@@ -159,7 +160,7 @@ class World(object):
 
     def set_action(self, action=None):
         if action is not None:
-            self.action.copy_(torch.as_tensor(action, dtype=torch.float32).reshape(self.B, 4), non_blocking=True)
+            self.action.copy_(torch.as_tensor(action, dtype=torch.float32).reshape(self.B, self.G * 4), non_blocking=True)
         self._chk(self.lib.b2s_set_action(self.h, self._stream()))
 
     def env_substeps(self, n, sync=True):

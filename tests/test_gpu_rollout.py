@@ -202,3 +202,100 @@ def test_push_env_step_async_bookkeeping():
     assert done.all()
     env.close()
     env2.close()
+
+
+def test_two_goal_steps_per_action_bit_exact():
+    """NUM_GOAL_STEPS = 2 (action [B, 2, 4], the arm goes post -> pre once before it leaves; push_env.py:259-262,
+    803-806): CUDA == oracle at every check point, and PushEnv takes / advertises the [2, 4] action."""
+    B = 16
+    cfg, gpu, cpu = helpers.make_pair(B, params={'export_debug': 0}, NUM_GOAL_STEPS=2)
+    assert gpu.G == 2 and gpu.action.shape == (B, 8)
+    _prepare(gpu, cpu, seed=7)
+    rs = np.random.RandomState(5)
+    pos = cpu.observe()[:, 0, :2]
+    lo, hi = np.array(cfg.ACTION.CSPACE.LOW[:2]), np.array(cfg.ACTION.CSPACE.HIGH[:2])
+    off, rng = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    act = np.zeros((B, 2, 4), np.float32)
+    for g in range(2):
+        ang = rs.uniform(-np.pi, np.pi, B)
+        d = np.stack([np.cos(ang), np.sin(ang)], 1)
+        act[:, g, :2] = np.clip((pos - 0.08 * d - off) / rng, -1, 1)
+        act[:, g, 2:] = d
+    gpu.set_action(act)
+    cpu.set_action(act)
+    helpers.assert_bits_equal(gpu.array(_capi.ARR_WAYPOINTS).cpu().numpy(), cpu.array(_capi.ARR_WAYPOINTS), 'waypoints [B][2][2][7]')
+    seen_second_pre = False
+    for it in range(400):
+        ug = gpu.env_substeps(200)
+        uc = cpu.env_substeps(200)
+        assert ug == uc
+        ph = cpu.array(_capi.ARR_PHASE)
+        nw = cpu.array(_capi.ARR_PHASE_STATE).reshape(B, 8)[:, 1]
+        seen_second_pre |= bool(((ph >= _capi.PHASE_PRE) & (ph <= _capi.PHASE_MOTION) & (nw == 1)).any())
+        np.testing.assert_array_equal(gpu.array(_capi.ARR_PHASE).cpu().numpy(), ph)
+        if it % 5 == 0 or uc == 0:
+            helpers.assert_bits_equal(gpu.body_state.cpu().numpy(), cpu.body_state, 'body_state at slice %d' % it)
+            helpers.assert_bits_equal(gpu.joint_state.cpu().numpy(), cpu.joint_state, 'joint_state at slice %d' % it)
+        if uc == 0:
+            break
+    assert uc == 0 and seen_second_pre
+    np.testing.assert_array_equal(gpu.is_effective.cpu().numpy(), cpu.array('is_effective'))
+    gpu.close()
+    cpu.close()
+    from robovat_b200 import config as config_lib
+    from robovat_b200.envs import PushEnv
+    env = PushEnv(config=config_lib.default_push_env_config(NUM_GOAL_STEPS=2), num_envs=4, seed=1)
+    assert env.action_space.shape == (2, 4)
+    env.reset()
+    obs, reward, done, _ = env.step(act[:4])
+    assert obs['position'].shape == (4, env.world.N, 3) and reward.shape == (4,)
+    with pytest.raises(_capi.B2SError):
+        env.world.rollout_begin(2, 1)                 # the device policies draw one pair per action
+    env.close()
+
+
+def test_point_cloud_crop_wall_and_calibration_noise():
+    """OBS.CROP_MIN/MAX in k_point_cloud and the SIM.WALL static body: CUDA == oracle bit for bit (depth, segmentation,
+    cropped segmented cloud); KINECT2.DEPTH.*_NOISE gives every env of a batched PushEnv its own calibration."""
+    from robovat_b200 import config
+    from robovat_b200.assets import quat_from_euler, quat_to_matrix
+    size = 64
+    kin = dict(config.DEFAULT_PUSH_ENV['KINECT2']['DEPTH'], HEIGHT=size, WIDTH=size, INTRINSICS=[60.0, 0, 32.0, 0, 60.0, 32.0, 0, 0, 1])
+    sim = dict(config.DEFAULT_PUSH_ENV['SIM'])
+    sim['WALL'] = dict(sim['WALL'], USE=True, POSE=[[0.95, 0.0, 0.2], [0, 0, 0.2]])
+    bind = dict(KINECT2={'DEPTH': kin}, SIM=sim, OBS={'NUM_POINTS': 64, 'CROP_MIN': [0.35, -0.4, -0.05], 'CROP_MAX': [0.62, 0.4, 0.5]})
+    cfg, gpu, cpu = helpers.make_pair(24, with_camera=True, **bind)
+    assert gpu.params.use_crop == 1 and [s['name'] for s in gpu.scene.statics[:3]] == ['ground', 'table', 'wall']
+    for w in (gpu, cpu):
+        w.reset(seed=3)
+        w.settle(0.1, 0.1, 500)
+    helpers.assert_bits_equal(gpu.body_state.cpu().numpy(), cpu.body_state, 'settled state with the wall in the scene')
+    R = quat_to_matrix(quat_from_euler(np.pi, 0, 0))
+    for w in (gpu, cpu):
+        w.set_camera(np.array(kin['INTRINSICS'], np.float64), R.reshape(9), -R.dot(np.array([0.6, 0.0, 1.2])))
+    dg, sg = gpu.render()
+    dc, sc = cpu.render()
+    np.testing.assert_array_equal(sg.cpu().numpy(), sc)
+    helpers.assert_bits_equal(dg.cpu().numpy(), dc, 'depth')
+    assert (sc == 2).any()                                   # the wall (uid 2) is in view
+    pg = gpu.point_cloud(seed=9).cpu().numpy()
+    pcc = cpu.point_cloud(seed=9)
+    helpers.assert_bits_equal(pg, pcc, 'cropped segmented point cloud')
+    nz = pg[np.any(pg != 0, axis=-1)]
+    assert len(nz) > 0 and (nz >= np.array([0.35, -0.4, -0.05]) - 1e-6).all() and (nz <= np.array([0.62, 0.4, 0.5]) + 1e-6).all()
+    gpu.close()
+    cpu.close()
+    from robovat_b200.envs import PushEnv
+    kin2 = dict(kin, INTRINSICS_NOISE=[2.0, 0, 2.0, 0, 2.0, 2.0, 0, 0, 0], TRANSLATION_NOISE=[0.01, 0.01, 0.01], ROTATION_NOISE=[0.02, 0.02, 0.05])
+    cfg2 = config.default_push_env_config(KINECT2={'DEPTH': kin2}, USE_POINT_CLOUD_OBS=True, OBS={'NUM_POINTS': 32, 'CROP_MIN': None, 'CROP_MAX': None})
+    env = PushEnv(config=cfg2, num_envs=6, seed=4)
+    obs = env.reset()
+    K, t, r = env._calibration
+    assert K.shape == (6, 3, 3) and len({tuple(np.round(x, 6)) for x in t}) == 6
+    assert np.abs(K - np.array(kin['INTRINSICS'], np.float32).reshape(3, 3)).max() <= 2.0 + 1e-6
+    assert np.abs(t - np.array(kin['TRANSLATION'], np.float32)).max() <= 0.01 + 1e-6
+    assert obs['point_cloud'].shape == (6, env.world.N, 32, 3)
+    first = t.copy()
+    env.reset(mask=np.array([1, 0, 0, 0, 0, 0], bool))
+    assert not np.array_equal(env._calibration[1][0], first[0]) and np.array_equal(env._calibration[1][1:], first[1:])
+    env.close()
