@@ -246,7 +246,9 @@ enum {
   B2S_ARR_PROF = 24,           /* uint64 [8] stage timing of the substep kernel (ns; tuning builds only) */
   B2S_ARR_NUM_EPISODES = 25,   /* int32 [B] episodes finished by b2s_rollout_* (RobotEnv.num_episodes, robot_env.py:262) */
   B2S_ARR_ROLLOUT_STATE = 26,  /* int32 [B][4] rollout: steps of the current episode, episodes of this rollout, re-samples, spare */
-  B2S_ARR_COUNT = 27
+  B2S_ARR_RAY_SCENE = 27,      /* bytes: the raster's per-env camera-space scene and per-tile hull lists (valid after b2s_render;
+                                  layout in b2s_obs.cu; inspection / tuning only) */
+  B2S_ARR_COUNT = 28
 };
 #define B2S_CP_FLOATS 16   /* localA3 localB3 normalB3 dist lambda_n lambda_t1 lambda_t2, then 3 spare words: in point 0 of a
                               manifold they hold the GJK simplex of the pair's last call (int n, (ia | ib << 8) x 4) */

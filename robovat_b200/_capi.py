@@ -35,7 +35,7 @@ STATIC_ON_TABLE, STATIC_IS_TABLE, STATIC_NO_COLLIDE, STATIC_IS_TILE = 1, 2, 4, 8
  ARR_NUM_PAIRS, ARR_PHASE, ARR_NUM_STEPS, ARR_CTRL, ARR_CTRL_FLAGS, ARR_LINK_POSES,
  ARR_MOV_PARAMS, ARR_TABLE_DZ, ARR_ERROR_FLAGS, ARR_WAYPOINTS, ARR_STATUS, ARR_CONTACT_FLAGS,
  ARR_PHASE_STATE, ARR_SOLVER_STATS, ARR_CTRL_TIME, ARR_LINK_VEL, ARR_NUM_COLLIDERS,
- ARR_COL_SLOT, ARR_COL_HULL, ARR_PROF, ARR_NUM_EPISODES, ARR_ROLLOUT_STATE) = range(27)
+ ARR_COL_SLOT, ARR_COL_HULL, ARR_PROF, ARR_NUM_EPISODES, ARR_ROLLOUT_STATE, ARR_RAY_SCENE) = range(28)
 
 f32, i32, u32, u8, f64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint8, C.c_double
 P = C.POINTER

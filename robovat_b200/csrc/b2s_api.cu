@@ -260,6 +260,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     d.max_ray_cols = cols + d.Nmax * mc;
     d.max_ray_planes = std::max(1, pls + d.Nmax * mp);
     if (d.max_ray_cols > 256) return fail(B2S_E_CAPACITY, "b2s_load_scene: %d hulls per environment exceed the raster's 256", d.max_ray_cols);
+    if (d.max_ray_planes > 65535 || s->num_hulls > 32767) return fail(B2S_E_CAPACITY, "b2s_load_scene: the raster indexes at most 65535 face planes per environment and 32767 hulls");
   }
   const size_t B = d.B, N = d.Nmax, M = P.max_manifolds;
 #define ALLOC(field, count, fill) if ((rc = dalloc(w, &d.field, (count), (fill)))) return rc
@@ -607,8 +608,14 @@ int b2s_set_camera(B2SWorld* w, const float* K, const float* R, const float* t, 
 int b2s_render(B2SWorld* w, void* stream) {
   NEED_READY(w);
   if (!w->d.buf.depth || !w->d.buf.segmask) return fail(B2S_E_STATE, "b2s_render: depth/segmask buffers are not bound");
+  if (!w->d.ray_scratch) {                   // the raster's scene scratch exists only in worlds that render
+    DeviceGuard device_guard_(w->device);
+    int rc = dalloc(w, &w->d.ray_scratch, b2s_render_scratch_bytes(w->d), 0);
+    if (rc) return rc;
+    w->arr_ptr[B2S_ARR_RAY_SCENE] = w->d.ray_scratch; w->arr_bytes[B2S_ARR_RAY_SCENE] = b2s_render_scratch_bytes(w->d);
+  }
   b2s_launch_render(w->d, (cudaStream_t)stream);
-  return check_launch(w, "render", 2);
+  return check_launch(w, "render", 3);
 }
 int b2s_point_cloud(B2SWorld* w, uint64_t seed, void* stream) {
   NEED_READY(w);

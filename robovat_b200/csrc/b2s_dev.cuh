@@ -185,6 +185,7 @@ struct DWorld {
   int32_t* async_events;          // [B] b2s_env_async_step: what happened to the env since the last call (B2S_ASYNC_*)
   DRollout ro;
   SmemLayout sm;
+  unsigned char* ray_scratch;   // raster: per-environment camera-space scene + per-tile hull lists (allocated at the first render)
   int max_ray_planes;    // raster: upper bound of hull face planes / hulls in one environment
   int max_ray_cols;
   int envs_per_block;    // E: environment SLOTS of a block (capacity; the deal may leave some empty)
@@ -214,6 +215,7 @@ static inline void b2s_opt_in_smem(K kernel, size_t smem, size_t* configured /* 
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s,
                          int free_chunk = 0);
 void b2s_launch_begin_episode(const DWorld& W, const uint8_t* mask, cudaStream_t s);
+size_t b2s_render_scratch_bytes(const DWorld& W);
 void b2s_launch_rollout_begin(const DWorld& W, const float* first_action, cudaStream_t s);
 void b2s_launch_async_commands(const DWorld& W, const uint8_t* command, cudaStream_t s);
 void b2s_launch_async_status(const DWorld& W, uint8_t* status, cudaStream_t s);

@@ -33,7 +33,7 @@ _ARR_TYPES = {
     _capi.ARR_CONTACT_FLAGS: '<i4', _capi.ARR_PHASE_STATE: '<i4', _capi.ARR_SOLVER_STATS: '<i4',
     _capi.ARR_CTRL_TIME: '<f8', _capi.ARR_LINK_VEL: '<f4', _capi.ARR_NUM_COLLIDERS: '<i4',
     _capi.ARR_COL_SLOT: '<i4', _capi.ARR_COL_HULL: '<i4', _capi.ARR_PROF: '<i8',
-    _capi.ARR_NUM_EPISODES: '<i4', _capi.ARR_ROLLOUT_STATE: '<i4',
+    _capi.ARR_NUM_EPISODES: '<i4', _capi.ARR_ROLLOUT_STATE: '<i4', _capi.ARR_RAY_SCENE: '|u1',
 }
 
 
