@@ -298,6 +298,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   sm.col = take(d.Hmax * COL_STRIDE);
   sm.pairs = take(P.max_pairs);
   sm.cmk = take(P.max_contacts);
+  sm.pstage = o; sm.ps_cap = 0;               // sized below, once the rest of the block's shared memory is known
   sm.words_env = o;
   o = 0;
   const int x0 = o;                 // region shared by the narrow-phase scratch and the solver rows
@@ -339,6 +340,22 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
 #endif
     if (P.envs_per_block <= 0 && E > wpb) E = std::min(maxE, E + std::max(4, E / 7) + B2S_EXTRA_SLOTS);
     d.envs_per_block = E;
+    {
+      // staging records of the narrow phase in shared memory: as many pairs per environment as fit in what is left of
+      // B2S_SMEM_BUDGET (the rest of the SM's 256 KB stays L1: hull vertices, manifolds and scene tables live there)
+#ifndef B2S_SMEM_BUDGET
+#define B2S_SMEM_BUDGET (200 * 1024)
+#endif
+#ifndef B2S_PS_CAP_MAX
+#define B2S_PS_CAP_MAX 4
+#endif
+      const size_t used = ((size_t)E * (sm.words_env + META_WORDS) + (size_t)wpb * sm.words_warp) * 4;
+      int cap = used < (size_t)B2S_SMEM_BUDGET ? (int)(((size_t)B2S_SMEM_BUDGET - used) / ((size_t)E * 68 * 4)) : 0;
+      cap = std::min(std::min(cap, (int)P.max_pairs), B2S_PS_CAP_MAX);
+      if (cap < 2) cap = 0;
+      sm.ps_cap = cap;
+      sm.words_env += cap * 68;
+    }
     const size_t blocks = d.num_blocks;
     if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * UNITS_PER_WARP * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
     if ((rc = dalloc(w, &d.pair_stage, blocks * (size_t)E * P.max_pairs * 68, 0))) return rc;

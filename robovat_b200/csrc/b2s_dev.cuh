@@ -107,7 +107,7 @@ struct DRollout {
 // (stage .. simplex): the solve-stage tables are only alive in the solve stage.  The EPA polytope (rare path, 4 KB per
 // warp) lives in global memory so that the block leaves more of the SM's 256 KB to the L1 cache.
 struct SmemLayout {
-  int body, col, pairs, cmk, words_env;                        // per environment
+  int body, col, pairs, cmk, pstage, ps_cap, words_env;        // per environment (pstage: staging records of the first ps_cap candidate pairs)
   int con, stage, fk, simplex, words_warp;                     // per warp: scratch
 };
 #define META_ACTIVE 0

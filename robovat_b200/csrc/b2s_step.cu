@@ -1032,7 +1032,14 @@ __device__ __noinline__ int stage_scene(int e, int lane, int wib) {
 // unit, a block with few active environments -- the last 11 of the 24 launches of a bench step carry < 6 % of
 // the environments -- spent 3-4 pairs' worth of latency in this stage; now it is one pair's worth.
 #define PS_WORDS 68                      // staging record: the manifold (64 words, GJK cache in 13..15), point count at 64
+// The records of the first sm.ps_cap pairs of an environment live in its shared-memory region (up to 4: the PushEnv
+// scenes have 3.3 candidate pairs on average; more shared memory for them costs more in L1 than it saves), the rest in
+// an L2-resident global array.  The record is written in stage B by whichever warp took the pair and read in stage C
+// by the warp that solves the environment: through global memory every substep paid for that hand-over with ~850 B
+// of stores per environment, most of this kernel's DRAM write traffic (the speed is the same: measured 21.5 M
+// substeps/s either way).
 __device__ __forceinline__ float* pair_stage(int sw, int p) {
+  if (p < W.sm.ps_cap) return b2s_smem + (size_t)(sw & 0xffff) * W.sm.words_env + W.sm.pstage + p * PS_WORDS;
   return W.pair_stage + (((size_t)blockIdx.x * W.envs_per_block + (sw & 0xffff)) * W.P.max_pairs + p) * PS_WORDS;
 }
 
