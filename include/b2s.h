@@ -357,7 +357,7 @@ int b2s_rollout_run(B2SWorld* world, int chunk, int max_substeps, int* unfinishe
 int b2s_env_async_step(B2SWorld* world, const uint8_t* command_dev, int n_substeps, uint64_t reset_seed, uint8_t* status_dev,
                        void* stream);
 /* the same with a free-running launch (see B2SRollout.free_running): n_substeps x (busy envs) substeps in total, at most
- * 2 n_substeps for one env */
+ * 4 n_substeps for one env */
 int b2s_env_async_step_free(B2SWorld* world, const uint8_t* command_dev, int n_substeps, uint64_t reset_seed, uint8_t* status_dev,
                             void* stream);
 

@@ -275,7 +275,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   ALLOC(contact_flags, B, 0); ALLOC(phase_state, B * 8, 0); ALLOC(solver_stats, B * 4, 0);
   ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
   ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
-  ALLOC(ro_state, B * 4, 0); ALLOC(num_episodes, B, 0); ALLOC(async_events, B, 0);
+  ALLOC(ro_state, B * 4, 0); ALLOC(num_episodes, B, 0); ALLOC(async_events, B, 0); ALLOC(work_ema, B, 0);
   ALLOC(substeps, 1, 0); ALLOC(free_target, 1, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16, 0);
   if ((rc = dalloc(w, &w->exp_keys, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_npts, B * M, 0))) return rc;
@@ -500,7 +500,7 @@ int b2s_rollout_run(B2SWorld* w, int chunk, int max_substeps, int* unfinished_ho
   while (launched < max_substeps) {
     CU(cudaMemsetAsync(w->d.unfinished, 0, sizeof(int), s));
     const int n = (max_substeps - launched < chunk) ? (max_substeps - launched) : chunk;
-    if (w->d.ro.free_running) b2s_launch_substeps(w->d, 2 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
+    if (w->d.ro.free_running) b2s_launch_substeps(w->d, 4 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
     else b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
     int rc = check_launch(w, "rollout_run", 2);
     if (rc) return rc;
@@ -541,7 +541,7 @@ static int async_step(B2SWorld* w, const uint8_t* command, int n, uint64_t reset
   int rc = check_launch(w, "async_commands");
   if (rc) return rc;
   if (n > 0) {
-    if (free_running) b2s_launch_substeps(w->d, 2 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
+    if (free_running) b2s_launch_substeps(w->d, 4 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
     else b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
     if ((rc = check_launch(w, "env_async_step", 2))) return rc;
   }

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
   __syncthreads();
   for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
     const int32_t* st = W.solver_stats + (size_t)e * 4;
-    int key = 1 + min(254, st[1] * st[2]);
+    int key = 1 + min(254, free_chunk > 0 ? (int)W.work_ema[e] : st[1] * st[2]);
     if (mode == MODE_ENV && W.phase[e] == B2S_PHASE_IDLE) key = 0;
     atomicAdd(&hist[255 - key], 1);                 // bin 0 = most expensive
   }
@@ -223,10 +223,20 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
   const int nl = W.B - min(hcap, W.B), fill = min(Hb * LF, nl);
   for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
     const int32_t* st = W.solver_stats + (size_t)e * 4;
-    int key = 1 + min(254, st[1] * st[2]);
+    int key = 1 + min(254, free_chunk > 0 ? (int)W.work_ema[e] : st[1] * st[2]);
     if (mode == MODE_ENV && W.phase[e] == B2S_PHASE_IDLE) key = 0;
     const int p = atomicAdd(&base[255 - key], 1);
     int block, slot;
+#ifndef B2S_FREE_DEAL_SPREAD
+    if (free_chunk > 0) {
+      // free-running launch: nobody waits for the slowest block, so a block's cost need not match the others' -- what
+      // counts is that the warps of ONE block finish their stage together.  Environments of similar cost share a
+      // block (ranked by cost, dealt in consecutive runs): the expensive blocks make fewer rounds with all warps busy
+      // on long solves, the cheap ones make many short rounds.
+      const int per = (W.B + nblocks - 1) / nblocks;
+      block = p / per; slot = p % per;
+    } else
+#endif
     if (p < hcap) { block = p % Hb; slot = p / Hb; }
     else {
       const int q = p - hcap, qr = nl - 1 - q;          // qr: rank from the cheap end

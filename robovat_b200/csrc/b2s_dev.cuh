@@ -182,6 +182,7 @@ struct DWorld {
   int32_t* ro_state;              // [B][4] rollout: step of the episode, episode index, re-samples of the current reset, spare
   int32_t* num_episodes;          // [B] episodes finished by the device-side driver
   unsigned long long* free_target;   // [1] value of *substeps at which a free-running launch stops (set by k_assign_envs)
+  float* work_ema;                // [B] running mean of an environment's solver work (colours x iterations): what the deal of a free-running launch ranks by
   int32_t* async_events;          // [B] b2s_env_async_step: what happened to the env since the last call (B2S_ASYNC_*)
   DRollout ro;
   SmemLayout sm;

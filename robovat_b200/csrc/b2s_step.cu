@@ -2228,6 +2228,10 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       if (W.reg_rows) substep_post_reg(e, lane, sw, C, newn);
       else substep_post_big(e, lane, sw, C, newn);
       ++done_steps;
+      if (free_run && lane == 0) {            // what the next launch's deal ranks the environments by (k_assign_envs)
+        const int32_t* st = W.solver_stats + (size_t)e * 4;
+        W.work_ema[e] = 0.75f * W.work_ema[e] + 0.25f * (float)(st[1] * st[2]);
+      }
       bool nxt = (s + 1 < n);
       if (mode == MODE_ENV) {
         int32_t* ps = W.phase_state + (size_t)e * 8;
