@@ -142,10 +142,11 @@ def measured_peak():
 
 def measured_traffic():
     """DRAM bytes per env-substep of k_substeps from the committed ncu --set full capture (None when absent)."""
-    path = os.path.join(ROOT, 'profiles', 'r01_k_substeps_dram_traffic.json')
-    if os.path.exists(path):
-        with open(path) as f:
-            return float(json.load(f)['dram_bytes_per_env_substep'])
+    for name in ('r02_k_substeps_dram_traffic.json', 'r01_k_substeps_dram_traffic.json'):
+        path = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(path):
+            with open(path) as f:
+                return float(json.load(f)['dram_bytes_per_env_substep'])
     return None
 
 

@@ -276,7 +276,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
   ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
   ALLOC(ro_state, B * 4, 0); ALLOC(num_episodes, B, 0); ALLOC(async_events, B, 0); ALLOC(work_ema, B, 0);
-  ALLOC(substeps, 1, 0); ALLOC(free_target, 1, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16, 0);
+  ALLOC(substeps, 1, 0); ALLOC(free_target, 2, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16, 0);
   if ((rc = dalloc(w, &w->exp_keys, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_npts, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_pts, B * M * 4 * B2S_CP_FLOATS, 0))) return rc;
@@ -444,11 +444,12 @@ int b2s_env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream) {
   NEED_READY(w);
   if (n < 0) return fail(B2S_E_INVALID, "b2s_env_substeps: n < 0");
   cudaStream_t s = (cudaStream_t)stream;
-  CU(cudaMemsetAsync(w->d.unfinished, 0, sizeof(int), s));
   b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
   int rc = check_launch(w, "env_substeps", 2);
   if (rc) return rc;
   if (unfinished_host) {
+    b2s_launch_count_running(w->d, s);
+    if ((rc = check_launch(w, "count_running"))) return rc;
     CU(cudaMemcpyAsync(w->unfinished_pinned, w->d.unfinished, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     *unfinished_host = *w->unfinished_pinned;
@@ -498,12 +499,13 @@ int b2s_rollout_run(B2SWorld* w, int chunk, int max_substeps, int* unfinished_ho
   cudaStream_t s = (cudaStream_t)stream;
   int launched = 0, i = 0, last = -1;
   while (launched < max_substeps) {
-    CU(cudaMemsetAsync(w->d.unfinished, 0, sizeof(int), s));
     const int n = (max_substeps - launched < chunk) ? (max_substeps - launched) : chunk;
     if (w->d.ro.free_running) b2s_launch_substeps(w->d, 4 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
     else b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
     int rc = check_launch(w, "rollout_run", 2);
     if (rc) return rc;
+    b2s_launch_count_running(w->d, s);
+    if ((rc = check_launch(w, "count_running"))) return rc;
     CU(cudaMemcpyAsync(w->unfinished_pinned + (i & 3), w->d.unfinished, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(w->ring_event[i & 3], s));
     launched += n;

@@ -178,7 +178,7 @@ __global__ void k_rebuild_colliders(const __grid_constant__ DWorld W) {
 // warm start), which no deal can predict.
 #define HEAVY_KEY 60       // iterations x colours of the last substep from which an environment counts as expensive (a resting
                            // scene has none: then the deal is a plain round-robin, which is the best for uniform work)
-__global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DWorld W, int mode, int nblocks, int free_chunk) {
+__global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DWorld W, int mode, int nblocks) {
   __shared__ int hist[256];
   __shared__ int base[256];
   __shared__ int s_heavy;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
   __syncthreads();
   for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
     const int32_t* st = W.solver_stats + (size_t)e * 4;
-    int key = 1 + min(254, free_chunk > 0 ? (int)W.work_ema[e] : st[1] * st[2]);
+    int key = 1 + min(254, st[1] * st[2]);
     if (mode == MODE_ENV && W.phase[e] == B2S_PHASE_IDLE) key = 0;
     atomicAdd(&hist[255 - key], 1);                 // bin 0 = most expensive
   }
@@ -204,7 +204,6 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
   // (only when the stepping environments need more than one wave per block anyway: a sparse launch -- the tail of
   // a batched PushEnv.step -- is fastest with the environments spread one per block)
   const int stepping = W.B - hist[255];
-  if (threadIdx.x == 0 && free_chunk > 0) *W.free_target = *W.substeps + (unsigned long long)stepping * (unsigned long long)free_chunk;
   // B2S_HW expensive environments per block of that class (default: one per warp), topped up with B2S_LF of the
   // cheapest ones (default: none)
 #ifndef B2S_HW
@@ -223,20 +222,10 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
   const int nl = W.B - min(hcap, W.B), fill = min(Hb * LF, nl);
   for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
     const int32_t* st = W.solver_stats + (size_t)e * 4;
-    int key = 1 + min(254, free_chunk > 0 ? (int)W.work_ema[e] : st[1] * st[2]);
+    int key = 1 + min(254, st[1] * st[2]);
     if (mode == MODE_ENV && W.phase[e] == B2S_PHASE_IDLE) key = 0;
     const int p = atomicAdd(&base[255 - key], 1);
     int block, slot;
-#ifndef B2S_FREE_DEAL_SPREAD
-    if (free_chunk > 0) {
-      // free-running launch: nobody waits for the slowest block, so a block's cost need not match the others' -- what
-      // counts is that the warps of ONE block finish their stage together.  Environments of similar cost share a
-      // block (ranked by cost, dealt in consecutive runs): the expensive blocks make fewer rounds with all warps busy
-      // on long solves, the cheap ones make many short rounds.
-      const int per = (W.B + nblocks - 1) / nblocks;
-      block = p / per; slot = p % per;
-    } else
-#endif
     if (p < hcap) { block = p % Hb; slot = p / Hb; }
     else {
       const int q = p - hcap, qr = nl - 1 - q;          // qr: rank from the cheap end
@@ -245,6 +234,56 @@ __global__ void __launch_bounds__(1024) k_assign_envs(const __grid_constant__ DW
     }
     W.env_map[(size_t)block * E + slot] = e;
   }
+}
+
+// The deal of a FREE-RUNNING launch (MODE_ENV; b2s_rollout_run / b2s_env_async_step_free).  Nobody waits for the slowest
+// block there, so a block's cost need not match the others' -- what counts is that the warps of ONE block finish their
+// stages together: environments are ranked by a running mean of their solver work and dealt in consecutive runs, the
+// expensive blocks make fewer rounds with every warp on a long solve, the cheap ones many short rounds.
+// Only blocks that are resident together take part (run_blocks <= SM count): a block that started after the launch's
+// total was reached would stop after one round and its environments would starve.  When the world needs more blocks
+// than that (large scenes: fewer environments fit a block), every launch steps a window of the environments that
+// advances round-robin over the env index, so all of them get the same share of launches.
+__global__ void __launch_bounds__(1024) k_assign_envs_free(const __grid_constant__ DWorld W, int total_blocks, int run_blocks, int per,
+                                                           int free_chunk) {
+  __shared__ int hist[256];
+  __shared__ int base[256];
+  __shared__ int s_stepping;
+  const int E = W.envs_per_block;
+  const int capacity = run_blocks * per;
+  const int offset = (int)(W.free_target[1] % (unsigned long long)W.B);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  for (int i = threadIdx.x; i < total_blocks * E; i += blockDim.x) W.env_map[i] = -1;
+  __syncthreads();
+  for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
+    const int rot = (e - offset + W.B) % W.B;
+    if (rot < capacity && W.phase[e] != B2S_PHASE_IDLE) atomicAdd(&hist[254 - min(254, (int)W.work_ema[e])], 1);   // bin 0 = most expensive
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < 256; ++i) { base[i] = acc; acc += hist[i]; }
+    s_stepping = acc;
+    W.free_target[0] = *W.substeps + (unsigned long long)acc * (unsigned long long)free_chunk;
+    W.free_target[1] = (unsigned long long)((offset + (capacity < W.B ? capacity : 0)) % W.B);
+  }
+  __syncthreads();
+  // few running environments (the end of a rollout): spread them over the blocks
+  const int run = min(per, max(1, (s_stepping + run_blocks - 1) / run_blocks));
+  for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
+    const int rot = (e - offset + W.B) % W.B;
+    if (!(rot < capacity && W.phase[e] != B2S_PHASE_IDLE)) continue;
+    const int p = atomicAdd(&base[254 - min(254, (int)W.work_ema[e])], 1);
+    W.env_map[(size_t)(p / run) * E + (p % run)] = e;
+  }
+}
+
+// number of environments whose action / episode is still in flight (what b2s_env_substeps & co. report to the host)
+__global__ void k_count_running(const __grid_constant__ DWorld W) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = e < W.B && W.phase[e] != B2S_PHASE_IDLE;
+  const unsigned m = __ballot_sync(0xffffffffu, on);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(W.unfinished, __popc(m));
 }
 
 // scalar DLS IK (same arithmetic as arm_ik in b2s_step.cu / oracle arm_ik)
@@ -361,8 +400,24 @@ __global__ void k_se3(int op, const float* a, const float* b, float* out, int n)
 
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
-void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk) {
-  k_assign_envs<<<1, 1024, 0, s>>>(W, mode, W.num_blocks, free_chunk);
+int b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk) {
+  if (free_chunk > 0) {
+    static int sms[B2S_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= B2S_MAX_DEVICES) dev = 0;
+    if (!sms[dev]) { int n = 148; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); sms[dev] = n > 0 ? n : 148; }
+    const int run_blocks = W.num_blocks < sms[dev] ? W.num_blocks : sms[dev];
+    const int per = (W.B + W.num_blocks - 1) / W.num_blocks;
+    k_assign_envs_free<<<1, 1024, 0, s>>>(W, W.num_blocks, run_blocks, per, free_chunk);
+    return run_blocks;
+  }
+  k_assign_envs<<<1, 1024, 0, s>>>(W, mode, W.num_blocks);
+  return W.num_blocks;
+}
+void b2s_launch_count_running(const DWorld& W, cudaStream_t s) {
+  cudaMemsetAsync(W.unfinished, 0, sizeof(int), s);
+  k_count_running<<<blocks_for(W.B, 256), 256, 0, s>>>(W);
 }
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s) { k_reset<<<blocks_for(W.B, 64), 64, 0, s>>>(W, mask, seed); }
 void b2s_launch_set_action(const DWorld& W, cudaStream_t s) { k_set_action<<<blocks_for(W.B, 128), 128, 0, s>>>(W); }

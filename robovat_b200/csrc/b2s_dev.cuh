@@ -181,7 +181,7 @@ struct DWorld {
   float* row_scratch;             // [blocks][warps][32][68] solver rows of the environment a warp is solving (L1/L2 resident)
   int32_t* ro_state;              // [B][4] rollout: step of the episode, episode index, re-samples of the current reset, spare
   int32_t* num_episodes;          // [B] episodes finished by the device-side driver
-  unsigned long long* free_target;   // [1] value of *substeps at which a free-running launch stops (set by k_assign_envs)
+  unsigned long long* free_target;   // [2] value of *substeps at which a free-running launch stops; start of the env window of the next one
   float* work_ema;                // [B] running mean of an environment's solver work (colours x iterations): what the deal of a free-running launch ranks by
   int32_t* async_events;          // [B] b2s_env_async_step: what happened to the env since the last call (B2S_ASYNC_*)
   DRollout ro;
@@ -220,7 +220,8 @@ size_t b2s_render_scratch_bytes(const DWorld& W);
 void b2s_launch_rollout_begin(const DWorld& W, const float* first_action, cudaStream_t s);
 void b2s_launch_async_commands(const DWorld& W, const uint8_t* command, cudaStream_t s);
 void b2s_launch_async_status(const DWorld& W, uint8_t* status, cudaStream_t s);
-void b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk = 0);
+int b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk = 0);   // returns the blocks to launch
+void b2s_launch_count_running(const DWorld& W, cudaStream_t s);
 void b2s_launch_staged(const DWorld& W, int n, cudaStream_t s, int64_t* launches);
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s);
 void b2s_launch_set_action(const DWorld& W, cudaStream_t s);

@@ -2298,11 +2298,6 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     if (threadIdx.x == 0) { atomicAdd(W.prof + 7, (unsigned long long)s_maxc); s_maxc = 0; }
 #endif
   }
-  if (mode == MODE_ENV)
-    for (int slot = wib; slot < E; slot += Wn) {
-      const int e = W.env_map[e0 + slot];
-      if (e >= 0 && lane == 0 && W.phase[e] != B2S_PHASE_IDLE) atomicAdd(W.unfinished, 1);
-    }
   if (lane == 0 && done_steps) atomicAdd(W.substeps, (unsigned long long)done_steps);
 }
 
@@ -2328,9 +2323,9 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
   DevLaunch* L = (dev >= 0 && dev < B2S_MAX_DEVICES) ? &g_launch[dev] : nullptr;
   if (L && L->have && L->stream != s) cudaStreamWaitEvent(s, L->done, 0);
   if (mode != MODE_ENV) free_chunk = 0;
-  b2s_launch_assign_envs(W, mode, s, free_chunk);
+  const int run_blocks = b2s_launch_assign_envs(W, mode, s, free_chunk);
   cudaMemcpyToSymbolAsync(g_W, &W, sizeof(DWorld), 0, cudaMemcpyHostToDevice, s);
-  k_substeps<<<blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, free_chunk > 0 ? 1 : 0);
+  k_substeps<<<run_blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, free_chunk > 0 ? 1 : 0);
   if (L) {
     if (!L->have) { if (cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming) == cudaSuccess) L->have = true; }
     if (L->have) { cudaEventRecord(L->done, s); L->stream = s; }

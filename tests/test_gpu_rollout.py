@@ -67,6 +67,25 @@ def test_rollout_matches_oracle_rollout(task, free_running):
     cpu.close()
 
 
+def test_free_running_rollout_with_more_blocks_than_sms():
+    """A world that needs more thread blocks than the device has SMs (here: one env per block, 200 envs) steps a
+    rotating window of its envs per free-running launch; every env still completes the same episodes."""
+    A, EP, B = 2, 2, 200
+    cfg, gpu, cpu = helpers.make_pair(B, params={'export_debug': 0, 'envs_per_block': 1})
+    _prepare(gpu, cpu, seed=12)
+    rec = RolloutRecord(B, gpu.N, EP, A, gpu.device)
+    gpu.rollout_begin(A, EP, policy_seed=5, reset_seed=6, record=rec, policy_kind=_capi.POLICY_AIMED, free_running=True)
+    ref = cpu.rollout_begin(A, EP, policy_seed=5, reset_seed=6, policy_kind=_capi.POLICY_AIMED)
+    assert gpu.rollout_run(chunk=250, max_substeps=400000) == 0
+    while cpu.rollout_run(5000) > 0:
+        pass
+    _compare_records(rec, ref, A)
+    helpers.assert_bits_equal(gpu.body_state.cpu().numpy(), cpu.body_state, 'final body_state')
+    assert gpu.substeps_executed() == cpu.substeps_executed()
+    gpu.close()
+    cpu.close()
+
+
 def test_rollout_budget_stops_mid_episode_and_resumes():
     """A substep budget cuts the rollout anywhere (mid action, mid reset); the state then equals the oracle's after the
     same number of substeps per env, and a second run call finishes the episodes.  Uses the aimed policy (bench.py)."""

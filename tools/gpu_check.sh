@@ -17,7 +17,7 @@ timeout 600 ncu --set full --clock-control none --import-source on --profile-fro
     -o $OUT/k_substeps_full -f python tools/profile_rollout.py 4096 50 3 24 0 > $OUT/profile_rollout.log 2>&1; echo "ncu full rc=$?"
 B2S_CFG=crossing timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_substeps -c 1 \
     -o $OUT/k_substeps_crossing_full -f python tools/profile_rollout.py 4096 20 3 8 0 > $OUT/profile_rollout_crossing.log 2>&1; echo "ncu crossing rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_render -c 1 -s 3 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_render_shade -c 1 -s 3 \
     -o $OUT/k_render_full -f python tools/bench_render.py 2048 128 5 > $OUT/bench_render_under_ncu.log 2>&1; echo "ncu render rc=$?"
 timeout 300 python tools/bench_render.py 2048 128 20 > $OUT/bench_render.json 2>&1
 timeout 300 python tools/profile_rollout.py 4096 250 4 24 1 > $OUT/profile_rollout_free.log 2>&1
