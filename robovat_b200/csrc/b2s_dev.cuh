@@ -28,10 +28,13 @@ typedef b2s_m3 M3;
 #define B2S_TYPE_DYNAMIC 2
 
 // narrow-phase unit: the lanes that work on one candidate pair.  B2S_HALF = log2(units per warp): 0 = the whole warp
-// on one pair, 1 = two pairs of 16 lanes, 2 = four pairs of 8 lanes.  Hulls have 8..64 vertices and most of GJK is
-// uniform simplex arithmetic, so narrow units waste fewer lanes; the halves diverge only where their pairs differ.
+// on one pair, 1 = two pairs of 16 lanes, 2 = four pairs of 8 lanes, 3 = eight pairs of 4 lanes.  Hulls have 8..64
+// vertices and most of GJK is uniform simplex arithmetic, so narrow units waste fewer lanes; the units diverge only
+// where their pairs differ.  A call takes about as long with one pair as with eight (it is a latency chain), and the
+// stage ends with its slowest warp: with eight pairs per grab the ~92 pairs of a block's round are one grab per warp
+// (measured in free-running rollouts: 16 lanes 21.7, 8 lanes 23.4, 4 lanes 24.5 M substeps/s).
 #ifndef B2S_HALF
-#define B2S_HALF 2
+#define B2S_HALF 3
 #endif
 #if B2S_HALF
 #define UW (32 >> B2S_HALF)
