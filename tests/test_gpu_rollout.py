@@ -318,3 +318,40 @@ def test_point_cloud_crop_wall_and_calibration_noise():
     env.reset(mask=np.array([1, 0, 0, 0, 0, 0], bool))
     assert not np.array_equal(env._calibration[1][0], first[0]) and np.array_equal(env._calibration[1][1:], first[1:])
     env.close()
+
+
+def test_full_size_free_running_rollout_against_the_oracle():
+    """BASELINE.json configs[1] at full size: 4096 envs at dt = 1/240, one episode of three aimed pushes each,
+    free-running launches on the GPU against the oracle on all host threads: every env's actions, rewards, flags,
+    substep counts and return are bit-identical, and the total of substeps executed is the same."""
+    import os
+    import bench
+    from oracle import b2o
+    from robovat_b200 import config
+    from robovat_b200.world import World
+    A, EP, B = 3, 1, 4096
+    cfg = bench.bench_config(B)
+    scene = config.build_scene(cfg)
+    params = config.build_params(cfg, scene, num_envs=B)
+    gpu = World(params, scene)
+    cpu = b2o.OracleWorld(params, scene, threads=os.cpu_count() or 4)
+    _prepare(gpu, cpu, seed=21)
+    rec = RolloutRecord(B, gpu.N, EP, A, gpu.device, positions=False)
+    gpu.rollout_begin(A, EP, policy_seed=bench.POLICY_SEED, reset_seed=bench.RESET_SEED, record=rec, policy_kind=_capi.POLICY_AIMED,
+                      free_running=True)
+    ref = cpu.rollout_begin(A, EP, policy_seed=bench.POLICY_SEED, reset_seed=bench.RESET_SEED, positions=False, policy_kind=_capi.POLICY_AIMED)
+    assert gpu.rollout_run(chunk=250, max_substeps=200000) == 0
+    while cpu.rollout_run(20000) > 0:
+        pass
+    torch.cuda.synchronize()
+    g = {k: v.cpu().numpy() for k, v in rec.tensors().items()}
+    for k in ('lengths', 'flags', 'substeps'):
+        np.testing.assert_array_equal(g[k], ref[k], err_msg=k)
+    helpers.assert_bits_equal(g['actions'], ref['actions'], 'actions')
+    helpers.assert_bits_equal(g['rewards'], ref['rewards'], 'rewards')
+    helpers.assert_bits_equal(g['returns'], ref['returns'], 'returns')
+    helpers.assert_bits_equal(gpu.body_state.cpu().numpy(), cpu.body_state, 'final body_state')
+    assert gpu.substeps_executed() == cpu.substeps_executed()
+    assert (g['lengths'] == A).mean() > 0.9
+    gpu.close()
+    cpu.close()
