@@ -16,11 +16,16 @@
 // collider AABBs, pair list, contact list) live in the block's shared memory; only the persistent state (13
 // floats per movable, 14 per arm, the <=4-point manifolds) goes back to HBM/L2.  Lanes split the work inside a
 // unit: one hull vertex per lane in the GJK/EPA support function (exact max via redux on order-preserving
-// keys), one collider per lane for AABBs, ballot-compacted pair lists, one contact per lane for Jacobian rows
-// and colouring, one BODY per lane in the Gauss-Seidel sweeps (velocities in registers), which run the oracle's
-// colour order exactly.  The residual test is a warp reduce.  All fp32 arithmetic is ordered exactly as in
-// oracle/ (no FMA contraction), so every output matches bit for bit.  Why stages and barriers at all when the
-// environments never interact: the kernel is ~10x the instruction cache, see the note above k_substeps.
+// keys), one collider per lane for AABBs, ballot-compacted pair lists, one contact per lane for Jacobian rows,
+// colouring and the Gauss-Seidel sweeps (rows in registers, the body's velocity handed from lane to lane with
+// shuffles; one BODY per lane when movables touch each other), which run the oracle's colour order exactly.  The
+// residual test is a warp reduce.  All fp32 arithmetic is ordered exactly as in oracle/ (no FMA contraction), so
+// every output matches bit for bit.  Why stages and barriers at all when the environments never interact: the
+// kernel is ~10x the instruction cache, see the note above k_substeps.
+// Episodes: in MODE_ENV an environment that finishes an action can go straight on (b2s_rollout.cuh: reward, record,
+// next action from the device policy, or scene reset + drop + settle and the next episode), or wait for the host
+// (asynchronous stepping).  A launch either gives every environment exactly n substeps, or is free-running: it ends
+// when it has executed a total of substeps, all blocks stopping within one round of each other.
 #include <mutex>
 
 #include "b2s_dev.cuh"
@@ -347,9 +352,9 @@ __device__ void arm_set_joint_target(int e, int lane, const float* q) {
 }
 
 // -------------------------------------------------------------- support ----
-// Narrow-phase units.  A unit (one candidate pair) is processed by UW consecutive lanes: the whole warp, or with
-// -DB2S_HALF=1 a half warp, so that one warp works on two pairs at once (the support function of an 8-vertex
-// box keeps 8 lanes busy either way; everything else in GJK/EPA is scalar work replicated on the lanes).
+// Narrow-phase units.  A unit (one candidate pair) is processed by UW consecutive lanes: 4 by default (B2S_HALF = 3,
+// eight pairs per warp at once; -DB2S_HALF=0..2 for 32 / 16 / 8 lanes).  The support function spreads the hull's
+// vertices over the unit's lanes; everything else in GJK/EPA is scalar work replicated on them.
 // UL = lane within the unit, UB = first lane of the unit, UM = member mask of the unit, UH = unit index in the warp.
 // unit macros (UW, UL, UB, UM, UH): b2s_dev.cuh
 
