@@ -297,6 +297,10 @@ int b2s_step_staged(B2SWorld* world, int n_substeps, void* stream);
  * unfinished envs to *unfinished_host (after synchronising the stream) when it is not NULL. */
 int b2s_set_action(B2SWorld* world, void* stream);
 int b2s_env_substeps(B2SWorld* world, int n_substeps, int* unfinished_host, void* stream);
+/* the same as a free-running launch (see B2SRollout.free_running): n_substeps x (envs in flight) substeps in total, at
+ * most 4 n_substeps for one env.  For callers that loop until every action has finished (PushEnv._execute_action does):
+ * which env gets how many substeps per call does not matter to them, and no SM waits for the slowest block. */
+int b2s_env_substeps_free(B2SWorld* world, int n_substeps, int* unfinished_host, void* stream);
 /* convenience: set_action + env_substeps until every env finished (or max_substeps) */
 int b2s_env_step(B2SWorld* world, int chunk, int max_substeps, void* stream);
 

@@ -137,6 +137,7 @@ SYMBOLS = {
     'b2s_step_staged': (C.c_int, [_vp, C.c_int, _vp]),
     'b2s_set_action': (C.c_int, [_vp, _vp]),
     'b2s_env_substeps': (C.c_int, [_vp, C.c_int, P(C.c_int), _vp]),
+    'b2s_env_substeps_free': (C.c_int, [_vp, C.c_int, P(C.c_int), _vp]),
     'b2s_env_step': (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     'b2s_rollout_begin': (C.c_int, [_vp, P(B2SRollout), _vp]),
     'b2s_rollout_run': (C.c_int, [_vp, C.c_int, C.c_int, P(C.c_int), _vp]),

@@ -440,11 +440,12 @@ int b2s_set_action(B2SWorld* w, void* stream) {
   return check_launch(w, "set_action");
 }
 
-int b2s_env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream) {
+static int env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream, bool free_running) {
   NEED_READY(w);
   if (n < 0) return fail(B2S_E_INVALID, "b2s_env_substeps: n < 0");
   cudaStream_t s = (cudaStream_t)stream;
-  b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
+  if (free_running && n > 0) b2s_launch_substeps(w->d, 4 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
+  else b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
   int rc = check_launch(w, "env_substeps", 2);
   if (rc) return rc;
   if (unfinished_host) {
@@ -456,6 +457,9 @@ int b2s_env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream) {
   }
   return 0;
 }
+
+int b2s_env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream) { return env_substeps(w, n, unfinished_host, stream, false); }
+int b2s_env_substeps_free(B2SWorld* w, int n, int* unfinished_host, void* stream) { return env_substeps(w, n, unfinished_host, stream, true); }
 
 int b2s_env_step(B2SWorld* w, int chunk, int max_substeps, void* stream) {
   NEED_READY(w);

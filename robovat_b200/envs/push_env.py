@@ -324,7 +324,7 @@ class PushEnv(object):
             ph[torch.from_numpy(self._done).to(ph.device)] = _capi.PHASE_IDLE
         done_substeps = 0
         while done_substeps < self.max_action_substeps:
-            unfinished = self.world.env_substeps(self.substep_chunk)
+            unfinished = self.world.env_substeps(self.substep_chunk, free_running=True)   # order of stepping is immaterial here
             done_substeps += self.substep_chunk
             if unfinished == 0:
                 break

@@ -163,9 +163,10 @@ class World(object):
             self.action.copy_(torch.as_tensor(action, dtype=torch.float32).reshape(self.B, self.G * 4), non_blocking=True)
         self._chk(self.lib.b2s_set_action(self.h, self._stream()))
 
-    def env_substeps(self, n, sync=True):
+    def env_substeps(self, n, sync=True, free_running=False):
         u = C.c_int(-1)
-        self._chk(self.lib.b2s_env_substeps(self.h, int(n), C.byref(u) if sync else None, self._stream()))
+        fn = self.lib.b2s_env_substeps_free if free_running else self.lib.b2s_env_substeps
+        self._chk(fn(self.h, int(n), C.byref(u) if sync else None, self._stream()))
         return u.value
 
     def env_step(self, chunk=200, max_substeps=40000):
