@@ -10,6 +10,9 @@ a leading [T, B] axis, and a per-environment episode length.  Nothing in this
 module loops over environments while stepping.
 
   collect(env, policy, num_steps)   -> EpisodeBatch (columnar, [T, B, ...])
+  collect_rollouts(env, ...)        -> list of EpisodeBatch, one per episode index: the episodes run on the device
+                                       (b2s_rollout_*: policy, reward, reset without the host), nobody waits for the
+                                       slowest environment; `batches_from_records` is the pure conversion
   EpisodeBatch.episodes()           -> the reference's per-episode dict layout, for
                                        consumers that expect it (one dict per env)
   ShardWriter / read_shard          -> .npz shards of whole batches (robovat/io's
@@ -102,6 +105,68 @@ def collect(env, policy, num_steps=None):
             break
     final = {k: _batched(v, B).copy() for k, v in obs.items()}
     return EpisodeBatch({k: np.stack(v) for k, v in states.items()}, np.stack(actions), np.stack(rewards), lengths, final)
+
+
+def batches_from_records(records, body_mask=None, hostname=None, timestamp=None):
+    """Device-side rollout records (the arrays of B2SRollout: actions [B, EP, A, 4], rewards [B, EP, A], positions
+    [B, EP, A+1, N, 3], flags [B, EP, A], substeps [B, EP, A], lengths [B, EP], returns [B, EP]) -> one EpisodeBatch per
+    episode index, in the layout `collect` produces: states['position'][t] is the observation action t was computed
+    from, final['position'] the one after the episode's last step; is_safe / is_effective / termination of the
+    transition and Simulator.num_steps after it ride along as states of the NEXT slice (as the reference's
+    observations report them) and in `final`."""
+    rec = {k: np.asarray(v) for k, v in records.items() if v is not None}
+    B, EP, A = rec['rewards'].shape
+    t = np.arange(A)
+    out = []
+    for ep in range(EP):
+        lengths = rec['lengths'][:, ep].astype(np.int64)
+        valid = t[None, :] < lengths[:, None]                                   # [B, A]
+        actions = np.where(valid[..., None], rec['actions'][:, ep], 0).transpose(1, 0, 2)
+        rewards = np.where(valid, rec['rewards'][:, ep], 0.0).transpose(1, 0).astype(np.float64)
+        states, final = {}, {}
+        if 'positions' in rec:
+            pos = rec['positions'][:, ep]                                         # [B, A+1, N, 3]
+            states['position'] = np.where(valid[..., None, None], pos[:, :A], 0).transpose(1, 0, 2, 3)
+            final['position'] = pos[np.arange(B), lengths]
+            # the scene (and with ragged counts the number of bodies) changes from episode to episode: a body is present
+            # iff its first recorded position is not the zero padding (no body rests at the world origin)
+            mask = (pos[:, 0] != 0).any(axis=-1).astype(np.float32) if body_mask is None or ep > 0 else np.asarray(body_mask, np.float32)
+            states['body_mask'] = np.broadcast_to(mask[None], (A,) + mask.shape).copy()
+            final['body_mask'] = mask
+        flags = rec['flags'][:, ep]
+        prev = np.concatenate([np.full((B, 1), 3, flags.dtype), flags[:, :A - 1]], axis=1)     # before step 0: safe, effective
+        for name, bit in (('is_safe', 1), ('is_effective', 2)):
+            states[name] = np.where(valid, (prev & bit) != 0, False).transpose(1, 0).astype(np.int64)
+            final[name] = ((flags[np.arange(B), np.maximum(lengths - 1, 0)] & bit) != 0).astype(np.int64)
+        states['num_steps'] = np.broadcast_to(t[:, None], (A, B)).copy()
+        final['num_steps'] = lengths.copy()
+        final['termination'] = (flags[np.arange(B), np.maximum(lengths - 1, 0)] & 4) != 0
+        if 'substeps' in rec:
+            final['simulator_num_steps'] = rec['substeps'][np.arange(B), ep, np.maximum(lengths - 1, 0)]
+        out.append(EpisodeBatch(states, actions, rewards, lengths, final, hostname, timestamp))
+    return out
+
+
+def collect_rollouts(env, num_episodes=1, num_steps=None, policy_seed=0, reset_seed=None, policy_kind=0, max_attempts=None,
+                     chunk=250, free_running=True, max_substeps=1 << 30):
+    """`num_episodes` episodes in every environment of a batched PushEnv, run on the device: HeuristicPushPolicy
+    (policy_kind 0) or the aimed synthetic policy (1) draws the actions, rewards and resets happen without the host
+    (World.rollout_begin / rollout_run).  Episode 0 starts from a fresh `env.reset()`.  Returns one EpisodeBatch per
+    episode index (batches_from_records)."""
+    from robovat_b200.world import RolloutRecord
+    cfg = env.config
+    A = int(num_steps if num_steps is not None else cfg.MAX_STEPS)
+    env.reset()
+    w = env.world
+    rec = RolloutRecord(w.B, w.N, num_episodes, A, w.device)
+    attempts = int(max_attempts if max_attempts is not None else cfg.get('HEURISTICS', {}).get('MAX_ATTEMPS', 2000))
+    w.rollout_begin(A, num_episodes, policy_seed=policy_seed, reset_seed=env.seed * 1000003 + 7919 if reset_seed is None else reset_seed,
+                    max_attempts=attempts, record=rec, policy_kind=policy_kind, free_running=free_running)
+    left = w.rollout_run(chunk=chunk, max_substeps=max_substeps)
+    if left:
+        raise RuntimeError('collect_rollouts: %d environments did not finish within %d substeps' % (left, max_substeps))
+    records = {k: v.cpu().numpy() for k, v in rec.tensors().items()}
+    return batches_from_records(records)
 
 
 def generate_batched_episodes(env, policy, num_steps=None):

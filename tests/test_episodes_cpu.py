@@ -115,3 +115,35 @@ def test_batched_sampler_is_distribution_equivalent_to_the_scalar_one():
     se = np.sqrt(scalar.var(axis=0) / n + batched.var(axis=0) / n)
     assert (np.abs(scalar.mean(axis=0) - batched.mean(axis=0)) < 5 * se + 1e-3).all(), (scalar.mean(axis=0), batched.mean(axis=0))
     assert (np.abs(scalar.std(axis=0) - batched.std(axis=0)) < 0.25 * scalar.std(axis=0) + 1e-3).all()
+
+
+def test_rollout_records_become_episode_batches():
+    """batches_from_records on the oracle's device-rollout twin: the per-episode batches carry the recorded actions,
+    rewards and observations with `collect`'s conventions (state t = observation before step t, final = after the
+    last step, nothing counts after an environment's own end) and survive the shard round trip."""
+    from tests import helpers
+    cfg, w = helpers.make_oracle(5, threads=4, TASK_NAME='clearing', LAYOUT_ID=0)
+    w.reset(seed=2)
+    w.settle(0.1, 0.1, 500)
+    w.settle()
+    w.begin_episode()
+    rec = w.rollout_begin(num_actions=3, num_episodes=2, policy_seed=9, reset_seed=4, max_attempts=500)
+    while w.rollout_run(2000) > 0:
+        pass
+    batches = episodes.batches_from_records(rec)
+    assert len(batches) == 2
+    for ep, b in enumerate(batches):
+        L = rec['lengths'][:, ep]
+        assert b.lengths.tolist() == L.tolist() and b.actions.shape == (3, 5, 4) and b.states['position'].shape == (3, 5, w.N, 3)
+        for e in range(5):
+            n = int(L[e])
+            np.testing.assert_array_equal(b.actions[:n, e], rec['actions'][e, ep, :n])
+            np.testing.assert_array_equal(b.states['position'][:n, e], rec['positions'][e, ep, :n])
+            np.testing.assert_array_equal(b.final['position'][e], rec['positions'][e, ep, n])
+            assert (b.actions[n:, e] == 0).all() and (b.rewards[n:, e] == 0).all()
+            assert b.states['is_safe'][0, e] == 1 and b.final['is_safe'][e] == (rec['flags'][e, ep, n - 1] & 1)
+        np.testing.assert_allclose(b.returns, rec['returns'][:, ep], rtol=1e-6)
+        eps = b.episodes()
+        assert [len(x['transitions']) for x in eps] == L.tolist()
+    np.testing.assert_array_equal(batches[1].final['body_mask'], w.body_mask.astype(np.float32))     # the last scene's bodies
+    w.close()
