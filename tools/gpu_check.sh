@@ -21,5 +21,5 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_re
     -o $OUT/k_render_full -f python tools/bench_render.py 2048 128 5 > $OUT/bench_render_under_ncu.log 2>&1; echo "ncu render rc=$?"
 timeout 300 python tools/bench_render.py 2048 128 20 > $OUT/bench_render.json 2>&1
 timeout 300 python tools/profile_rollout.py 4096 250 4 24 1 > $OUT/profile_rollout_free.log 2>&1
-tail -5 $OUT/profile_rollout.log $OUT/profile_rollout_free.log
+tail -n 5 $OUT/profile_rollout.log; tail -n 5 $OUT/profile_rollout_free.log
 tail -3 $OUT/pytest_gpu.log
