@@ -400,14 +400,9 @@ __global__ void k_se3(int op, const float* a, const float* b, float* out, int n)
 
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
-int b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk) {
+int b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk, int resident_blocks) {
   if (free_chunk > 0) {
-    static int sms[B2S_MAX_DEVICES];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= B2S_MAX_DEVICES) dev = 0;
-    if (!sms[dev]) { int n = 148; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); sms[dev] = n > 0 ? n : 148; }
-    const int run_blocks = W.num_blocks < sms[dev] ? W.num_blocks : sms[dev];
+    const int run_blocks = W.num_blocks < resident_blocks ? W.num_blocks : resident_blocks;
     const int per = (W.B + W.num_blocks - 1) / W.num_blocks;
     k_assign_envs_free<<<1, 1024, 0, s>>>(W, W.num_blocks, run_blocks, per, free_chunk);
     return run_blocks;

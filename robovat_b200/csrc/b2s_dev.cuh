@@ -223,7 +223,8 @@ size_t b2s_render_scratch_bytes(const DWorld& W);
 void b2s_launch_rollout_begin(const DWorld& W, const float* first_action, cudaStream_t s);
 void b2s_launch_async_commands(const DWorld& W, const uint8_t* command, cudaStream_t s);
 void b2s_launch_async_status(const DWorld& W, uint8_t* status, cudaStream_t s);
-int b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk = 0);   // returns the blocks to launch
+// returns the blocks to launch; resident_blocks: how many blocks of the substep kernel the device holds at once
+int b2s_launch_assign_envs(const DWorld& W, int mode, cudaStream_t s, int free_chunk = 0, int resident_blocks = 1 << 30);
 void b2s_launch_count_running(const DWorld& W, cudaStream_t s);
 void b2s_launch_staged(const DWorld& W, int n, cudaStream_t s, int64_t* launches);
 void b2s_launch_reset(const DWorld& W, const uint8_t* mask, uint64_t seed, cudaStream_t s);

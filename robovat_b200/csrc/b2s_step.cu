@@ -2328,7 +2328,22 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
   DevLaunch* L = (dev >= 0 && dev < B2S_MAX_DEVICES) ? &g_launch[dev] : nullptr;
   if (L && L->have && L->stream != s) cudaStreamWaitEvent(s, L->done, 0);
   if (mode != MODE_ENV) free_chunk = 0;
-  const int run_blocks = b2s_launch_assign_envs(W, mode, s, free_chunk);
+  int resident = 1 << 30;
+  if (free_chunk > 0 && dev >= 0 && dev < B2S_MAX_DEVICES) {
+    // a free-running launch only uses blocks that are resident together (k_assign_envs_free)
+    static int g_resident[B2S_MAX_DEVICES];
+    static size_t g_resident_key[B2S_MAX_DEVICES];
+    const size_t key = smem * 64 + (size_t)wpb;
+    if (g_resident_key[dev] != key) {
+      int occ = 1, sms = 148;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_substeps, wpb * 32, smem);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      g_resident[dev] = (occ > 0 ? occ : 1) * (sms > 0 ? sms : 148);
+      g_resident_key[dev] = key;
+    }
+    resident = g_resident[dev];
+  }
+  const int run_blocks = b2s_launch_assign_envs(W, mode, s, free_chunk, resident);
   cudaMemcpyToSymbolAsync(g_W, &W, sizeof(DWorld), 0, cudaMemcpyHostToDevice, s);
   k_substeps<<<run_blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, free_chunk > 0 ? 1 : 0);
   if (L) {
