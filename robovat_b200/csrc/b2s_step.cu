@@ -1522,8 +1522,9 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   V3 rdir[3], rangA[3], riangA[3];
   float rinvd[3], rd[3], rk1[3], rk2[3], rl[3];
   float imA = 0.0f, imB = 0.0f, bias0 = 0.0f, mu = 0.0f;
+  V3 rangB[3], riangB[3];          // B side of the rows: only used by environments in which movables touch each other
 #pragma unroll
-  for (int r = 0; r < 3; ++r) { rdir[r] = rangA[r] = riangA[r] = v3(0, 0, 0); rinvd[r] = rd[r] = rk1[r] = rk2[r] = rl[r] = 0.0f; }
+  for (int r = 0; r < 3; ++r) { rdir[r] = rangA[r] = riangA[r] = rangB[r] = riangB[r] = v3(0, 0, 0); rinvd[r] = rd[r] = rk1[r] = rk2[r] = rl[r] = 0.0f; }
   __syncwarp();
   if (act) {
     mk = S.cmk[lane];
@@ -1600,11 +1601,7 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       if (r >= nrows) l0 = 0.0f;
       rdir[r] = dir; rangA[r] = angA; riangA[r] = iangA; rinvd[r] = inv_d; rd[r] = d;
       rk1[r] = dot(dir, velB); rk2[r] = dot(angB, angvB); rl[r] = l0;
-      if (coupled != 0ull && dB) {
-        float* recb = rr + lane * RR_WORDS + RR_B;
-        recb[r * 6 + 0] = angB.x; recb[r * 6 + 1] = angB.y; recb[r * 6 + 2] = angB.z;
-        recb[r * 6 + 3] = iangB.x; recb[r * 6 + 4] = iangB.y; recb[r * 6 + 5] = iangB.z;
-      }
+      rangB[r] = angB; riangB[r] = iangB;
     }
   }
   __syncwarp();     // the contact lanes rejoin the others here: the sweeps below are warp-synchronous (shuffles in every
@@ -1718,150 +1715,81 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       p[10] = rl[0]; p[11] = rl[1]; p[12] = rl[2];
     }
   } else {
-    // ---- general case (movables touching each other): rows parked in the per-warp record array, sweeps one BODY
-    // per lane, coupled colours exchange velocities between the two lanes of a contact
-    if (act) {
-      float4* rec = (float4*)(rr + lane * RR_WORDS);
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        lam[r * 32 + lane] = rl[r];
-        rec[r * 4 + 0] = make_float4(rdir[r].x, rdir[r].y, rdir[r].z, rangA[r].x);
-        rec[r * 4 + 1] = make_float4(rangA[r].y, rangA[r].z, riangA[r].x, riangA[r].y);
-        rec[r * 4 + 2] = make_float4(riangA[r].z, rinvd[r], rd[r], rk1[r]);
-        rec[r * 4 + 3] = make_float4(rk2[r], imA, (r == 0) ? bias0 : mu, imB);
+    // ---- movables touch each other (5 % of the env-substeps, but the long solves: 57 us on average against 10).
+    // Still one CONTACT per lane with its rows in registers; the velocities of the bodies stay in the shared body
+    // table: the lanes whose contact has colour k load the velocities of their one or two dynamic bodies, update their
+    // row(s) -- body B takes the opposite impulse -- and store them back; a warp barrier separates the colours.  No
+    // two contacts of a colour share a dynamic body, so the order inside a colour is immaterial, and every row update
+    // performs the oracle's IEEE operations on the same operands: bit-identical to the sequential sweep.
+    const bool mine = act && dA && mycol >= 0;
+    float* vA = S.body + sA * BODY_STRIDE + BO_VEL;        // vel3 then ang3 (BO_ANG = BO_VEL + 3)
+    float* vB = S.body + sB * BODY_STRIDE + BO_VEL;
+    // one row update: (va, wa) of body A, (vb, wb) of body B when it is dynamic (else its constant terms k1, k2)
+#define CROW(r, BIAS, LO, HI)                                                                                     \
+      {                                                                                                           \
+        const float a_ = dot(rdir[r], va) + dot(rangA[r], wa);                                                    \
+        const float k1_ = dB ? dot(rdir[r], vb) : rk1[r], k2_ = dB ? dot(rangB[r], wb) : rk2[r];                  \
+        const float jv = (a_ - k1_) - k2_;                                                                        \
+        float dl = ((BIAS) - jv) * rinvd[r];                                                                      \
+        float nl = rl[r] + dl;                                                                                    \
+        nl = fminf((HI), fmaxf((LO), nl));                                                                        \
+        dl = nl - rl[r];                                                                                          \
+        rl[r] = nl;                                                                                               \
+        const float res = dl * rd[r];                                                                             \
+        maxres = fmaxf(maxres, res * res);                                                                        \
+        va = vmad(va, rdir[r], imA * dl); wa = vmad(wa, riangA[r], dl);                                           \
+        if (dB) { vb = vmad(vb, rdir[r], -(imB * dl)); wb = vmad(wb, riangB[r], -dl); }                           \
       }
+#define CLOAD V3 va = LD3(vA), wa = LD3(vA + 3), vb = v3(0, 0, 0), wb = v3(0, 0, 0); if (dB) { vb = LD3(vB); wb = LD3(vB + 3); }
+#define CSTORE { ST3(vA, va); ST3(vA + 3, wa); if (dB) { ST3(vB, vb); ST3(vB + 3, wb); } }
+    // warm start
+#pragma unroll 1
+    for (int k = 0; k < ncolours; ++k) {
+      if (mine && mycol == k) {
+        CLOAD
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          if (r < nrows) {
+            va = vmad(va, rdir[r], imA * rl[r]); wa = vmad(wa, riangA[r], rl[r]);
+            if (dB) { vb = vmad(vb, rdir[r], -(imB * rl[r])); wb = vmad(wb, riangB[r], -rl[r]); }
+          }
+        CSTORE
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    const float* myb = S.body + (lane < W.NB ? lane : 0) * BODY_STRIDE;
-    const bool dyn = lane < W.NB && __float_as_int(myb[BO_TYPE]) == B2S_TYPE_DYNAMIC;
-    V3 vel = LD3(myb + BO_VEL), ang = LD3(myb + BO_ANG);
-  // one row update of the contact this lane meets in colour k; pass 0: warm start, 1: normal row, 2: friction rows.
-  // STEP_FAST: no contact of the colour joins two dynamic bodies (warp uniform) -- every lane is the A side.
-#define STEP_FAST(PASS)                                                                                           \
-  {                                                                                                               \
-    const unsigned t = dyn ? (unsigned)T[k * 32 + lane] : 0xffu;                                                  \
-    if (t != 0xffu) {                                                                                             \
-      const int c = t & 31;                                                                                       \
-      const float4* rec = (const float4*)(rr + c * RR_WORDS);                                                     \
-      float lim = 0.0f;                                                                                           \
-      if (PASS == 2) lim = rec[7].z * lam[c];                                                                     \
-      _Pragma("unroll")                                                                                           \
-      for (int r = (PASS == 2) ? 1 : 0; r < ((PASS == 1) ? 1 : 3); ++r) {                                         \
-        if (r >= nrows) break;                                                                                    \
-        const float4 q0 = rec[r * 4], q1 = rec[r * 4 + 1], q2 = rec[r * 4 + 2], q3 = rec[r * 4 + 3];              \
-        const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
-        const float l = lam[r * 32 + c];                                                                          \
-        float dl = l;                                                                                             \
-        if (PASS != 0) {                                                                                          \
-          const float jv = ((dot(dir, vel) + dot(angA, ang)) - q2.w) - q3.x;                                      \
-          dl = (((PASS == 1) ? q3.z : 0.0f) - jv) * q2.y;                                                         \
-          float nl = l + dl;                                                                                      \
-          nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
-          dl = nl - l;                                                                                            \
-          lam[r * 32 + c] = nl;                                                                                   \
-          const float res = dl * q2.z;                                                                            \
-          maxres = fmaxf(maxres, res * res);                                                                      \
-        }                                                                                                         \
-        vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                              \
-      }                                                                                                           \
-    }                                                                                                             \
-  }
-  // slots of the two bodies of every contact (partner lookup of coupled contacts) and the B lane's copy of lambda
-  if (act) {
-    lam[192 + lane] = __int_as_float(sA); lam[224 + lane] = __int_as_float(sB);
-    lam[96 + lane] = lam[lane]; lam[128 + lane] = lam[32 + lane]; lam[160 + lane] = lam[64 + lane];
-  }
-  __syncwarp();
-  // STEP_SLOW: the colour holds a contact between two dynamic bodies (rare: movables touching each other).  Its
-  // two lanes exchange velocities with shuffles, compute the same impulse (each on its own copy of lambda) and
-  // apply their own side.  (Measured: moving this step out of line costs 20% -- taking the address of the
-  // velocities parks them in local memory for the whole sweep.)
-#define STEP_SLOW(PASS)                                                                                           \
-  {                                                                                                               \
-    const unsigned t = dyn ? (unsigned)T[k * 32 + lane] : 0xffu;                                                  \
-    const bool has = t != 0xffu;                                                                                  \
-    const int c = t & 31;                                                                                         \
-    const bool sideB = (t & 32u) != 0u, cpl = (t & 64u) != 0u;                                                    \
-    int src = lane;                                                                                               \
-    if (has && cpl) src = __float_as_int(sideB ? lam[192 + c] : lam[224 + c]);                                    \
-    V3 ov = v3(__shfl_sync(FULL, vel.x, src), __shfl_sync(FULL, vel.y, src), __shfl_sync(FULL, vel.z, src));      \
-    V3 ow = v3(__shfl_sync(FULL, ang.x, src), __shfl_sync(FULL, ang.y, src), __shfl_sync(FULL, ang.z, src));      \
-    if (has) {                                                                                                    \
-      const float4* rec = (const float4*)(rr + c * RR_WORDS);                                                     \
-      const float* recb = rr + c * RR_WORDS + RR_B;                                                               \
-      const int r0 = (PASS == 2) ? 1 : 0, r1 = (PASS == 1) ? 1 : nrows;                                           \
-      float* ml = sideB ? lam + 96 : lam;                                                                         \
-      float lim = 0.0f;                                                                                           \
-      if (PASS == 2) lim = rec[7].z * ml[c];                                                                      \
-      for (int r = r0; r < r1; ++r) {                                                                             \
-        const float4 q0 = rec[r * 4], q1 = rec[r * 4 + 1], q2 = rec[r * 4 + 2], q3 = rec[r * 4 + 3];              \
-        const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
-        V3 angB = v3(0, 0, 0), iangB = v3(0, 0, 0);                                                               \
-        if (cpl) { angB = LD3(recb + r * 6); iangB = LD3(recb + r * 6 + 3); }                                     \
-        const float l = ml[r * 32 + c];                                                                           \
-        float dl = l;                                                                                             \
-        if (PASS != 0) {                                                                                          \
-          const V3 vA = sideB ? ov : vel, wA = sideB ? ow : ang;                                                  \
-          const float a = dot(dir, vA) + dot(angA, wA);                                                           \
-          float k1 = q2.w, k2 = q3.x;                                                                             \
-          if (cpl) { k1 = dot(dir, sideB ? vel : ov); k2 = dot(angB, sideB ? ang : ow); }                         \
-          const float jv = (a - k1) - k2;                                                                         \
-          dl = (((PASS == 1) ? q3.z : 0.0f) - jv) * q2.y;                                                         \
-          float nl = l + dl;                                                                                      \
-          nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
-          dl = nl - l;                                                                                            \
-          ml[r * 32 + c] = nl;                                                                                    \
-          const float res = dl * q2.z;                                                                            \
-          maxres = fmaxf(maxres, res * res);                                                                      \
-        }                                                                                                         \
-        if (!sideB) {                                                                                             \
-          vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                            \
-          if (cpl) { ov = vmad(ov, dir, -(q3.w * dl)); ow = vmad(ow, iangB, -dl); }   /* what the partner does */ \
-        } else {                                                                                                  \
-          vel = vmad(vel, dir, -(q3.w * dl)); ang = vmad(ang, iangB, -dl);                                        \
-          ov = vmad(ov, dir, q3.y * dl); ow = vmad(ow, iangA, dl);                                                \
-        }                                                                                                         \
-      }                                                                                                           \
-    }                                                                                                             \
-  }
-  // warm start (pass 0), then per iteration the normal rows (pass 1) of all colours and the friction rows
-  // (pass 2).  The fast step is specialised per pass; the coupled step takes the pass at run time.
-  // (Measured alternatives, all slower: one flattened row-step loop with run-time row selects, 1.5x; software
-  // pipelining of the operand loads across colour steps, 1.3x -- the compiler keeps this loop tight as it is.)
-  // Two instances of the sweep: environments without a coupled colour (the rule) run loops that contain the
-  // fast step only -- ~200 instructions that stay in the L0 instruction cache for up to 50 iterations -- the
-  // others run the general loops.
-#define SWEEP(GENERAL)                                                                                            \
-  {                                                                                                               \
-    _Pragma("unroll 1")                                                                                           \
-    for (int k = 0; k < ncolours; ++k) { if (GENERAL && ((coupled >> k) & 1ull)) { const int pass = 0; STEP_SLOW(pass) } else STEP_FAST(0) } \
-    __syncwarp();                                                                                                 \
-    for (int it = 0; it < P.solver_iterations && C > 0; ++it) {                                                   \
-      maxres = 0.0f;                                                                                              \
-      _Pragma("unroll 1")                                                                                         \
-      for (int k = 0; k < ncolours; ++k) { if (GENERAL && ((coupled >> k) & 1ull)) { const int pass = 1; STEP_SLOW(pass) } else STEP_FAST(1) } \
-      __syncwarp();                                                                                               \
-      _Pragma("unroll 1")                                                                                         \
-      for (int k = 0; k < ncolours; ++k) { if (GENERAL && ((coupled >> k) & 1ull)) { const int pass = 2; STEP_SLOW(pass) } else STEP_FAST(2) } \
-      __syncwarp();                                                                                               \
-      iters = it + 1;                                                                                             \
-      unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));                                             \
-      if (__uint_as_float(mx) <= P.residual_threshold) break;                                                     \
-    }                                                                                                             \
-  }
-    SWEEP(true)
+    for (int it = 0; it < P.solver_iterations && C > 0; ++it) {
+      maxres = 0.0f;
+#pragma unroll 1
+      for (int k = 0; k < ncolours; ++k) {                 // normal rows
+        if (mine && mycol == k) {
+          CLOAD
+          CROW(0, bias0, 0.0f, __int_as_float(0x7f800000))
+          CSTORE
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int k = 0; k < ncolours; ++k) {                 // friction rows
+        if (mine && mycol == k) {
+          CLOAD
+          const float lim = mu * rl[0];
+          CROW(1, 0.0f, -lim, lim)
+          if (nrows > 2) CROW(2, 0.0f, -lim, lim)
+          CSTORE
+        }
+        __syncwarp();
+      }
+      iters = it + 1;
+      unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
+      if (__uint_as_float(mx) <= P.residual_threshold) break;
+    }
+#undef CROW
+#undef CLOAD
+#undef CSTORE
     PROF_SEC(2)
-#undef SWEEP
-#undef STEP_FAST
-#undef STEP_SLOW
-    if (dyn) {
-      float* wb = S.body + lane * BODY_STRIDE;
-      ST3(wb + BO_VEL, vel); ST3(wb + BO_ANG, ang);
-    }
-    __syncwarp();
     if (act) {
       float* p = W.man_pts + ((nbase + (mk >> 2)) * 4 + (mk & 3)) * B2S_CP_FLOATS;
-      p[10] = lam[lane]; p[11] = lam[32 + lane]; p[12] = lam[64 + lane];
+      p[10] = rl[0]; p[11] = rl[1]; p[12] = rl[2];
     }
   }
   if (lane == 0) {
