@@ -134,7 +134,12 @@ typedef struct B2SParams {
   /* camera (bullet_camera.py:17-19) */
   float cam_near, cam_far;
   float crop_min[3], crop_max[3];  /* world frame, metres */
-  float reserved_f[2];
+  /* torsional friction of the movables (tools/templates/urdf_template.xml:12-14: rolling 0.001, spinning 0.001 in every
+   * generated URDF; Body.set_dynamics forwards `rolling_friction` as the spinning value too, body.py:225-230).  Per contact
+   * point of a movable: one spinning row about the normal and two rolling rows about the tangents, angular only, limited
+   * to mu_c * min(normal impulse, 1) with mu_c = roll_A * friction_B + roll_B * friction_A (statics and arm links: 0).
+   * rolling_friction == 0 switches the three rows off (as Bullet does).  Needs friction_dirs == 2. */
+  float rolling_friction, spinning_friction;
 } B2SParams;
 
 /* Scene description: host pointers, copied to the device by b2s_load_scene.

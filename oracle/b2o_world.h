@@ -87,6 +87,9 @@ struct ContactRow {
 struct Contact {
   int slotA, slotB; float mu;
   ContactRow row[3];
+  /* torsional rows (spinning about row[0].dir, rolling about row[1].dir and row[2].dir; angular only, no warm start):
+     I^-1 axis of both bodies, 1/d, impulse; mu_t[0] = combined spinning, mu_t[1] = combined rolling coefficient */
+  V3 tiA[3], tiB[3]; float tinv_d[3], tl[3]; float mu_t[2]; int tors;
   int manifold, point; int colour;
 };
 

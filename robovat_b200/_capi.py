@@ -63,7 +63,7 @@ class B2SParams(C.Structure):
         ('gripper_safe_height', f32), ('offstage_positions', f32 * NUM_JOINTS),
         ('min_delta_position', f32), ('min_delta_angle', f32),
         ('table_workspace_low', f32 * 2), ('table_workspace_high', f32 * 2),
-        ('cam_near', f32), ('cam_far', f32), ('crop_min', f32 * 3), ('crop_max', f32 * 3), ('reserved_f', f32 * 2),
+        ('cam_near', f32), ('cam_far', f32), ('crop_min', f32 * 3), ('crop_max', f32 * 3), ('rolling_friction', f32), ('spinning_friction', f32),
     ]
 
 

