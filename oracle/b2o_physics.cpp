@@ -627,6 +627,7 @@ void substep(World& w, int e) {
         row.dir = dir;
         row.angA = cross(rA, dir); row.angB = cross(rB, dir);
         row.iangA = mmul(bA.inv_inertia, row.angA); row.iangB = mmul(bB.inv_inertia, row.angB);
+        row.dirMA = dir * bA.inv_mass; row.dirMB = dir * bB.inv_mass;
         float d = ((bA.inv_mass + bB.inv_mass) + dot(row.iangA, row.angA)) + dot(row.iangB, row.angB);
         row.inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
         row.d = d;
@@ -679,16 +680,22 @@ void substep(World& w, int e) {
   std::vector<int> order;
   for (int k = 0; k < ncolours; ++k) for (int i = 0; i < C; ++i) if (con[i].colour == k) order.push_back(i);
 
+  /* A row update is a chain of dependent operations, and a 50-iteration solve is a chain of row updates: the arithmetic
+     is arranged so that the chain is short (the constant terms and the mass scaling are folded into per-row constants,
+     the clamp acts on the increment).  impulse increment = ((bias + J_B u_B) - J_A u_A) / d, clamped so that the
+     accumulated impulse stays inside [lo, hi]. */
   auto apply = [&](Contact& c, const ContactRow& row, float dl) {
     BodyX& bA = body[c.slotA];
     BodyX& bB = body[c.slotB];
-    if (bA.type == TYPE_DYNAMIC) { bA.vel = vmad(bA.vel, row.dir, bA.inv_mass * dl); bA.ang = vmad(bA.ang, row.iangA, dl); }
-    if (bB.type == TYPE_DYNAMIC) { bB.vel = vmad(bB.vel, row.dir, -(bB.inv_mass * dl)); bB.ang = vmad(bB.ang, row.iangB, -dl); }
+    if (bA.type == TYPE_DYNAMIC) { bA.vel = vmad(bA.vel, row.dirMA, dl); bA.ang = vmad(bA.ang, row.iangA, dl); }
+    if (bB.type == TYPE_DYNAMIC) { bB.vel = vmad(bB.vel, row.dirMB, -dl); bB.ang = vmad(bB.ang, row.iangB, -dl); }
   };
-  auto jv = [&](const Contact& c, const ContactRow& row) {
+  auto rel = [&](const Contact& c, const ContactRow& row, float bias) {
     const BodyX& bA = body[c.slotA];
     const BodyX& bB = body[c.slotB];
-    return ((dot(row.dir, bA.vel) + dot(row.angA, bA.ang)) - dot(row.dir, bB.vel)) - dot(row.angB, bB.ang);
+    const float a = dot(row.dir, bA.vel) + dot(row.angA, bA.ang);
+    const float kb = dot(row.dir, bB.vel) + dot(row.angB, bB.ang);
+    return (bias + kb) - a;
   };
   /* warm start */
   for (int oi = 0; oi < (int)order.size(); ++oi) {
@@ -702,10 +709,9 @@ void substep(World& w, int e) {
     for (int oi = 0; oi < (int)order.size(); ++oi) {
       Contact& c = con[order[oi]];
       ContactRow& row = c.row[0];
-      float dl = (row.bias - jv(c, row)) * row.inv_d;
-      float nl = fmaxf(0.0f, row.lambda + dl);
-      dl = nl - row.lambda;
-      row.lambda = nl;
+      float dl = rel(c, row, row.bias) * row.inv_d;
+      dl = fmaxf(0.0f - row.lambda, dl);
+      row.lambda = row.lambda + dl;
       apply(c, row, dl);
       float res = dl * row.d;
       maxres = fmaxf(maxres, res * res);
@@ -715,10 +721,9 @@ void substep(World& w, int e) {
       float lim = c.mu * c.row[0].lambda;
       for (int r = 1; r < nrows; ++r) {
         ContactRow& row = c.row[r];
-        float dl = (0.0f - jv(c, row)) * row.inv_d;
-        float nl = fminf(lim, fmaxf(-lim, row.lambda + dl));
-        dl = nl - row.lambda;
-        row.lambda = nl;
+        float dl = rel(c, row, 0.0f) * row.inv_d;
+        dl = fminf(lim - row.lambda, fmaxf((0.0f - lim) - row.lambda, dl));
+        row.lambda = row.lambda + dl;
         apply(c, row, dl);
         float res = dl * row.d;
         maxres = fmaxf(maxres, res * res);
@@ -741,11 +746,9 @@ void substep(World& w, int e) {
           float tlim = mu_c * tot;
           if (tlim > mu_c) tlim = mu_c;
           const V3 ax = c.row[r].dir;
-          const float jw = dot(ax, bA.ang) - dot(ax, bB.ang);
-          float dl = (0.0f - jw) * c.tinv_d[r];
-          float nl = fminf(tlim, fmaxf(-tlim, c.tl[r] + dl));
-          dl = nl - c.tl[r];
-          c.tl[r] = nl;
+          float dl = (dot(ax, bB.ang) - dot(ax, bA.ang)) * c.tinv_d[r];
+          dl = fminf(tlim - c.tl[r], fmaxf((0.0f - tlim) - c.tl[r], dl));
+          c.tl[r] = c.tl[r] + dl;
           if (bA.type == TYPE_DYNAMIC) bA.ang = vmad(bA.ang, c.tiA[r], dl);
           if (bB.type == TYPE_DYNAMIC) bB.ang = vmad(bB.ang, c.tiB[r], -dl);
         }

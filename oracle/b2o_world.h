@@ -82,6 +82,7 @@ struct BodyX {       /* per body slot, rebuilt each substep */
 
 struct ContactRow {
   V3 dir, angA, angB, iangA, iangB;
+  V3 dirMA, dirMB;                 /* dir / mass of A, of B: what a unit impulse adds to the linear velocities */
   float inv_d, d, bias, lambda;
 };
 struct Contact {

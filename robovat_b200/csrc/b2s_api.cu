@@ -322,18 +322,19 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     // its block (dynamic hand-out), so a block may own more environments than warps; otherwise one per warp
     int maxE = 4 * wpb;
     while (maxE > 1 && ((size_t)maxE * (sm.words_env + META_WORDS) + (size_t)wpb * sm.words_warp) * 4 > 220 * 1024) --maxE;
-    int E;
+    int E, whole_waves = 0;
     if (P.envs_per_block > 0) E = P.envs_per_block;
     else {
-      // fill whole waves of SMs (one block per SM): B = 4096 -> 28 per block -> 147 blocks
+      // fill whole waves of SMs (one block per SM): B = 4096 -> 27 or 28 per block -> 148 blocks
       int dev_sms = 148;
       cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, w->device);
       const int waves = (d.B + dev_sms * maxE - 1) / (dev_sms * maxE);
       E = (d.B + dev_sms * waves - 1) / (dev_sms * waves);
+      whole_waves = std::min(dev_sms * waves, d.B);
     }
     if (E < 1) E = 1;
     if (E > maxE) E = maxE;
-    d.num_blocks = (d.B + E - 1) / E;
+    d.num_blocks = std::max((d.B + E - 1) / E, whole_waves);     // both deals (b2s_aux.cu) spread the envs evenly over them
     // spare slots: the deal (k_assign_envs) gives the blocks that hold the expensive environments at most one
     // environment per warp and lets the cheap blocks take the rest
     // (B2S_EXTRA_SLOTS: tuning knob for variant builds -- more spare slots let the deal form more, smaller blocks of
@@ -363,7 +364,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
     if ((rc = dalloc(w, &d.epa_scratch, blocks * wpb * UNITS_PER_WARP * (size_t)(EPA_MAXV * 11 + EPA_MAXF * 7), 0))) return rc;
     if ((rc = dalloc(w, &d.pair_stage, blocks * (size_t)E * P.max_pairs * 68, 0))) return rc;
     if ((rc = dalloc(w, &d.env_map, blocks * (size_t)E, 0xff))) return rc;
-    if ((rc = dalloc(w, &d.row_scratch, blocks * wpb * (size_t)std::max(32 * 68, P.max_contacts * 112), 0))) return rc;
+    if ((rc = dalloc(w, &d.row_scratch, d.reg_rows ? 4 : blocks * wpb * (size_t)P.max_contacts * 124, 0))) return rc;
   }
   size_t smem = b2s_smem_bytes(d);
   if (smem > 227 * 1024) return fail(B2S_E_CAPACITY, "b2s_load_scene: %zu bytes of shared memory per block exceed 227 KB; lower warps_per_block or the capacities", smem);

@@ -268,13 +268,17 @@ __global__ void __launch_bounds__(1024) k_assign_envs_free(const __grid_constant
     W.free_target[1] = (unsigned long long)((offset + (capacity < W.B ? capacity : 0)) % W.B);
   }
   __syncthreads();
-  // few running environments (the end of a rollout): spread them over the blocks
-  const int run = min(per, max(1, (s_stepping + run_blocks - 1) / run_blocks));
+  // consecutive runs of the ranking, of equal length (+-1) over all blocks that run: block b holds the ranks
+  // [ceil(b S / nb), ceil((b + 1) S / nb)) -- 4096 environments on 148 SMs are 27 or 28 per block, and few running
+  // environments (the end of a rollout) end up one per block
+  const int S = s_stepping, nb = max(1, min(run_blocks, S));
   for (int e = threadIdx.x; e < W.B; e += blockDim.x) {
     const int rot = (e - offset + W.B) % W.B;
     if (!(rot < capacity && W.phase[e] != B2S_PHASE_IDLE)) continue;
     const int p = atomicAdd(&base[254 - min(254, (int)W.work_ema[e])], 1);
-    W.env_map[(size_t)(p / run) * E + (p % run)] = e;
+    const int b = (int)(((long long)p * nb) / S);
+    const int first = (int)(((long long)b * S + nb - 1) / nb);
+    W.env_map[(size_t)b * E + (p - first)] = e;
   }
 }
 

@@ -181,7 +181,7 @@ struct DWorld {
   int32_t* env_map;               // [blocks][E] environment stepped in a block slot (-1 none), re-dealt before every launch
   unsigned long long* prof;       // [8] stage timing counters (only written by -DB2S_PROF builds)
   float* pair_stage;              // [blocks][E][max_pairs][68] narrow-phase result of every candidate pair of the substep
-  float* row_scratch;             // [blocks][warps][32][68] solver rows of the environment a warp is solving (L1/L2 resident)
+  float* row_scratch;             // [blocks][warps][max_contacts][124] contact records of substep_post_big (large scenes only; L2 resident)
   int32_t* ro_state;              // [B][4] rollout: step of the episode, episode index, re-samples of the current reset, spare
   int32_t* num_episodes;          // [B] episodes finished by the device-side driver
   unsigned long long* free_target;   // [2] value of *substeps at which a free-running launch stops; start of the env window of the next one

@@ -1213,16 +1213,18 @@ __device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np
 // per SM on config #3, whose solve stage took 76 % of the substep.  Measured on config #3, 4096 envs x 50 substeps:
 // 470 ms -> 305 ms; the sweeps are still 60 % of the warp time there (~1 500 cycles per colour step: the records of
 // 16 warps, 580 KB, do not fit the L1 the block leaves; prefetching them three colours ahead changed nothing).)
-#define RR_B 48                          // word offset of angB/iangB in a contact record (both body-centric paths)
-#define RB_WORDS 112                     // record: rows [0,48) as in substep_post_reg, angB/iangB [48,66), lambda [66,69),
-#define RB_LAM 66                        //   the B lane's lambda [69,72), movable index of A | B << 8 | flags at 72,
-#define RB_LAMB 69                       //   torsional rows from 76: float4 (1/d of the three rows, combined spinning coeff.),
-#define RB_INFO 72                       //   float4 (axis . wB of the three rows, combined rolling coeff.; 0 = rows off),
-#define RB_TQ 76                         //   float4 impulses of the A lane, float4 impulses of the B lane, then -- only
-#define RB_TL 84                         //   read in a colour that joins two movables -- I_A^-1 axis [92,101) and
-#define RB_TLB 88                        //   I_B^-1 axis [101,110): what the partner lane applies
-#define RB_TIA 92
-#define RB_TIB 101
+#define RR_B 48                          // word offset of the B side of the rows in a contact record: per row angB, iangB,
+                                         //   dir / mass of B (9 words)
+#define RB_WORDS 124                     // record, in words: rows [0,48): row r = float4 (dir.xyz, angA.x) (angA.yz, iangA.xy)
+#define RB_LAM 76                        //   (iangA.z, 1/d, d, c = bias + dir . vB + angB . wB of a body B that is not dynamic)
+#define RB_LAMB 80                       //   (dir.xyz / mass of A, mu); B side [48,75); lambda [76,79), the B lane's lambda
+#define RB_INFO 84                       //   [80,83); movable index of A | B << 8 at 84, bias of the normal row at 85;
+#define RB_BIAS 85                       //   torsional rows from 88: float4 (1/d of the three rows, combined spinning coeff.),
+#define RB_TQ 88                         //   float4 (axis . wB of the three rows, combined rolling coeff.; 0 = rows off),
+#define RB_TL 96                         //   float4 impulses of the A lane, float4 impulses of the B lane, then -- only read
+#define RB_TLB 100                       //   in a colour that joins two movables -- I_A^-1 axis [104,113) and I_B^-1 axis
+#define RB_TIA 104                       //   [113,122): what the partner lane applies
+#define RB_TIB 113
 
 __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, int newn) {
   const WarpSmem S = carve(wib);
@@ -1286,12 +1288,13 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
         if (r >= nrows) l0 = 0.0f;
         rec[r * 4 + 0] = make_float4(dir.x, dir.y, dir.z, angA.x);
         rec[r * 4 + 1] = make_float4(angA.y, angA.z, iangA.x, iangA.y);
-        rec[r * 4 + 2] = make_float4(iangA.z, inv_d, d, dot(dir, velB));
-        rec[r * 4 + 3] = make_float4(dot(angB, angvB), imA, (r == 0) ? bias0 : mu, imB);
-        rec1[RR_B + r * 6 + 0] = angB.x; rec1[RR_B + r * 6 + 1] = angB.y; rec1[RR_B + r * 6 + 2] = angB.z;
-        rec1[RR_B + r * 6 + 3] = iangB.x; rec1[RR_B + r * 6 + 4] = iangB.y; rec1[RR_B + r * 6 + 5] = iangB.z;
+        const V3 dirMA = dir * imA, dirMB = dir * imB;
+        rec[r * 4 + 2] = make_float4(iangA.z, inv_d, d, ((r == 0) ? bias0 : 0.0f) + (dot(dir, velB) + dot(angB, angvB)));
+        rec[r * 4 + 3] = make_float4(dirMA.x, dirMA.y, dirMA.z, mu);
+        ST3(rec1 + RR_B + r * 9, angB); ST3(rec1 + RR_B + r * 9 + 3, iangB); ST3(rec1 + RR_B + r * 9 + 6, dirMB);
         rec1[RB_LAM + r] = l0; rec1[RB_LAMB + r] = l0;
       }
+      rec1[RB_BIAS] = bias0;
       {
         float mu_s = 0.0f, mu_r = 0.0f;
         if (tors_world) {
@@ -1386,11 +1389,9 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
         const V3 ax = v3(q0.x, q0.y, q0.z);                                                                       \
         const float mu_c = (r == 0) ? qd.w : qk.w;                                                                \
         const float tlim = fminf(mu_c * tot, mu_c);                                                               \
-        const float jw = dot(ax, wA) - ((CPL) ? dot(ax, wB) : tk[r]);                                             \
-        float dl = (0.0f - jw) * tinvd[r];                                                                        \
-        float nl = fminf(tlim, fmaxf(-tlim, tl[r] + dl));                                                         \
-        dl = nl - tl[r];                                                                                          \
-        tl[r] = nl;                                                                                               \
+        float dl = (((CPL) ? dot(ax, wB) : tk[r]) - dot(ax, wA)) * tinvd[r];                                      \
+        dl = fminf(tlim - tl[r], fmaxf((0.0f - tlim) - tl[r], dl));                                               \
+        tl[r] = tl[r] + dl;                                                                                       \
         const V3 mine_i = mmul(myI, ax);                                                                          \
         if (!(SIDEB)) {                                                                                           \
           wA = vmad(wA, mine_i, dl);                                                                              \
@@ -1422,36 +1423,35 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
       const float4* rec = (const float4*)rec1;                                                                    \
       float* ml = rec1 + (sideB ? RB_LAMB : RB_LAM);                                                              \
       float lim = 0.0f;                                                                                           \
-      if (PASS == 2) lim = rec[7].z * ml[0];                                                                      \
+      if (PASS == 2) lim = rec[7].w * ml[0];                                                                      \
+      const float bias = (PASS == 1) ? rec1[RB_BIAS] : 0.0f;                                                      \
       _Pragma("unroll")                                                                                           \
       for (int r = (PASS == 2) ? 1 : 0; r < ((PASS == 1) ? 1 : 3); ++r) {                                         \
         if (r >= nrows) break;                                                                                    \
         const float4 q0 = rec[r * 4], q1 = rec[r * 4 + 1], q2 = rec[r * 4 + 2], q3 = rec[r * 4 + 3];              \
         const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
-        V3 angB = v3(0, 0, 0), iangB = v3(0, 0, 0);                                                               \
-        if (cpl || sideB) { angB = LD3(rec1 + RR_B + r * 6); iangB = LD3(rec1 + RR_B + r * 6 + 3); }              \
+        const V3 dirMA = v3(q3.x, q3.y, q3.z);                                                                    \
+        V3 angB = v3(0, 0, 0), iangB = v3(0, 0, 0), dirMB = v3(0, 0, 0);                                          \
+        if (cpl || sideB) { angB = LD3(rec1 + RR_B + r * 9); iangB = LD3(rec1 + RR_B + r * 9 + 3); dirMB = LD3(rec1 + RR_B + r * 9 + 6); } \
         const float l = ml[r];                                                                                    \
         float dl = l;                                                                                             \
         if (PASS != 0) {                                                                                          \
           const V3 vA = sideB ? ov : vel, wA = sideB ? ow : ang;                                                  \
           const float a = dot(dir, vA) + dot(angA, wA);                                                           \
-          float k1 = q2.w, k2 = q3.x;                                                                             \
-          if (cpl) { k1 = dot(dir, sideB ? vel : ov); k2 = dot(angB, sideB ? ang : ow); }                         \
-          const float jv = (a - k1) - k2;                                                                         \
-          dl = (((PASS == 1) ? q3.z : 0.0f) - jv) * q2.y;                                                         \
-          float nl = l + dl;                                                                                      \
-          nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
-          dl = nl - l;                                                                                            \
-          ml[r] = nl;                                                                                             \
+          float cc = q2.w;                                                                                        \
+          if (cpl) cc = bias + (dot(dir, sideB ? vel : ov) + dot(angB, sideB ? ang : ow));                        \
+          dl = (cc - a) * q2.y;                                                                                   \
+          dl = (PASS == 1) ? fmaxf(0.0f - l, dl) : fminf(lim - l, fmaxf((0.0f - lim) - l, dl));                   \
+          ml[r] = l + dl;                                                                                         \
           const float res = dl * q2.z;                                                                            \
           maxres = fmaxf(maxres, res * res);                                                                      \
         }                                                                                                         \
         if (!sideB) {                                                                                             \
-          vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                            \
-          if (cpl) { ov = vmad(ov, dir, -(q3.w * dl)); ow = vmad(ow, iangB, -dl); }   /* what the partner does */ \
+          vel = vmad(vel, dirMA, dl); ang = vmad(ang, iangA, dl);                                                 \
+          if (cpl) { ov = vmad(ov, dirMB, -dl); ow = vmad(ow, iangB, -dl); }          /* what the partner does */ \
         } else {                                                                                                  \
-          vel = vmad(vel, dir, -(q3.w * dl)); ang = vmad(ang, iangB, -dl);                                        \
-          ov = vmad(ov, dir, q3.y * dl); ow = vmad(ow, iangA, dl);                                                \
+          vel = vmad(vel, dirMB, -dl); ang = vmad(ang, iangB, -dl);                                               \
+          ov = vmad(ov, dirMA, dl); ow = vmad(ow, iangA, dl);                                                     \
         }                                                                                                         \
       }                                                                                                           \
       if (PASS == 2 && tors_world) BIG_TORS_ROWS(sideB, cpl)                                                      \
@@ -1466,25 +1466,24 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
       const float4* rec = (const float4*)rec1;                                                                    \
       float* ml = rec1 + RB_LAM;                                                                                  \
       float lim = 0.0f;                                                                                           \
-      if (PASS == 2) lim = rec[7].z * ml[0];                                                                      \
+      if (PASS == 2) lim = rec[7].w * ml[0];                                                                      \
       _Pragma("unroll")                                                                                           \
       for (int r = (PASS == 2) ? 1 : 0; r < ((PASS == 1) ? 1 : 3); ++r) {                                         \
         if (r >= nrows) break;                                                                                    \
         const float4 q0 = rec[r * 4], q1 = rec[r * 4 + 1], q2 = rec[r * 4 + 2], q3 = rec[r * 4 + 3];              \
         const V3 dir = v3(q0.x, q0.y, q0.z), angA = v3(q0.w, q1.x, q1.y), iangA = v3(q1.z, q1.w, q2.x);           \
+        const V3 dirMA = v3(q3.x, q3.y, q3.z);                                                                    \
         const float l = ml[r];                                                                                    \
         float dl = l;                                                                                             \
         if (PASS != 0) {                                                                                          \
-          const float jv = ((dot(dir, vel) + dot(angA, ang)) - q2.w) - q3.x;                                      \
-          dl = (((PASS == 1) ? q3.z : 0.0f) - jv) * q2.y;                                                         \
-          float nl = l + dl;                                                                                      \
-          nl = (PASS == 1) ? fmaxf(0.0f, nl) : fminf(lim, fmaxf(-lim, nl));                                       \
-          dl = nl - l;                                                                                            \
-          ml[r] = nl;                                                                                             \
+          const float a = dot(dir, vel) + dot(angA, ang);                                                         \
+          dl = (q2.w - a) * q2.y;                                                                                 \
+          dl = (PASS == 1) ? fmaxf(0.0f - l, dl) : fminf(lim - l, fmaxf((0.0f - lim) - l, dl));                   \
+          ml[r] = l + dl;                                                                                         \
           const float res = dl * q2.z;                                                                            \
           maxres = fmaxf(maxres, res * res);                                                                      \
         }                                                                                                         \
-        vel = vmad(vel, dir, q3.y * dl); ang = vmad(ang, iangA, dl);                                              \
+        vel = vmad(vel, dirMA, dl); ang = vmad(ang, iangA, dl);                                                   \
       }                                                                                                           \
       if (PASS == 2 && tors_world) { V3 ow = v3(0, 0, 0); BIG_TORS_ROWS(false, false) (void)ow; }                 \
     }                                                                                                             \
@@ -1551,25 +1550,16 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
   (void)newn;
 }
 
-// ---- body-centric solve (max_contacts <= 32 and NB <= 32) ------------------------------------------------
-// Row build and colouring run one CONTACT per lane; the Gauss-Seidel sweeps run one BODY per lane.
-// The sweep of one environment is a chain of dependent row updates (12 per body and iteration for a body
-// resting on four points) and 5% of the env-substeps run all 50 iterations, so its latency -- not its
-// throughput -- sets the length of the block's solve stage.  With the velocity of a body in the registers of
-// "its" lane (lane = body slot) a row update is two dot products, a clamp and two fused multiply-adds on
-// registers: no shared-memory round trip of the velocities, no warp barrier between colours.  The rows are
-// immutable during the sweeps; the contact lanes park them in a per-warp record array in global memory
-// (256 B per contact, read back as 128-bit loads that hit L1 after the warm start), lambda lives in shared
-// memory.  Order of operations per body = colour order = the oracle's order, and every row update performs
-// the oracle's IEEE operations, so results stay bit-identical.
-// A contact between two dynamic bodies is processed by both lanes in the same colour step: they exchange
-// their velocities with shuffles, compute the same impulse and each applies its own side.
-// record of one contact, in float4 units: row r at [4r .. 4r+3] =
-//   (dir.xyz, angA.x) (angA.yz, iangA.xy) (iangA.z, 1/d, d, k1) (k2, imA, bias0 | mu, imB)
-// then, as scalars from word 48, angB.xyz iangB.xyz of every row (only read for a dynamic body B)
-#define RR_WORDS 68                     // per contact (272 B, 16-byte aligned)
+// ---- register-resident solve (max_contacts <= 32 and NB <= 32) -------------------------------------------
+// Row build, colouring AND the Gauss-Seidel sweeps run one CONTACT per lane: the rows of a contact never leave the
+// registers they were built in.  The sweep of one environment is a chain of dependent row updates (12 per body and
+// iteration for a body resting on four points, 24 with the torsional rows) and 5% of the env-substeps run all 50
+// iterations, so its latency -- not its throughput -- sets the length of the block's solve stage: a row update is two
+// dot products, a subtraction, a multiplication, the clamp of the increment and one fused multiply-add on registers
+// (the constant terms, the mass scaling and the bounds are folded into per-row values off the chain).  Order of
+// operations per body = colour order = the oracle's order, and every row update performs the oracle's IEEE operations
+// on the same operands, so results stay bit-identical.
 #define SOLVE_T_WORDS 512               // byte table [64 colours][32 slots] in the warp's `con` scratch
-#define SOLVE_LAM (SOLVE_T_WORDS)       // float lambda [3][32], the B lane's copy of it [3][32], slotA [32], slotB [32]
 
 __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, int newn) {
   const WarpSmem S = carve(wib);
@@ -1581,17 +1571,15 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   const size_t nbase = ((size_t)par * W.B + e) * P.max_manifolds;
   const int nrows = 1 + P.friction_dirs;
   const bool act = lane < C;
-  float* rr = W.row_scratch + ((size_t)blockIdx.x * W.P.warps_per_block + (wib >> 16)) * (32 * RR_WORDS);
   PROF_SEC0()
   unsigned char* T = (unsigned char*)S.con;
-  float* lam = S.con + SOLVE_LAM;
   int sA = 0, sB = 0, mk = 0;
   bool dA = false, dB = false;
-  // the three rows of this lane's contact (row r: dir, angA = rA x dir, iangA = I_A^-1 angA, 1/d, d, k1 = dir . vB,
-  // k2 = angB . wB) and its scalars
-  V3 rdir[3], rangA[3], riangA[3];
-  float rinvd[3], rd[3], rk1[3], rk2[3], rl[3];
-  float imA = 0.0f, imB = 0.0f, bias0 = 0.0f, mu = 0.0f;
+  // the three rows of this lane's contact (row r: dir, dirM = dir / mass of A, angA = rA x dir, iangA = I_A^-1 angA, 1/d,
+  // d, c = bias + (dir . vB + angB . wB) for a body B that is not dynamic) and its scalars
+  V3 rdir[3], rdirM[3], rangA[3], riangA[3];
+  float rinvd[3], rd[3], rc[3], rl[3];
+  float imB = 0.0f, bias0 = 0.0f, mu = 0.0f;
   V3 rangB[3], riangB[3];          // B side of the rows: only used by environments in which movables touch each other
   // torsional rows of this lane's contact (spinning about rdir[0], rolling about rdir[1] and rdir[2]; angular only, no
   // warm start, not part of the residual test: see the oracle): I_A^-1 axis, 1/d, axis . wB of a kinematic body B,
@@ -1601,8 +1589,8 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   const bool tors_world = P.rolling_friction > 0.0f;     // warp uniform; b2s_create checked friction_dirs == 2
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    rdir[r] = rangA[r] = riangA[r] = rangB[r] = riangB[r] = tiA[r] = v3(0, 0, 0);
-    rinvd[r] = rd[r] = rk1[r] = rk2[r] = rl[r] = tinvd[r] = tk[r] = tl[r] = 0.0f;
+    rdir[r] = rdirM[r] = rangA[r] = riangA[r] = rangB[r] = riangB[r] = tiA[r] = v3(0, 0, 0);
+    rinvd[r] = rd[r] = rc[r] = rl[r] = tinvd[r] = tk[r] = tl[r] = 0.0f;
   }
   __syncwarp();
   if (act) {
@@ -1664,7 +1652,8 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       float l2 = len2(lat);
       if (l2 > 1e-12f) t1 = lat * (1.0f / sqrtf(l2));
     }
-    imA = bA[BO_INVM]; imB = bB[BO_INVM];
+    const float imA = bA[BO_INVM];
+    imB = bB[BO_INVM];
     const M3 iA = ldm3(bA + BO_INVI), iB = ldm3(bB + BO_INVI);
     const float pen = p[9] + P.linear_slop;
     bias0 = (pen > 0.0f) ? -(pen / dt) : -(pen * P.erp2 / dt);
@@ -1678,8 +1667,8 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       const float inv_d = (d > 0.0f && r < nrows) ? 1.0f / d : 0.0f;
       float l0 = (r == 0 || P.friction_dirs == 2) ? p[10 + r] * P.warmstart : 0.0f;
       if (r >= nrows) l0 = 0.0f;
-      rdir[r] = dir; rangA[r] = angA; riangA[r] = iangA; rinvd[r] = inv_d; rd[r] = d;
-      rk1[r] = dot(dir, velB); rk2[r] = dot(angB, angvB); rl[r] = l0;
+      rdir[r] = dir; rdirM[r] = dir * imA; rangA[r] = angA; riangA[r] = iangA; rinvd[r] = inv_d; rd[r] = d;
+      rc[r] = ((r == 0) ? bias0 : 0.0f) + (dot(dir, velB) + dot(angB, angvB)); rl[r] = l0;
       rangB[r] = angB; riangB[r] = iangB;
     }
     if (tors_world) {
@@ -1732,18 +1721,19 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
     }
 #define KEEP(on, nv, na) { vel.x = (on) ? (nv).x : vel.x; vel.y = (on) ? (nv).y : vel.y; vel.z = (on) ? (nv).z : vel.z; \
                            ang.x = (on) ? (na).x : ang.x; ang.y = (on) ? (na).y : ang.y; ang.z = (on) ? (na).z : ang.z; }
-    // one row update on (v, w) -> (v, w), lambda and the residual in temporaries
-#define ROW(r, BIAS, LO, HI, v, w, lnew, res2)                                                                    \
+    // one row update on (v, w) -> (v, w), lambda and the residual in temporaries.  The chain from (v, w) to the new
+    // (v, w) is two dot products, a subtraction, a multiplication, the clamp of the increment and one fused
+    // multiply-add; everything else (the bounds of the increment, the new lambda, the residual) hangs off it
+#define ROW(r, LO, HI, v, w, lnew, res2)                                                                          \
       {                                                                                                           \
-        const float jv = ((dot(rdir[r], v) + dot(rangA[r], w)) - rk1[r]) - rk2[r];                                \
-        float dl = ((BIAS) - jv) * rinvd[r];                                                                      \
-        float nl = rl[r] + dl;                                                                                    \
-        nl = fminf((HI), fmaxf((LO), nl));                                                                        \
-        dl = nl - rl[r];                                                                                          \
-        lnew = nl;                                                                                                \
+        const float lo_ = (LO) - rl[r], hi_ = (HI) - rl[r];                                                       \
+        const float a_ = dot(rdir[r], v) + dot(rangA[r], w);                                                      \
+        float dl = (rc[r] - a_) * rinvd[r];                                                                       \
+        dl = fminf(hi_, fmaxf(lo_, dl));                                                                          \
+        lnew = rl[r] + dl;                                                                                        \
         const float res = dl * rd[r];                                                                             \
         res2 = res * res;                                                                                         \
-        v = vmad(v, rdir[r], imA * dl); w = vmad(w, riangA[r], dl);                                               \
+        v = vmad(v, rdirM[r], dl); w = vmad(w, riangA[r], dl);                                                    \
       }
     // warm start
 #pragma unroll 1
@@ -1753,7 +1743,7 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       V3 v = vel, w = ang;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
-        if (r < nrows) { v = vmad(v, rdir[r], imA * rl[r]); w = vmad(w, riangA[r], rl[r]); }
+        if (r < nrows) { v = vmad(v, rdirM[r], rl[r]); w = vmad(w, riangA[r], rl[r]); }
       KEEP(on, v, w)
       XCHG()
     }
@@ -1766,15 +1756,14 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
         V3 v = vel, w = ang;
         float l0n, r0;
         {
-          const float jv = ((dot(rdir[0], v) + dot(rangA[0], w)) - rk1[0]) - rk2[0];
-          float dl = (bias0 - jv) * rinvd[0];
-          float nl = rl[0] + dl;
-          nl = fmaxf(0.0f, nl);
-          dl = nl - rl[0];
-          l0n = nl;
+          const float lo_ = 0.0f - rl[0];
+          const float a_ = dot(rdir[0], v) + dot(rangA[0], w);
+          float dl = (rc[0] - a_) * rinvd[0];
+          dl = fmaxf(lo_, dl);
+          l0n = rl[0] + dl;
           const float res = dl * rd[0];
           r0 = res * res;
-          v = vmad(v, rdir[0], imA * dl); w = vmad(w, riangA[0], dl);
+          v = vmad(v, rdirM[0], dl); w = vmad(w, riangA[0], dl);
         }
         rl[0] = on ? l0n : rl[0];
         maxres = on ? fmaxf(maxres, r0) : maxres;
@@ -1788,8 +1777,8 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
         const float lim = mu * rl[0];
         V3 v = vel, w = ang;
         float l1n, r1, l2n = rl[2], r2 = 0.0f;
-        ROW(1, 0.0f, -lim, lim, v, w, l1n, r1)
-        if (nrows > 2) ROW(2, 0.0f, -lim, lim, v, w, l2n, r2)
+        ROW(1, 0.0f - lim, lim, v, w, l1n, r1)
+        if (nrows > 2) ROW(2, 0.0f - lim, lim, v, w, l2n, r2)
         rl[1] = on ? l1n : rl[1]; rl[2] = on ? l2n : rl[2];
         maxres = on ? fmaxf(fmaxf(maxres, r1), r2) : maxres;
         if (tors_world) {                                    // torsional rows of the same contact: angular velocity only
@@ -1800,11 +1789,10 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
           for (int r = 0; r < 3; ++r) {
             const float mu_c = (r == 0) ? mu_s : mu_r;
             const float tlim = fminf(mu_c * rl[0], mu_c);
-            const float jw = dot(rdir[r], wt) - tk[r];
-            float dl = (0.0f - jw) * tinvd[r];
-            float nl = fminf(tlim, fmaxf(-tlim, tl[r] + dl));
-            dl = nl - tl[r];
-            tn[r] = nl;
+            const float lo_ = (0.0f - tlim) - tl[r], hi_ = tlim - tl[r];
+            float dl = (tk[r] - dot(rdir[r], wt)) * tinvd[r];
+            dl = fminf(hi_, fmaxf(lo_, dl));
+            tn[r] = tl[r] + dl;
             wt = vmad(wt, tiA[r], dl);
           }
 #pragma unroll
@@ -1845,18 +1833,16 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
     // one row update: (va, wa) of body A, (vb, wb) of body B when it is dynamic (else its constant terms k1, k2)
 #define CROW(r, BIAS, LO, HI)                                                                                     \
       {                                                                                                           \
+        const float lo_ = (LO) - rl[r], hi_ = (HI) - rl[r];                                                       \
         const float a_ = dot(rdir[r], va) + dot(rangA[r], wa);                                                    \
-        const float k1_ = dB ? dot(rdir[r], vb) : rk1[r], k2_ = dB ? dot(rangB[r], wb) : rk2[r];                  \
-        const float jv = (a_ - k1_) - k2_;                                                                        \
-        float dl = ((BIAS) - jv) * rinvd[r];                                                                      \
-        float nl = rl[r] + dl;                                                                                    \
-        nl = fminf((HI), fmaxf((LO), nl));                                                                        \
-        dl = nl - rl[r];                                                                                          \
-        rl[r] = nl;                                                                                               \
+        const float c_ = dB ? (BIAS) + (dot(rdir[r], vb) + dot(rangB[r], wb)) : rc[r];                            \
+        float dl = (c_ - a_) * rinvd[r];                                                                          \
+        dl = fminf(hi_, fmaxf(lo_, dl));                                                                          \
+        rl[r] = rl[r] + dl;                                                                                       \
         const float res = dl * rd[r];                                                                             \
         maxres = fmaxf(maxres, res * res);                                                                        \
-        va = vmad(va, rdir[r], imA * dl); wa = vmad(wa, riangA[r], dl);                                           \
-        if (dB) { vb = vmad(vb, rdir[r], -(imB * dl)); wb = vmad(wb, riangB[r], -dl); }                           \
+        va = vmad(va, rdirM[r], dl); wa = vmad(wa, riangA[r], dl);                                                \
+        if (dB) { vb = vmad(vb, rdir[r] * imB, -dl); wb = vmad(wb, riangB[r], -dl); }                             \
       }
 #define CLOAD V3 va = LD3(vA), wa = LD3(vA + 3), vb = v3(0, 0, 0), wb = v3(0, 0, 0); if (dB) { vb = LD3(vB); wb = LD3(vB + 3); }
 #define CSTORE { ST3(vA, va); ST3(vA + 3, wa); if (dB) { ST3(vB, vb); ST3(vB + 3, wb); } }
@@ -1868,8 +1854,8 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
 #pragma unroll
         for (int r = 0; r < 3; ++r)
           if (r < nrows) {
-            va = vmad(va, rdir[r], imA * rl[r]); wa = vmad(wa, riangA[r], rl[r]);
-            if (dB) { vb = vmad(vb, rdir[r], -(imB * rl[r])); wb = vmad(wb, riangB[r], -rl[r]); }
+            va = vmad(va, rdirM[r], rl[r]); wa = vmad(wa, riangA[r], rl[r]);
+            if (dB) { vb = vmad(vb, rdir[r] * imB, -rl[r]); wb = vmad(wb, riangB[r], -rl[r]); }
           }
         CSTORE
       }
@@ -1891,8 +1877,8 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
         if (mine && mycol == k) {
           CLOAD
           const float lim = mu * rl[0];
-          CROW(1, 0.0f, -lim, lim)
-          if (nrows > 2) CROW(2, 0.0f, -lim, lim)
+          CROW(1, 0.0f, 0.0f - lim, lim)
+          if (nrows > 2) CROW(2, 0.0f, 0.0f - lim, lim)
           if (tors_world && mu_r > 0.0f && rl[0] > 0.0f) {   // torsional rows of the same contact
             M3 iB = {v3(0, 0, 0), v3(0, 0, 0), v3(0, 0, 0)};
             if (dB) iB = ldm3(S.body + sB * BODY_STRIDE + BO_INVI);
@@ -1900,11 +1886,10 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
             for (int r = 0; r < 3; ++r) {
               const float mu_c = (r == 0) ? mu_s : mu_r;
               const float tlim = fminf(mu_c * rl[0], mu_c);
-              const float jw = dot(rdir[r], wa) - (dB ? dot(rdir[r], wb) : tk[r]);
-              float dl = (0.0f - jw) * tinvd[r];
-              float nl = fminf(tlim, fmaxf(-tlim, tl[r] + dl));
-              dl = nl - tl[r];
-              tl[r] = nl;
+              const float lo_ = (0.0f - tlim) - tl[r], hi_ = tlim - tl[r];
+              float dl = ((dB ? dot(rdir[r], wb) : tk[r]) - dot(rdir[r], wa)) * tinvd[r];
+              dl = fminf(hi_, fmaxf(lo_, dl));
+              tl[r] = tl[r] + dl;
               wa = vmad(wa, tiA[r], dl);
               if (dB) wb = vmad(wb, mmul(iB, rdir[r]), -dl);
             }
