@@ -279,7 +279,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   ALLOC(ncol, B, 0); ALLOC(col_slot, B * d.Hmax, 0); ALLOC(col_hull, B * d.Hmax, 0);
   ALLOC(reset_count, B, 0); ALLOC(prev_xy, B * N * 2, 0); ALLOC(cam, B * 21, 0);
   ALLOC(ro_state, B * 4, 0); ALLOC(num_episodes, B, 0); ALLOC(async_events, B, 0); ALLOC(work_ema, B, 0);
-  ALLOC(substeps, 1, 0); ALLOC(free_target, 2, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16, 0);
+  ALLOC(substeps, 1, 0); ALLOC(free_target, 2, 0); ALLOC(unfinished, 1, 0); ALLOC(prof, 8 + 4 * 1024 + 16 + 128, 0);
   if ((rc = dalloc(w, &w->exp_keys, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_npts, B * M, 0))) return rc;
   if ((rc = dalloc(w, &w->exp_pts, B * M * 4 * B2S_CP_FLOATS, 0))) return rc;
@@ -382,7 +382,7 @@ int b2s_load_scene(B2SWorld* w, const B2SSceneDesc* s) {
   reg(B2S_ARR_SOLVER_STATS, d.solver_stats, B * 16); reg(B2S_ARR_CTRL_TIME, d.ctrl_time, B * 40);
   reg(B2S_ARR_LINK_VEL, d.link_vel, B * d.L * 24); reg(B2S_ARR_NUM_COLLIDERS, d.ncol, B * 4);
   reg(B2S_ARR_COL_SLOT, d.col_slot, B * d.Hmax * 4); reg(B2S_ARR_COL_HULL, d.col_hull, B * d.Hmax * 4);
-  reg(B2S_ARR_PROF, d.prof, (8 + 4 * 1024 + 16) * 8);
+  reg(B2S_ARR_PROF, d.prof, (8 + 4 * 1024 + 16 + 128) * 8);
   reg(B2S_ARR_NUM_EPISODES, d.num_episodes, B * 4); reg(B2S_ARR_ROLLOUT_STATE, d.ro_state, B * 4 * 4);
   w->scene_loaded = true;
   return 0;

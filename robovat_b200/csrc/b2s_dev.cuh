@@ -115,7 +115,7 @@ struct SmemLayout {
 };
 #define META_ACTIVE 0
 #define META_NP 1
-#define META_C 2
+#define META_COST 2           // solver work of the environment's previous substep: stage C hands the expensive ones out first
 #define META_NEWN 3
 #define META_SETTLE_STEPS 4
 #define META_SETTLE_STABLE 5

@@ -2180,6 +2180,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
                                                                                  const uint8_t* __restrict__ env_mask, int free_run) {
   __shared__ int s_cnt[4];    // hand-out counters of the three stages, candidate pairs of the block in this round
   __shared__ int s_stop;      // free-running launch: the launch has done its total of substeps, every block stops after its round
+  __shared__ unsigned char s_order[256];   // stage C hand-out order of the slots: most solver work in the previous substep first
 #ifdef B2S_PROF
   __shared__ int s_maxc;
   if (threadIdx.x == 0) s_maxc = 0;
@@ -2207,7 +2208,11 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
         if (mode == MODE_RAW) active = valid && n > 0;
         else if (mode == MODE_ENV) active = valid && n > 0 && W.phase[valid ? e : 0] != B2S_PHASE_IDLE;
         else active = valid && (!env_mask || env_mask[valid ? e : 0]);
-        if (lane == 0) env_meta(slot)[META_ACTIVE] = active ? 1 : 0;
+        if (lane == 0) {
+          env_meta(slot)[META_ACTIVE] = active ? 1 : 0;
+          const int32_t* st = W.solver_stats + (size_t)(valid ? e : 0) * 4;
+          env_meta(slot)[META_COST] = valid ? st[1] * st[2] * 4 + st[3] : 0;
+        }
         any |= active ? 1 : 0;
       }
     }
@@ -2225,6 +2230,19 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     if (!__syncthreads_or(any)) break;
     if (free_run && s_stop) break;
     if (threadIdx.x == 0) s_cnt[2] = 0;
+    // Stage C ends with the warp that finishes last, and an environment's solve is one warp's sequential chain: a long
+    // solve that is picked up late IS the end of the stage.  So the slots are handed out longest first, ranked by the
+    // solver work (colours x iterations) of their previous substep, which the next one resembles.
+    if (threadIdx.x < E) {
+      const int t = threadIdx.x;
+      const int my = env_meta(t)[META_ACTIVE] ? env_meta(t)[META_COST] : -1;
+      int rank = 0;
+      for (int j = 0; j < E; ++j) {
+        const int cj = env_meta(j)[META_ACTIVE] ? env_meta(j)[META_COST] : -1;
+        rank += (cj > my || (cj == my && j < t)) ? 1 : 0;
+      }
+      s_order[rank] = (unsigned char)t;
+    }
 #ifdef B2S_PROF
     long long pstart_ = prof_now();
     if (threadIdx.x == 0) { atomicAdd(W.prof + 6, 1ull); W.prof[8 + blockIdx.x * 4 + 3] += 1ull; }
@@ -2264,11 +2282,12 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     if (threadIdx.x == 0) { s_cnt[1] = 0; s_cnt[3] = 0; }
     // ---- stage C: solve, integrate, phase machine / settle bookkeeping
     for (;;) {
-      const int slot = grab_slot(&s_cnt[2], lane, wib, E, first2);
+      const int turn = grab_slot(&s_cnt[2], lane, wib, E, first2);
       first2 = false;
-      if (slot >= E) break;
+      if (turn >= E) break;
+      const int slot = s_order[turn];
       int* meta = env_meta(slot);
-      if (!meta[META_ACTIVE]) continue;
+      if (!meta[META_ACTIVE]) break;          // inactive slots rank last
 #ifdef B2S_PROF
       const long long penv_ = prof_now();
 #endif
@@ -2279,10 +2298,13 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       stage_narrow_merge(e, lane, sw, meta[META_NP], &C, &newn);
       if (W.reg_rows) substep_post_reg(e, lane, sw, C, newn);
       else substep_post_big(e, lane, sw, C, newn);
+      PROF_SEC0()
       ++done_steps;
-      if (free_run && lane == 0) {            // what the next launch's deal ranks the environments by (k_assign_envs)
+      if (lane == 0) {
         const int32_t* st = W.solver_stats + (size_t)e * 4;
-        W.work_ema[e] = 0.75f * W.work_ema[e] + 0.25f * (float)(st[1] * st[2]);
+        meta[META_COST] = st[1] * st[2] * 4 + st[3];
+        // what the next launch's deal ranks the environments by (k_assign_envs_free)
+        if (free_run) W.work_ema[e] = 0.75f * W.work_ema[e] + 0.25f * (float)(st[1] * st[2]);
       }
       bool nxt = (s + 1 < n);
       if (mode == MODE_ENV) {
@@ -2339,8 +2361,18 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       // activity of this environment in the next substep, published by the warp that just stepped it
       if (lane == 0) meta[META_ACTIVE] = nxt ? 1 : 0;
       any_next |= nxt ? 1 : 0;
+      PROF_SEC(12)
 #ifdef B2S_PROF
-      if (lane == 0) atomicMax(&s_maxc, (int)(prof_now() - penv_));
+      {
+        // histogram of the stage-C time of an environment (2 us bins) and of its start time within the stage (4 us bins)
+        const long long now2_ = prof_now();
+        if (lane == 0) {
+          atomicMax(&s_maxc, (int)(now2_ - penv_));
+          atomicAdd(W.prof + 8 + 4096 + 16 + min(63, (int)((now2_ - penv_) / 2000)), 1ull);
+          atomicAdd(W.prof + 8 + 4096 + 16 + 64 + min(31, (int)((penv_ - pstart_) / 4000)), 1ull);
+          if (turn == 0) atomicAdd(W.prof + 8 + 4096 + 16 + 96 + min(31, (int)((now2_ - penv_) / 4000)), 1ull);
+        }
+      }
 #endif
     }
 #ifdef B2S_PROF

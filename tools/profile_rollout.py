@@ -59,3 +59,8 @@ if prof[6] > 0:
     sec = prof[8 + 4096:8 + 4096 + 16]
     n = max(1.0, float(sum(x[1] for x in t)))
     print('sections, ns per env-substep (warp time): ' + ' '.join('%d:%.0f' % (i, v / n) for i, v in enumerate(sec) if v > 0))
+    if len(prof) >= 8 + 4096 + 16 + 128:
+        h = prof[8 + 4096 + 16:8 + 4096 + 16 + 128]
+        print('stage-C time of an env, 2 us bins:', h[:64].astype(int).tolist())
+        print('start of an env within stage C, 4 us bins:', h[64:96].astype(int).tolist())
+        print('stage-C time of the env handed out first, 4 us bins:', h[96:128].astype(int).tolist())
