@@ -448,7 +448,7 @@ static int env_substeps(B2SWorld* w, int n, int* unfinished_host, void* stream, 
   NEED_READY(w);
   if (n < 0) return fail(B2S_E_INVALID, "b2s_env_substeps: n < 0");
   cudaStream_t s = (cudaStream_t)stream;
-  if (free_running && n > 0) b2s_launch_substeps(w->d, 4 * n, MODE_ENV, 0, 0, 0, nullptr, s, n);
+  if (free_running && n > 0) b2s_launch_substeps(w->d, 4 * n, MODE_ENV, 0, 0, 0, nullptr, s, n, false);    // lock-step: the batch waits for its slowest environments
   else b2s_launch_substeps(w->d, n, MODE_ENV, 0, 0, 0, nullptr, s);
   int rc = check_launch(w, "env_substeps", 2);
   if (rc) return rc;

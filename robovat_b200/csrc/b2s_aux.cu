@@ -276,9 +276,13 @@ __global__ void __launch_bounds__(1024) k_assign_envs_free(const __grid_constant
     const int rot = (e - offset + W.B) % W.B;
     if (!(rot < capacity && W.phase[e] != B2S_PHASE_IDLE)) continue;
     const int p = atomicAdd(&base[254 - min(254, (int)W.work_ema[e])], 1);
+#ifdef B2S_DEAL_STRIPED
+    W.env_map[(size_t)(p % nb) * E + (p / nb)] = e;         // ranks dealt round-robin: every block gets its share of the expensive ones
+#else
     const int b = (int)(((long long)p * nb) / S);
     const int first = (int)(((long long)b * S + nb - 1) / nb);
     W.env_map[(size_t)b * E + (p - first)] = e;
+#endif
   }
 }
 

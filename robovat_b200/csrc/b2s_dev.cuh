@@ -215,9 +215,12 @@ static inline void b2s_opt_in_smem(K kernel, size_t smem, size_t* configured /* 
 
 // host launchers (defined next to their kernels)
 // free_chunk > 0 (MODE_ENV only): a free-running launch -- the blocks stop together once the launch has executed
-// free_chunk substeps per stepping environment IN TOTAL (n then only caps what one environment may take)
+// free_chunk substeps per stepping environment IN TOTAL (n then only caps what one environment may take).
+// run_ahead (free-running launches): a long solve does not hold its block, its environment sits out the block's next
+// round(s) instead (b2s_step.cu).  Right for rollouts and asynchronous stepping, where only the total counts; wrong for
+// the lock-step PushEnv.step, whose batch waits for exactly those environments.
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s,
-                         int free_chunk = 0);
+                         int free_chunk = 0, bool run_ahead = true);
 void b2s_launch_begin_episode(const DWorld& W, const uint8_t* mask, cudaStream_t s);
 size_t b2s_render_scratch_bytes(const DWorld& W);
 void b2s_launch_rollout_begin(const DWorld& W, const float* first_action, cudaStream_t s);

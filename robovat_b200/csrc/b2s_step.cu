@@ -1202,6 +1202,62 @@ __device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np
 }
 
 // ---- body-centric solve, any number of contacts (max_movables <= 32) ---------------------------------------
+// ---- a long solve does not hold its block (free-running launches) ------------------------------------------------
+// The rounds of a block are separated by three block barriers (top of the round, end of stage A, end of stage B), and a
+// Gauss-Seidel solve is one warp's sequential chain: a 50-iteration solve (5 % of the env-substeps, 80-150 us against
+// a median of 18) used to be the end of its round, with the other 15 warps waiting at the barrier.  In a free-running
+// launch nobody needs that environment's result: which environment gets how many substeps depends on the schedule
+// anyway.  So a warp whose solve has run B2S_LONG_ITERS (20) iterations looks, after every further iteration, whether all
+// other warps are waiting at the next barrier (arrival counter in shared memory); if so it takes its environment out of
+// the hand-out (META_ACTIVE = 0), arrives at the barrier from where it stands -- a barrier counts arrivals, not program
+// counters -- and goes on solving while the block starts its next round without that environment.  When the solve is
+// done the warp finishes the environment's substep, passes the barriers that are left until the block is in a stage C
+// again, takes up stage-C work there, and the environment rejoins at the top of the following round.
+// Warp 0 never does this (thread 0 resets the hand-out counters after the barriers).  What an environment computes is
+// unchanged; only the schedule is.
+#ifndef B2S_LONG_ITERS
+#define B2S_LONG_ITERS 20
+#endif
+__shared__ int sh_arrived;   // barrier arrivals of this block since the start of the launch (free-running launches)
+__shared__ int sh_long;      // warps that are in a solve past B2S_LONG_ITERS iterations
+__shared__ int sh_stop;      // free-running launch: the launch has done its total of substeps, every block stops after its round
+
+struct BarState {
+  int g;          // block barriers this warp has passed in the round loop: g % 3 == 0 <=> the next one is a top-of-round barrier
+  int enabled;    // 1: free-running launch with run-ahead, not warp 0, not a B2S_PROF build; 0: free-running (arrivals are counted); -1: exact launch
+  int long_on;    // registered in sh_long
+  int stopped;    // passed a top-of-round barrier at which the launch ended: finish the environment, then leave
+  int slot;       // environment slot being solved (its META_ACTIVE is cleared when the warp first passes a barrier)
+  int passed;     // barriers passed inside the current solve
+};
+
+// one barrier of the round loop from wherever the warp stands; `any` is what a top-of-round barrier reduces
+__device__ __forceinline__ int bar_pass(BarState& bs, int lane, int any) {
+  if (bs.enabled >= 0 && lane == 0) atomicAdd(&sh_arrived, 1);
+  int r = 1;
+  if (bs.g % 3 == 0) r = __syncthreads_or(any); else __syncthreads();
+  bs.g += 1;
+  return r;
+}
+// called after every iteration of a solve: lets the block go on if everybody else is waiting for this warp
+__device__ __forceinline__ void long_solve_poll(BarState& bs, int lane, int it) {
+  if (it + 1 < B2S_LONG_ITERS) return;                 // (first: `bs` lives in local memory, and short solves never read it)
+  if (bs.enabled <= 0 || bs.stopped) return;
+  const int Wn = blockDim.x >> 5;
+  if (!bs.long_on) { if (lane == 0) atomicAdd(&sh_long, 1); bs.long_on = 1; __syncwarp(); }
+  const int arrived = *(volatile int*)&sh_arrived - bs.g * Wn;
+  const int lg = *(volatile int*)&sh_long;
+  if (arrived < Wn - lg) return;
+  if (!bs.passed) { if (lane == 0) env_meta(bs.slot)[META_ACTIVE] = 0; __syncwarp(); }
+  const bool top = (bs.g % 3 == 0);
+  bar_pass(bs, lane, 1);
+  bs.passed += 1;
+  if (top && *(volatile int*)&sh_stop) bs.stopped = 1;
+}
+__device__ __forceinline__ void long_solve_end(BarState& bs, int lane) {
+  if (bs.long_on) { if (lane == 0) atomicSub(&sh_long, 1); bs.long_on = 0; __syncwarp(); }
+}
+
 // Same scheme as substep_post_reg below (read its header first) for scenes that do not fit one contact per lane
 // and one body slot per lane: config #3 has 8 multi-hull movables on 18 tile bodies, ~120 contact points and ~30
 // colours per environment.  Differences: rows are built 32 contacts at a time; lane i of the sweeps is MOVABLE i
@@ -1226,7 +1282,7 @@ __device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np
 #define RB_TIA 104                       //   [113,122): what the partner lane applies
 #define RB_TIB 113
 
-__device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, int newn) {
+__device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, int newn, BarState& bs) {
   const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
   const float dt = (float)P.time_step;
@@ -1504,7 +1560,9 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
     iters = it + 1;
     unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
     if (__uint_as_float(mx) <= P.residual_threshold) break;
+    long_solve_poll(bs, lane, it);
   }
+  if (iters >= B2S_LONG_ITERS) long_solve_end(bs, lane);
 #undef BIG_PASS
 #undef BIG_TORS_ROWS
 #undef BIG_FAST
@@ -1561,7 +1619,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
 // on the same operands, so results stay bit-identical.
 #define SOLVE_T_WORDS 512               // byte table [64 colours][32 slots] in the warp's `con` scratch
 
-__device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, int newn) {
+__device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, int newn, BarState& bs) {
   const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
   const float dt = (float)P.time_step;
@@ -1805,7 +1863,9 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       iters = it + 1;
       unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
       if (__uint_as_float(mx) <= P.residual_threshold) break;
+      long_solve_poll(bs, lane, it);
     }
+    if (iters >= B2S_LONG_ITERS) long_solve_end(bs, lane);
 #undef KEEP
 #undef XCHG_SRC
 #undef ROW
@@ -1901,7 +1961,9 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       iters = it + 1;
       unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
       if (__uint_as_float(mx) <= P.residual_threshold) break;
+      long_solve_poll(bs, lane, it);
     }
+    if (iters >= B2S_LONG_ITERS) long_solve_end(bs, lane);
 #undef CROW
 #undef CLOAD
 #undef CSTORE
@@ -2178,8 +2240,7 @@ __device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_o
 // (1.15-1.25x slower: persistent stragglers become the tail of the launch), two 8-warp blocks per SM (1.2x).
 __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps,
                                                                                  const uint8_t* __restrict__ env_mask, int free_run) {
-  __shared__ int s_cnt[4];    // hand-out counters of the three stages, candidate pairs of the block in this round
-  __shared__ int s_stop;      // free-running launch: the launch has done its total of substeps, every block stops after its round
+  __shared__ int s_cnt[5];    // hand-out counters of the three stages, candidate pairs of the block in this round, active slots
   __shared__ unsigned char s_order[256];   // stage C hand-out order of the slots: most solver work in the previous substep first
 #ifdef B2S_PROF
   __shared__ int s_maxc;
@@ -2193,12 +2254,24 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
   const B2SParams& P = W.P;
   for (int slot = wib; slot < E; slot += Wn)
     if (lane < META_WORDS) env_meta(slot)[lane] = 0;
-  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; s_stop = 0; }
+  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; sh_stop = 0; sh_arrived = 0; sh_long = 0; }
   __syncthreads();
   int done_steps = 0;
   int any_next = 0;
+  BarState bs;
+  bs.g = 0; bs.long_on = 0; bs.stopped = 0; bs.slot = 0; bs.passed = 0;
+#ifdef B2S_PROF
+  bs.enabled = free_run ? 0 : -1;
+#else
+  bs.enabled = free_run ? ((free_run == 2 && wib != 0) ? 1 : 0) : -1;      // free_run: 1 = free-running, 2 = and long solves run ahead
+#endif
+  int pending_slot = -1, pending_active = 0;   // environment of a long solve: it rejoins the hand-out at the next top of a round
   for (int s = 0;; ++s) {
     int any = any_next;
+    if (pending_slot >= 0) {
+      if (lane == 0) env_meta(pending_slot)[META_ACTIVE] = pending_active;
+      pending_slot = -1;
+    }
     if (s == 0) {
       for (int slot = wib; slot < E; slot += Wn) {
         const int e = W.env_map[e0 + slot];
@@ -2225,23 +2298,33 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
     if (free_run && s > 0) {
       if (lane == 0 && done_steps) { atomicAdd(W.substeps, (unsigned long long)done_steps); }
       done_steps = 0;
-      if (threadIdx.x == 0) s_stop = (*(volatile unsigned long long*)W.substeps >= *(volatile unsigned long long*)W.free_target) ? 1 : 0;
+      if (threadIdx.x == 0) sh_stop = (*(volatile unsigned long long*)W.substeps >= *(volatile unsigned long long*)W.free_target) ? 1 : 0;
     }
-    if (!__syncthreads_or(any)) break;
-    if (free_run && s_stop) break;
+    if (!bar_pass(bs, lane, any)) break;
+    if (free_run && sh_stop) break;
     if (threadIdx.x == 0) s_cnt[2] = 0;
     // Stage C ends with the warp that finishes last, and an environment's solve is one warp's sequential chain: a long
     // solve that is picked up late IS the end of the stage.  So the slots are handed out longest first, ranked by the
     // solver work (colours x iterations) of their previous substep, which the next one resembles.
-    if (threadIdx.x < E) {
-      const int t = threadIdx.x;
-      const int my = env_meta(t)[META_ACTIVE] ? env_meta(t)[META_COST] : -1;
-      int rank = 0;
-      for (int j = 0; j < E; ++j) {
-        const int cj = env_meta(j)[META_ACTIVE] ? env_meta(j)[META_COST] : -1;
-        rank += (cj > my || (cj == my && j < t)) ? 1 : 0;
+    // (warp 0 ranks: the one warp that is never inside a long solve.  s_cnt[4] = active slots of this round: stage C hands
+    // out exactly those, it must not look at META_ACTIVE again -- the environment of a long solve is switched back on by
+    // its warp while others may still be in stage C)
+    if (wib == 0) {
+      int nact = 0;
+      for (int t0 = 0; t0 < E; t0 += 32) {
+        const int t = t0 + lane;
+        const bool valid = t < E;
+        const int act = valid ? env_meta(t)[META_ACTIVE] : 0;
+        const int my = act ? env_meta(t)[META_COST] : -1;
+        int rank = 0;
+        for (int j = 0; j < E; ++j) {
+          const int cj = env_meta(j)[META_ACTIVE] ? env_meta(j)[META_COST] : -1;
+          rank += (cj > my || (cj == my && j < t)) ? 1 : 0;
+        }
+        if (valid) s_order[rank] = (unsigned char)t;
+        nact += __popc(__ballot_sync(FULL, act != 0));
       }
-      s_order[rank] = (unsigned char)t;
+      if (lane == 0) s_cnt[4] = nact;
     }
 #ifdef B2S_PROF
     long long pstart_ = prof_now();
@@ -2259,7 +2342,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       if (lane == 0) { meta[META_NP] = np; atomicAdd(&s_cnt[3], np); }
     }
     PROF_STAGE(0)
-    __syncthreads();
+    bar_pass(bs, lane, 0);
     PROF_MARK(0)
     if (threadIdx.x == 0) s_cnt[0] = 0;
     // ---- stage B: narrow phase, one candidate pair per grab
@@ -2277,17 +2360,16 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
 #endif
     }
     PROF_STAGE(1)
-    __syncthreads();
+    bar_pass(bs, lane, 0);
     PROF_MARK(1)
     if (threadIdx.x == 0) { s_cnt[1] = 0; s_cnt[3] = 0; }
     // ---- stage C: solve, integrate, phase machine / settle bookkeeping
     for (;;) {
       const int turn = grab_slot(&s_cnt[2], lane, wib, E, first2);
       first2 = false;
-      if (turn >= E) break;
+      if (turn >= s_cnt[4]) break;            // inactive slots rank last
       const int slot = s_order[turn];
       int* meta = env_meta(slot);
-      if (!meta[META_ACTIVE]) break;          // inactive slots rank last
 #ifdef B2S_PROF
       const long long penv_ = prof_now();
 #endif
@@ -2296,8 +2378,11 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       const int ph = (mode == MODE_ENV) ? W.phase[e] : B2S_PHASE_IDLE;
       int C = 0, newn = 0;
       stage_narrow_merge(e, lane, sw, meta[META_NP], &C, &newn);
-      if (W.reg_rows) substep_post_reg(e, lane, sw, C, newn);
-      else substep_post_big(e, lane, sw, C, newn);
+      bs.slot = slot; bs.passed = 0;
+      if (W.reg_rows) substep_post_reg(e, lane, sw, C, newn, bs);
+      else substep_post_big(e, lane, sw, C, newn, bs);
+      const bool ran_ahead = bs.passed > 0;        // the block went on without this environment: bs.g says where it is now
+      if (ran_ahead) s = (bs.g - 1) / 3;
       PROF_SEC0()
       ++done_steps;
       if (lane == 0) {
@@ -2358,10 +2443,14 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
         __syncwarp();
         nxt = !fin;
       }
-      // activity of this environment in the next substep, published by the warp that just stepped it
-      if (lane == 0) meta[META_ACTIVE] = nxt ? 1 : 0;
+      // activity of this environment in the next substep, published by the warp that just stepped it (after a long
+      // solve: at the next top of a round, the environment must not appear in the middle of one)
+      if (ran_ahead) { pending_slot = slot; pending_active = nxt ? 1 : 0; }
+      else if (lane == 0) meta[META_ACTIVE] = nxt ? 1 : 0;
       any_next |= nxt ? 1 : 0;
       PROF_SEC(12)
+      if (bs.stopped) break;
+      if (ran_ahead) { while (bs.g % 3 != 0) bar_pass(bs, lane, 0); }     // sit out what is left of the block's stages A and B
 #ifdef B2S_PROF
       {
         // histogram of the stage-C time of an environment (2 us bins) and of its start time within the stage (4 us bins)
@@ -2375,6 +2464,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       }
 #endif
     }
+    if (bs.stopped) break;
 #ifdef B2S_PROF
     PROF_STAGE(2)
     __syncthreads();
@@ -2396,7 +2486,7 @@ static size_t g_smem_configured[B2S_MAX_DEVICES];
 static std::mutex g_launch_mutex;
 
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s,
-                         int free_chunk) {
+                         int free_chunk, bool run_ahead) {
   std::lock_guard<std::mutex> lock(g_launch_mutex);
   const int wpb = W.P.warps_per_block;
   const int blocks = W.num_blocks;
@@ -2424,7 +2514,7 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
   }
   const int run_blocks = b2s_launch_assign_envs(W, mode, s, free_chunk, resident);
   cudaMemcpyToSymbolAsync(g_W, &W, sizeof(DWorld), 0, cudaMemcpyHostToDevice, s);
-  k_substeps<<<run_blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, free_chunk > 0 ? 1 : 0);
+  k_substeps<<<run_blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, free_chunk > 0 ? (run_ahead ? 2 : 1) : 0);
   if (L) {
     if (!L->have) { if (cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming) == cudaSuccess) L->have = true; }
     if (L->have) { cudaEventRecord(L->done, s); L->stream = s; }
