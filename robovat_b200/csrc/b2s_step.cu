@@ -1214,7 +1214,9 @@ __device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np
 // done the warp finishes the environment's substep, passes the barriers that are left until the block is in a stage C
 // again, takes up stage-C work there, and the environment rejoins at the top of the following round.
 // Warp 0 never does this (thread 0 resets the hand-out counters after the barriers).  What an environment computes is
-// unchanged; only the schedule is.
+// unchanged; only the schedule is.  Used for large scenes (substep_post_big, k_substeps<true>: 1.12 -> 1.62 M substeps/s
+// on the crossing config); with register-resident rows it measured neutral (the deal already groups the expensive
+// environments) and its plumbing cost 1.2 %, so k_substeps<false> is the plain kernel.
 #ifndef B2S_LONG_ITERS
 #define B2S_LONG_ITERS 20
 #endif
@@ -1282,7 +1284,8 @@ __device__ __forceinline__ void long_solve_end(BarState& bs, int lane) {
 #define RB_TIA 104                       //   [113,122): what the partner lane applies
 #define RB_TIB 113
 
-__device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, int newn, BarState& bs) {
+template <bool RA>
+__device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, int newn, BarState* bsp) {
   const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
   const float dt = (float)P.time_step;
@@ -1560,9 +1563,9 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
     iters = it + 1;
     unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
     if (__uint_as_float(mx) <= P.residual_threshold) break;
-    long_solve_poll(bs, lane, it);
+    if (RA) long_solve_poll(*bsp, lane, it);
   }
-  if (iters >= B2S_LONG_ITERS) long_solve_end(bs, lane);
+  if (RA && iters >= B2S_LONG_ITERS) long_solve_end(*bsp, lane);
 #undef BIG_PASS
 #undef BIG_TORS_ROWS
 #undef BIG_FAST
@@ -1619,7 +1622,7 @@ __device__ __noinline__ void substep_post_big(int e, int lane, int wib, int C, i
 // on the same operands, so results stay bit-identical.
 #define SOLVE_T_WORDS 512               // byte table [64 colours][32 slots] in the warp's `con` scratch
 
-__device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, int newn, BarState& bs) {
+__device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, int newn) {
   const WarpSmem S = carve(wib);
   const B2SParams& P = W.P;
   const float dt = (float)P.time_step;
@@ -1863,9 +1866,7 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       iters = it + 1;
       unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
       if (__uint_as_float(mx) <= P.residual_threshold) break;
-      long_solve_poll(bs, lane, it);
     }
-    if (iters >= B2S_LONG_ITERS) long_solve_end(bs, lane);
 #undef KEEP
 #undef XCHG_SRC
 #undef ROW
@@ -1961,9 +1962,7 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
       iters = it + 1;
       unsigned mx = __reduce_max_sync(FULL, __float_as_uint(maxres));
       if (__uint_as_float(mx) <= P.residual_threshold) break;
-      long_solve_poll(bs, lane, it);
     }
-    if (iters >= B2S_LONG_ITERS) long_solve_end(bs, lane);
 #undef CROW
 #undef CLOAD
 #undef CSTORE
@@ -2238,6 +2237,9 @@ __device__ __forceinline__ int grab_pair(int* counter, int lane, int E, int* p_o
 // on 4096 envs x 100 substeps mid-push: no barriers + a ready ring of environments
 // (2.0x slower: 16 warps in 16 code regions), warps leaving the barrier protocol during long solves
 // (1.15-1.25x slower: persistent stragglers become the tail of the launch), two 8-warp blocks per SM (1.2x).
+// RA: the instantiation whose long solves run ahead (large scenes, free-running launches of rollouts / asynchronous
+// stepping).  The other one keeps the barrier state out of its way: plain barriers, nothing address-taken.
+template <bool RA>
 __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(int n, int mode, float lin, float ang, int max_steps,
                                                                                  const uint8_t* __restrict__ env_mask, int free_run) {
   __shared__ int s_cnt[5];    // hand-out counters of the three stages, candidate pairs of the block in this round, active slots
@@ -2263,8 +2265,9 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
 #ifdef B2S_PROF
   bs.enabled = free_run ? 0 : -1;
 #else
-  bs.enabled = free_run ? ((free_run == 2 && wib != 0) ? 1 : 0) : -1;      // free_run: 1 = free-running, 2 = and long solves run ahead
+  bs.enabled = free_run ? ((RA && wib != 0) ? 1 : 0) : -1;
 #endif
+  if (!RA) bs.enabled = -1;                            // nobody polls: no arrival counting either
   int pending_slot = -1, pending_active = 0;   // environment of a long solve: it rejoins the hand-out at the next top of a round
   for (int s = 0;; ++s) {
     int any = any_next;
@@ -2300,7 +2303,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       done_steps = 0;
       if (threadIdx.x == 0) sh_stop = (*(volatile unsigned long long*)W.substeps >= *(volatile unsigned long long*)W.free_target) ? 1 : 0;
     }
-    if (!bar_pass(bs, lane, any)) break;
+    if (!(RA ? bar_pass(bs, lane, any) : __syncthreads_or(any))) break;
     if (free_run && sh_stop) break;
     if (threadIdx.x == 0) s_cnt[2] = 0;
     // Stage C ends with the warp that finishes last, and an environment's solve is one warp's sequential chain: a long
@@ -2342,7 +2345,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       if (lane == 0) { meta[META_NP] = np; atomicAdd(&s_cnt[3], np); }
     }
     PROF_STAGE(0)
-    bar_pass(bs, lane, 0);
+    if (RA) bar_pass(bs, lane, 0); else __syncthreads();
     PROF_MARK(0)
     if (threadIdx.x == 0) s_cnt[0] = 0;
     // ---- stage B: narrow phase, one candidate pair per grab
@@ -2360,7 +2363,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
 #endif
     }
     PROF_STAGE(1)
-    bar_pass(bs, lane, 0);
+    if (RA) bar_pass(bs, lane, 0); else __syncthreads();
     PROF_MARK(1)
     if (threadIdx.x == 0) { s_cnt[1] = 0; s_cnt[3] = 0; }
     // ---- stage C: solve, integrate, phase machine / settle bookkeeping
@@ -2378,10 +2381,13 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       const int ph = (mode == MODE_ENV) ? W.phase[e] : B2S_PHASE_IDLE;
       int C = 0, newn = 0;
       stage_narrow_merge(e, lane, sw, meta[META_NP], &C, &newn);
-      bs.slot = slot; bs.passed = 0;
-      if (W.reg_rows) substep_post_reg(e, lane, sw, C, newn, bs);
-      else substep_post_big(e, lane, sw, C, newn, bs);
-      const bool ran_ahead = bs.passed > 0;        // the block went on without this environment: bs.g says where it is now
+      bool ran_ahead = false;                      // the block went on without this environment: bs.g says where it is now
+      if (RA) {
+        bs.slot = slot; bs.passed = 0;
+        substep_post_big<true>(e, lane, sw, C, newn, &bs);
+        ran_ahead = bs.passed > 0;
+      } else if (W.reg_rows) substep_post_reg(e, lane, sw, C, newn);
+      else substep_post_big<false>(e, lane, sw, C, newn, nullptr);
       if (ran_ahead) s = (bs.g - 1) / 3;
       PROF_SEC0()
       ++done_steps;
@@ -2449,8 +2455,8 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       else if (lane == 0) meta[META_ACTIVE] = nxt ? 1 : 0;
       any_next |= nxt ? 1 : 0;
       PROF_SEC(12)
-      if (bs.stopped) break;
-      if (ran_ahead) { while (bs.g % 3 != 0) bar_pass(bs, lane, 0); }     // sit out what is left of the block's stages A and B
+      if (RA && bs.stopped) break;
+      if (RA && ran_ahead) { while (bs.g % 3 != 0) bar_pass(bs, lane, 0); }     // sit out what is left of the block's stages A and B
 #ifdef B2S_PROF
       {
         // histogram of the stage-C time of an environment (2 us bins) and of its start time within the stage (4 us bins)
@@ -2464,7 +2470,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
       }
 #endif
     }
-    if (bs.stopped) break;
+    if (RA && bs.stopped) break;
 #ifdef B2S_PROF
     PROF_STAGE(2)
     __syncthreads();
@@ -2482,7 +2488,7 @@ __global__ void __launch_bounds__(B2S_BLOCK_THREADS, B2S_MIN_BLOCKS) k_substeps(
 // kernel that read it.  Worlds on different devices never meet (a __constant__ symbol exists once per device).
 struct DevLaunch { cudaEvent_t done; cudaStream_t stream; bool have; };
 static DevLaunch g_launch[B2S_MAX_DEVICES];
-static size_t g_smem_configured[B2S_MAX_DEVICES];
+static size_t g_smem_configured[B2S_MAX_DEVICES], g_smem_configured_ra[B2S_MAX_DEVICES];
 static std::mutex g_launch_mutex;
 
 void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang, int max_steps, const uint8_t* env_mask, cudaStream_t s,
@@ -2491,7 +2497,10 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
   const int wpb = W.P.warps_per_block;
   const int blocks = W.num_blocks;
   size_t smem = b2s_smem_bytes(W);
-  b2s_opt_in_smem(k_substeps, smem, g_smem_configured);
+  // long solves run ahead in the free-running launches of large scenes (rows in records: the solves are long and uneven);
+  // with register-resident rows it measured neutral and the plumbing cost 1.2 %
+  const bool ra = free_chunk > 0 && mode == MODE_ENV && run_ahead && !W.reg_rows;
+  if (ra) b2s_opt_in_smem(k_substeps<true>, smem, g_smem_configured_ra); else b2s_opt_in_smem(k_substeps<false>, smem, g_smem_configured);
   int dev = 0;
   cudaGetDevice(&dev);
   DevLaunch* L = (dev >= 0 && dev < B2S_MAX_DEVICES) ? &g_launch[dev] : nullptr;
@@ -2505,7 +2514,7 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
     const size_t key = smem * 64 + (size_t)wpb;
     if (g_resident_key[dev] != key) {
       int occ = 1, sms = 148;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_substeps, wpb * 32, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_substeps<false>, wpb * 32, smem);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       g_resident[dev] = (occ > 0 ? occ : 1) * (sms > 0 ? sms : 148);
       g_resident_key[dev] = key;
@@ -2514,7 +2523,8 @@ void b2s_launch_substeps(const DWorld& W, int n, int mode, float lin, float ang,
   }
   const int run_blocks = b2s_launch_assign_envs(W, mode, s, free_chunk, resident);
   cudaMemcpyToSymbolAsync(g_W, &W, sizeof(DWorld), 0, cudaMemcpyHostToDevice, s);
-  k_substeps<<<run_blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, free_chunk > 0 ? (run_ahead ? 2 : 1) : 0);
+  if (ra) k_substeps<true><<<run_blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, 2);
+  else k_substeps<false><<<run_blocks, wpb * 32, smem, s>>>(n, mode, lin, ang, max_steps, env_mask, free_chunk > 0 ? 1 : 0);
   if (L) {
     if (!L->have) { if (cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming) == cudaSuccess) L->have = true; }
     if (L->have) { cudaEventRecord(L->done, s); L->stream = s; }

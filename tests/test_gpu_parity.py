@@ -359,3 +359,23 @@ def test_full_size_batch_is_shard_and_schedule_independent():
     assert np.isfinite(b1[0]).all() and int(big.array(_capi.ARR_ERROR_FLAGS).max().item()) == 0
     assert (b1[0][2] > -0.95).all()                      # a pushed body may leave the table, nothing falls through the ground (z = -0.9)
     assert len(np.unique(b1[2])) >= 3                    # environments are spread over several phases
+
+
+@pytest.mark.parametrize('roll,spin', [(0.0, 0.001), (0.002, 0.005)])
+@pytest.mark.parametrize('big', [False, True])
+def test_torsional_friction_options_bit_exact(roll, spin, big):
+    """Rolling / spinning friction rows (B2SParams.rolling_friction / spinning_friction): rows off (rolling = 0, Bullet's
+    gate) and a spinning coefficient that differs from the rolling one, on the register-resident solve (3 convex
+    movables) and on the record-based solve of large scenes (8 concave movables): drop, impacts, rest."""
+    from robovat_b200 import config
+    phys = dict(config.DEFAULT_PUSH_ENV['PHYSICS'], ROLLING_FRICTION=roll, SPINNING_FRICTION=spin)
+    kw = dict(PHYSICS=phys)
+    if big:
+        kw.update(TASK_NAME='crossing', LAYOUT_ID=0, MOVABLE_NAME='concave', MIN_MOVABLE_BODIES=8, MAX_MOVABLE_BODIES=8)
+    cfg, gpu, cpu = helpers.make_pair(12 if big else 24, **kw)
+    assert abs(gpu.params.rolling_friction - roll) < 1e-9 and abs(gpu.params.spinning_friction - spin) < 1e-9
+    gpu.reset(seed=21); cpu.reset(seed=21)
+    for k in range(6):
+        gpu.step(60); cpu.step(60)
+        _compare_state(gpu, cpu, 'roll=%g spin=%g big=%d after %d substeps' % (roll, spin, big, 60 * (k + 1)))
+        _compare_contacts(gpu, cpu, 'roll=%g spin=%g big=%d after %d substeps' % (roll, spin, big, 60 * (k + 1)))

@@ -9,7 +9,7 @@ with tempfile.TemporaryDirectory() as d:
     sass = subprocess.run(['nvdisasm', '-c', os.path.join(d, cubin)], capture_output=True, text=True).stdout
 cur, cnt = 'k_substeps (body)', collections.Counter()
 for l in sass.split('\n'):
-    m = re.match(r'\$_Z10k_substepsiiffi\$(\w+):', l)
+    m = re.match(r'\$_Z10k_substepsILb0EEviiffi\w*\$(\w+):', l)
     if m:
         cur = m.group(1)
     if re.match(r'\s+/\*[0-9a-f]+\*/', l):
