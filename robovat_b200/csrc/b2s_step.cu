@@ -1754,11 +1754,7 @@ __device__ __noinline__ void substep_post_reg(int e, int lane, int wib, int C, i
   PROF_SEC(1)
   float maxres = 0.0f;
   int iters = 0;
-#ifdef B2S_ALWAYS_SMEM_SWEEP
-  if (false) {
-#else
   if (coupled == 0ull) {
-#endif
     // ---- the rule: no contact joins two dynamic bodies.  The sweeps stay on the CONTACT lanes: the rows never leave
     // the registers they were built in, and every lane carries a copy of the velocity of its (dynamic) body A.  In
     // colour step k the lanes whose contact has colour k update their rows -- at most one contact per body, that is
