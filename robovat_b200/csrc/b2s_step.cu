@@ -1201,7 +1201,6 @@ __device__ __noinline__ void stage_narrow_merge(int e, int lane, int wib, int np
   *newn_out = newn;
 }
 
-// ---- body-centric solve, any number of contacts (max_movables <= 32) ---------------------------------------
 // ---- a long solve does not hold its block (free-running launches) ------------------------------------------------
 // The rounds of a block are separated by three block barriers (top of the round, end of stage A, end of stage B), and a
 // Gauss-Seidel solve is one warp's sequential chain: a 50-iteration solve (5 % of the env-substeps, 80-150 us against
@@ -1254,12 +1253,14 @@ __device__ __forceinline__ void long_solve_poll(BarState& bs, int lane, int it) 
   const bool top = (bs.g % 3 == 0);
   bar_pass(bs, lane, 1);
   bs.passed += 1;
+  if (lane == 0) atomicAdd(W.prof + 8 + 4096 + 15, 1ull);     // B2S_ARR_PROF[8 + 4096 + 15]: barriers passed from inside a solve
   if (top && *(volatile int*)&sh_stop) bs.stopped = 1;
 }
 __device__ __forceinline__ void long_solve_end(BarState& bs, int lane) {
   if (bs.long_on) { if (lane == 0) atomicSub(&sh_long, 1); bs.long_on = 0; __syncwarp(); }
 }
 
+// ---- body-centric solve, any number of contacts (max_movables <= 32) ---------------------------------------
 // Same scheme as substep_post_reg below (read its header first) for scenes that do not fit one contact per lane
 // and one body slot per lane: config #3 has 8 multi-hull movables on 18 tile bodies, ~120 contact points and ~30
 // colours per environment.  Differences: rows are built 32 contacts at a time; lane i of the sweeps is MOVABLE i

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from robovat_b200 import _capi
+from robovat_b200 import _capi, config
 from robovat_b200.world import RolloutRecord
 from tests import helpers
 
@@ -378,3 +378,35 @@ def test_collect_rollouts_public_api():
         np.testing.assert_array_equal(back.actions, batches[1].actions)
     np.testing.assert_allclose(batches[1].returns, env.world.episode_return.cpu().numpy(), rtol=1e-6)
     env.close()
+
+
+@pytest.mark.parametrize('envs_per_block', [0, 6])
+def test_free_running_rollout_of_a_large_scene_long_solves_run_ahead(envs_per_block):
+    """BASELINE config #3 (crossing layout, 8 concave movables: rows in records, substep_post_big) as a free-running
+    rollout: the launches take k_substeps<true>, in which a warp whose solve is long passes the block barriers from inside
+    the solve while its block goes on without that env.  Only the schedule may differ: every env completes the oracle's
+    episodes bit for bit.  envs_per_block = 6: blocks of several envs, so that envs sit out rounds and rejoin; 0: the
+    default deal (here one or two envs per block, the other warps wait at the barrier from the start)."""
+    A, EP, B = 2, 1, 48
+    params = {'export_debug': 0}
+    if envs_per_block:
+        params['envs_per_block'] = envs_per_block
+    cfg, gpu, cpu = helpers.make_pair(B, params=params, TASK_NAME='crossing', LAYOUT_ID=0, MOVABLE_NAME='concave',
+                                      MIN_MOVABLE_BODIES=8, MAX_MOVABLE_BODIES=8,
+                                      SIM=dict(config.DEFAULT_PUSH_ENV['SIM'], TIME_STEP=1.0 / 240.0))
+    assert gpu.params.max_contacts > 32                        # the record-based solve, not the register-resident one
+    _prepare(gpu, cpu, seed=17)
+    rec = RolloutRecord(B, gpu.N, EP, A, gpu.device)
+    gpu.rollout_begin(A, EP, policy_seed=9, reset_seed=4, record=rec, policy_kind=_capi.POLICY_AIMED, free_running=True)
+    ref = cpu.rollout_begin(A, EP, policy_seed=9, reset_seed=4, policy_kind=_capi.POLICY_AIMED)
+    assert gpu.rollout_run(chunk=250, max_substeps=400000) == 0
+    while cpu.rollout_run(5000) > 0:
+        pass
+    _compare_records(rec, ref, A)
+    helpers.assert_bits_equal(gpu.body_state.cpu().numpy(), cpu.body_state, 'final body_state')
+    assert gpu.substeps_executed() == cpu.substeps_executed()
+    assert int(gpu.array(_capi.ARR_ERROR_FLAGS).cpu().numpy().max()) == 0
+    ran_ahead = int(gpu.array(_capi.ARR_PROF).cpu().numpy()[8 + 4096 + 15])
+    assert ran_ahead > 0, 'no solve passed a block barrier: the test did not exercise k_substeps<true>'
+    gpu.close()
+    cpu.close()
