@@ -291,7 +291,8 @@ int b2s_settle_masked(B2SWorld* world, const uint8_t* env_mask_dev, float lin_th
 int b2s_begin_episode(B2SWorld* world, const uint8_t* env_mask_dev, void* stream);
 
 /* Simulator.step x n for every env, phase machine untouched
- * (= ControllableBody.update + pybullet.stepSimulation; simulator.py:94-103).  THE benchmarked call. */
+ * (= ControllableBody.update + pybullet.stepSimulation; simulator.py:94-103).  The raw substep call of the parity
+ * tests; bench.py steps through b2s_rollout_run (`value`) and b2s_env_async_step_free (`e2e`). */
 int b2s_step(B2SWorld* world, int n_substeps, void* stream);
 /* the same substeps as n launches of one substep each (launch-granular profiling; results identical to b2s_step) */
 int b2s_step_staged(B2SWorld* world, int n_substeps, void* stream);
