@@ -324,4 +324,7 @@ class Scene(object):
                            if not (s['flags'] & _capi.STATIC_NO_COLLIDE))
         arm_hulls = sum(lib.asset_hull_cnt[a] for _, a, _ in arm['links'])
         self.fixed_colliders = static_hulls + arm_hulls
+        # tiles that collide are separate static bodies: a movable lying across several of them has one manifold (up to
+        # four points) with each, which is what the contact capacity has to hold (config.build_params)
+        self.colliding_tiles = sum(1 for s in statics if (s['flags'] & _capi.STATIC_IS_TILE) and not (s['flags'] & _capi.STATIC_NO_COLLIDE))
         self.max_movable_hulls = lib.max_hulls(list(movable_assets) + list(target_assets))

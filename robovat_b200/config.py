@@ -263,8 +263,13 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     p.envs_per_block = int(os.environ.get('B2S_EPB', 0))     # 0 = library default
     p.export_debug = int(os.environ.get('B2S_EXPORT_DEBUG', 0))
     p.num_goal_steps = int(cfg.NUM_GOAL_STEPS or 0)               # push_env.py:259-262
-    # <= 32 contact points keeps the solver's Jacobian rows in registers (one contact per lane)
-    p.max_contacts = max(32, 8 * movable_hulls)
+    # <= 32 contact points keeps the solver's Jacobian rows in registers (one contact per lane): enough for movables on
+    # the table (four points each + the pusher).  On colliding tiles a movable rests on up to four bodies at once
+    # (measured at rest, 3 convex movables: clearing layouts up to 50 points, 30 % of the env-substeps above 32; crossing
+    # up to 37), and a capacity that is too small drops contact points (error flag 8): such scenes get the room and with
+    # it the record-based solve.
+    per_hull = 20 if getattr(scene, 'colliding_tiles', 0) > 0 else 8
+    p.max_contacts = max(32, per_hull * movable_hulls + (4 if per_hull > 8 else 0))
     p.solver_iterations, p.friction_dirs = int(phys.SOLVER_ITERATIONS), int(phys.FRICTION_DIRS)
     p.gjk_max_iters, p.epa_max_iters, p.ik_max_iters = 32, 32, 20
     p.ik_interval, p.check_done_interval = 10, 100

@@ -188,6 +188,14 @@ class Simulator(object):
         else:
             raise RuntimeError('reset_scene: %d environments have no valid arrangement after %d re-samples'
                                % (int(bad.sum()), max_retries))
+        # capacities are part of the physics: a pair / manifold / contact / colour list that overflowed has dropped
+        # contacts (b2s.h error flags 1, 2, 8, 16).  A settled scene that already needs more than the world holds will
+        # need it during every push too: say so here, once per reset, instead of stepping wrong physics silently.
+        over = int(((w.array(_capi.ARR_ERROR_FLAGS) & (1 | 2 | 8 | 16)) != 0).sum().item())
+        if over:
+            import warnings
+            warnings.warn('reset_scene: %d of %d environments exceeded a capacity of the world (max_pairs / max_manifolds / '
+                          'max_contacts, B2SParams); contacts were dropped' % (over, w.B), RuntimeWarning)
         w.begin_episode(mask=None if mask is None else np.asarray(mask, bool))
         w.observe()
 

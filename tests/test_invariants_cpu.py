@@ -348,3 +348,24 @@ def test_spinning_friction_stops_a_frictionless_box(spin):
             w.step(24)
             np.testing.assert_allclose(w.body_state[12, :, 0], w0s, rtol=2e-2)
         w.close()
+
+
+@pytest.mark.parametrize('task,layout', [('clearing', 0), ('clearing', 2), ('crossing', 0), ('insertion', 0)])
+def test_default_capacities_hold_the_contacts_of_tiled_tasks(task, layout):
+    """Capacities are part of the physics: a contact list that overflows drops contact points (error flag 8).  On the
+    colliding tiles of the task layouts a movable rests on up to four static bodies at once (up to 50 points for three
+    convex movables on the clearing layouts), which config.build_params has to provide: no capacity flag after reset,
+    settle and 240 substeps, and the most crowded env stays below the capacity."""
+    sim = copy.deepcopy(config.DEFAULT_PUSH_ENV['SIM'])
+    sim['TIME_STEP'] = 1.0 / 240.0
+    cfg, w = helpers.make_oracle(192, threads=4, TASK_NAME=task, LAYOUT_ID=layout, SIM=sim)
+    w.reset(seed=3)
+    w.settle(0.1, 0.1, 500)
+    w.settle()
+    most = 0
+    for _ in range(12):
+        w.step(20)
+        most = max(most, int(w.array(_capi.ARR_SOLVER_STATS).reshape(-1, 4)[:, 3].max()))
+    assert int((w.array(_capi.ARR_ERROR_FLAGS) & (1 | 2 | 8 | 16)).max()) == 0
+    assert most < w.params.max_contacts, (most, w.params.max_contacts)
+    w.close()
