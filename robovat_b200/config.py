@@ -268,8 +268,11 @@ def build_params(config, scene, num_envs, env_id_offset=0, lib=None, **overrides
     # (measured at rest, 3 convex movables: clearing layouts up to 50 points, 30 % of the env-substeps above 32; crossing
     # up to 37), and a capacity that is too small drops contact points (error flag 8): such scenes get the room and with
     # it the record-based solve.
-    per_hull = 20 if getattr(scene, 'colliding_tiles', 0) > 0 else 8
-    p.max_contacts = max(32, per_hull * movable_hulls + (4 if per_hull > 8 else 0))
+    # (20 per movable BODY: the hulls of a multi-hull movable share its supports -- 8 concave movables of 3 hulls measure
+    # up to 142 points against the 192 that 8 per hull provide)
+    p.max_contacts = max(32, 8 * movable_hulls)
+    if getattr(scene, 'colliding_tiles', 0) > 0:
+        p.max_contacts = max(p.max_contacts, 20 * nmax + 4)
     p.solver_iterations, p.friction_dirs = int(phys.SOLVER_ITERATIONS), int(phys.FRICTION_DIRS)
     p.gjk_max_iters, p.epa_max_iters, p.ik_max_iters = 32, 32, 20
     p.ik_interval, p.check_done_interval = 10, 100
