@@ -25,9 +25,12 @@ for c in range(cases):
     big = rs.rand() < 0.3
     dt = [1e-3, 1.0 / 240.0][int(rs.rand() < 0.7)]
     task = [None, 'clearing', 'insertion', 'crossing'][rs.randint(4)]
-    kw = dict(SIM=dict(config.DEFAULT_PUSH_ENV['SIM'], TIME_STEP=dt), TASK_NAME=task, LAYOUT_ID=0)
+    sim = dict(config.DEFAULT_PUSH_ENV['SIM'], TIME_STEP=dt)
+    if rs.rand() < 0.3:
+        sim['WALL'] = dict(sim['WALL'], USE=True)
+    kw = dict(SIM=sim, TASK_NAME=task, LAYOUT_ID=int(rs.randint(3)) if task else 0)
     if big:
-        kw.update(TASK_NAME='crossing', MOVABLE_NAME='concave', MIN_MOVABLE_BODIES=6, MAX_MOVABLE_BODIES=8)
+        kw.update(TASK_NAME='crossing', LAYOUT_ID=int(rs.randint(3)), MOVABLE_NAME='concave', MIN_MOVABLE_BODIES=6, MAX_MOVABLE_BODIES=8)
     else:
         kw.update(MIN_MOVABLE_BODIES=int(rs.randint(1, 4)), MAX_MOVABLE_BODIES=3)
     phys = dict(config.DEFAULT_PUSH_ENV['PHYSICS'])
@@ -55,8 +58,8 @@ for c in range(cases):
         pass
     torch.cuda.synchronize()
     g = {k: v.cpu().numpy() for k, v in rec.tensors().items()}
-    what = 'case %d: %s B=%d dt=%.4g task=%s A=%d EP=%d free=%d policy=%d epb=%s roll=%g' % (
-        c, 'big' if big else 'small', B, dt, kw['TASK_NAME'], A, EP, free, policy, params.get('envs_per_block'), phys['ROLLING_FRICTION'])
+    what = 'case %d: %s B=%d dt=%.4g task=%s/%d wall=%d A=%d EP=%d free=%d policy=%d epb=%s roll=%g' % (
+        c, 'big' if big else 'small', B, dt, kw['TASK_NAME'], kw['LAYOUT_ID'], int(sim['WALL']['USE']), A, EP, free, policy, params.get('envs_per_block'), phys['ROLLING_FRICTION'])
     try:
         assert left == 0, 'rollout not finished (%d envs left)' % left
         for k in ('lengths', 'flags', 'substeps'):
