@@ -17,6 +17,8 @@ A = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 free = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 kind = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 cfg = bench.bench_config(envs)
+if os.environ.get('B2S_TASK'):                      # e.g. B2S_TASK=clearing: the task layouts (colliding tiles) with 3 convex movables
+    cfg.TASK_NAME, cfg.LAYOUT_ID = os.environ['B2S_TASK'], int(os.environ.get('B2S_LAYOUT', 0))
 env = PushEnv(config=cfg, num_envs=envs, seed=0)
 env.reset()
 w = env.world
